@@ -1,0 +1,117 @@
+/* tennis_b200 — C ABI of the B200-native hot path of HaydenFaulkner/Tennis.
+ *
+ * Every entry point replaces an operator that the reference reaches through MXNet/Gluon (the reference
+ * has no FFI of its own; its "plugin boundary" is the Gluon HybridBlock API).  The citation after each
+ * declaration names the reference call site the function stands in for (paths are into the reference tree).
+ *
+ * Conventions
+ *   - plain C types only; device pointers are raw addresses the caller owns (PyTorch is only a container);
+ *   - every function returns 0 on success, a negative tn_status on failure; tn_last_error() has the text;
+ *   - all device work is enqueued asynchronously on the caller's stream (a cudaStream_t passed as void*);
+ *   - handles own only the repacked weights, are bound to one device and are not thread-safe;
+ *   - there is NO CPU fallback: on a device that is not sm_100 every call returns TN_ERR_ARCH.
+ */
+#ifndef TENNIS_B200_H_
+#define TENNIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TN_OK = 0,
+  TN_ERR_INVALID = -1,   /* bad argument */
+  TN_ERR_CUDA = -2,      /* CUDA runtime error (text in tn_last_error) */
+  TN_ERR_ARCH = -3,      /* device is not compute capability 10.x */
+  TN_ERR_WORKSPACE = -4, /* workspace too small */
+  TN_ERR_NCCL = -5
+} tn_status;
+
+enum { TN_ARCH_DENSENET121 = 0, TN_ARCH_RESNET18_V2 = 1 };
+enum { TN_FRAMES_F32_NCHW = 0, TN_FRAMES_U8_NHWC = 1 };
+enum { TN_CELL_GRU = 0, TN_CELL_LSTM = 1 };
+enum { TN_POOL_MAX = 0, TN_POOL_MEAN = 1 };
+
+typedef struct tn_backbone tn_backbone_t;
+typedef struct tn_birnn tn_birnn_t;
+typedef struct tn_gnmt tn_gnmt_t;
+typedef void* tn_stream_t; /* cudaStream_t */
+
+int tn_version(void);
+const char* tn_last_error(void); /* thread-local, valid until the next call on this thread */
+int tn_device_check(int device);  /* TN_OK iff `device` is an sm_100 part */
+
+/* ------------------------------------------------------------------ per-frame CNN backbone
+ * Replaces gluoncv.model_zoo.get_model(name).features as called at train.py:204, evaluate.py:125,
+ * train_gnmt.py:150 and wrapped at models/vision/definitions.py:22,30 (FrameModel.backbone).
+ *
+ * `params` is ONE flat host fp32 array in the order Gluon's `features.collect_params()` enumerates:
+ *   DenseNet-121: conv0.weight(64,3,7,7); bn0{gamma,beta,running_mean,running_var};
+ *                 for block in 1..4: for layer: bn1{4}, conv1.weight(128,Cin,1,1), bn2{4}, conv2.weight(32,128,3,3);
+ *                   after blocks 1..3: transition bn{4}, conv.weight(C/2,C,1,1);
+ *                 final bn{4}.
+ *   ResNet-18 v2: bn_data{4}; conv0.weight(64,3,7,7); bn0{4};
+ *                 for stage in 1..4: for block in 1..2: bn1{4}, conv1.weight(C,Cin,3,3), bn2{4}, conv2.weight(C,C,3,3),
+ *                   [downsample.weight(C,Cin,1,1) when Cin != C];
+ *                 final bn{4}.
+ */
+size_t tn_backbone_param_count(int arch);
+int tn_backbone_feature_dim(int arch, int h, int w); /* 1024 @224 / 4096 @512 (DenseNet), 512 (ResNet) */
+int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* params, size_t n_params);
+void tn_backbone_destroy(tn_backbone_t* bb);
+size_t tn_backbone_workspace_bytes(const tn_backbone_t* bb, int n_frames, int h, int w);
+/* frames: device, (n,3,h,w) fp32 NCHW already normalised (dataset.py:214-217 / train.py:142-147), or
+ *         (n,h,w,3) uint8 NHWC raw pixels (ToTensor+Normalize is then applied on the device);
+ * feats : device fp32 (n, D); feats_bf16: optional device bf16 copy (n, D) for the RNN input projection. */
+int tn_backbone_forward(tn_backbone_t* bb, const void* frames, int frames_dtype, int n_frames, int h, int w,
+                        float* feats, void* feats_bf16, void* workspace, size_t workspace_bytes, tn_stream_t stream);
+
+/* ------------------------------------------------------------------ single convolution (building block / test hook)
+ * gluon nn.Conv2D(use_bias=False) with the pre-activation BatchNorm+ReLU of the consuming layer fused in front and
+ * an optional folded BatchNorm(+ReLU) / residual behind, as DenseNet/ResNet-v2 use it ([UPSTREAM] gluoncv densenet /
+ * resnetv2 blocks); also stands in for the Debug model's Conv2D (definitions.py:121).
+ * mode: 0 = RxS conv, 1 = 1x1 conv on the 2x2-average of the activated input (DenseNet transition),
+ *       2 = 7x7 stem on a channel-padded NHWC4 image.
+ * weight: host fp32 OIHW; pro_/epi_ scale+shift: host fp32 per-channel arrays or NULL. */
+typedef struct tn_conv tn_conv_t;
+int tn_conv_create(tn_conv_t** out, int device, const float* weight, int Cout, int Cin, int R, int S, int mode,
+                   const float* pro_scale, const float* pro_shift, const float* epi_scale, const float* epi_shift);
+void tn_conv_destroy(tn_conv_t* c);
+/* x: device NHWC bf16 (n,H,W,in_cstride); out: device NHWC bf16 or fp32 (n,Ho,Wo,out_cstride) written at out_coff;
+ * residual: optional device NHWC bf16 at the output resolution. */
+int tn_conv_forward(tn_conv_t* c, const void* x, int in_cstride, int n, int H, int W, int stride, int pad, int pro_relu,
+                    int epi_relu, void* out, int out_cstride, int out_coff, int out_fp32, const void* residual,
+                    int res_cstride, tn_stream_t stream);
+/* (n,3,h,w) fp32 NCHW -> (n,h,w,4) bf16 NHWC4 (input layout of the stem). */
+int tn_frames_to_nhwc4(const float* frames, void* out_bf16, int n, int h, int w, tn_stream_t stream);
+
+/* ------------------------------------------------------------------ Dense / temporal pooling
+ * gluon nn.Dense(num_classes, flatten=True): definitions.py:25,31-32 (FrameModel.classes),
+ * :60,70-71 (TemporalPooling.classes), :101,108-109 (CNNRNN.classes).  y = x W^T + b, W is (out,in). */
+int tn_dense_forward(const float* x, const float* weight, const float* bias, float* y, int rows, int in_dim,
+                     int out_dim, tn_stream_t stream);
+/* F.max / F.mean over axis 1: definitions.py:66-69 (TemporalPooling), :107 (CNNRNN). x (B,T,D) -> y (B,D) */
+int tn_temporal_pool(const float* x, float* y, int B, int T, int D, int pool, tn_stream_t stream);
+
+/* ------------------------------------------------------------------ fused (bi)directional RNN layer
+ * Replaces mx.gluon.rnn.GRU/LSTM(hidden, layout='NTC', bidirectional=True) at definitions.py:93-96,106 and,
+ * with valid_length, cell.unroll(...) of BidirectionalCell / GRUCell / LSTMCell at gnmt.py:143-145.
+ * Host fp32 weights per direction in Gluon order: i2h_weight (G*H, D), h2h_weight (G*H, H), i2h_bias, h2h_bias
+ * (G = 3 GRU [r,z,n], 4 LSTM [i,f,g,o]); pass the reverse direction's pointers as NULL for ndir = 1. */
+int tn_birnn_create(tn_birnn_t** out, int device, int cell, int D, int H, int ndir, const float* const* i2h_weight,
+                    const float* const* h2h_weight, const float* const* i2h_bias, const float* const* h2h_bias);
+void tn_birnn_destroy(tn_birnn_t* r);
+size_t tn_birnn_workspace_bytes(const tn_birnn_t* r, int B, int T);
+/* x: device (B,T,D) fp32, or bf16 when x_is_bf16; valid_len: device int32 (B) or NULL;
+ * y (B,T,ndir*H) / ymax (B,ndir*H) / h_final, c_final (ndir,B,H): device fp32, each may be NULL. */
+int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t* valid_len, int B, int T, float* y,
+                     float* ymax, float* h_final, float* c_final, void* workspace, size_t workspace_bytes,
+                     tn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENNIS_B200_H_ */

@@ -1,0 +1,264 @@
+"""CPU oracle for the event-detector half of the hot path (TEST INFRASTRUCTURE — never imported by the product).
+
+PARITY UNPINNED: the reference (HaydenFaulkner/Tennis) ships no golden vectors and executes all arithmetic
+inside MXNet / GluonCV, which are neither vendored in /root/reference nor installable here.
+This file restates, in plain PyTorch fp32/fp64 on the CPU, the published semantics of
+
+  * gluoncv.model_zoo densenet121 / resnet18_v2 `.features`      (call sites train.py:204, evaluate.py:125)
+  * utils/layers.py:26-48                TimeDistributed ('reshape' style)
+  * models/vision/definitions.py:10-33   FrameModel
+  * models/vision/definitions.py:36-72   TemporalPooling
+  * models/vision/definitions.py:75-110  CNNRNN (mx.gluon.rnn.GRU/LSTM, layout NTC, bidirectional)
+
+following SURVEY.md Appendix A.2/A.3.  tests/ pin it against two independent implementations available in
+this image (torchvision's densenet121 graph and torch.nn.GRU/LSTM) and against committed fixtures.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+DENSE_CFG = (6, 12, 24, 16)
+GROWTH, BOTTLENECK = 32, 128
+RESNET_CH = (64, 128, 256, 512)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# parameter inventories (canonical order == Gluon's collect_params() order; see include/tennis_b200.h)
+def _bn_names(prefix):
+    return [prefix + ".gamma", prefix + ".beta", prefix + ".running_mean", prefix + ".running_var"]
+
+
+def densenet121_param_shapes():
+    shapes = [("conv0.weight", (64, 3, 7, 7))] + [(n, (64,)) for n in _bn_names("bn0")]
+    c = 64
+    for b, nl in enumerate(DENSE_CFG):
+        for l in range(nl):
+            p = "block%d.layer%d" % (b + 1, l + 1)
+            shapes += [(n, (c,)) for n in _bn_names(p + ".bn1")]
+            shapes += [(p + ".conv1.weight", (BOTTLENECK, c, 1, 1))]
+            shapes += [(n, (BOTTLENECK,)) for n in _bn_names(p + ".bn2")]
+            shapes += [(p + ".conv2.weight", (GROWTH, BOTTLENECK, 3, 3))]
+            c += GROWTH
+        if b < 3:
+            p = "trans%d" % (b + 1)
+            shapes += [(n, (c,)) for n in _bn_names(p + ".bn")]
+            shapes += [(p + ".conv.weight", (c // 2, c, 1, 1))]
+            c //= 2
+    shapes += [(n, (c,)) for n in _bn_names("bn5")]
+    return shapes
+
+
+def resnet18_v2_param_shapes():
+    shapes = [(n, (3,)) for n in _bn_names("bn_data")]
+    shapes += [("conv0.weight", (64, 3, 7, 7))] + [(n, (64,)) for n in _bn_names("bn0")]
+    cin = 64
+    for s, c in enumerate(RESNET_CH):
+        for b in range(2):
+            p = "stage%d.block%d" % (s + 1, b + 1)
+            shapes += [(n, (cin,)) for n in _bn_names(p + ".bn1")]
+            shapes += [(p + ".conv1.weight", (c, cin, 3, 3))]
+            shapes += [(n, (c,)) for n in _bn_names(p + ".bn2")]
+            shapes += [(p + ".conv2.weight", (c, c, 3, 3))]
+            if b == 0 and cin != c:
+                shapes += [(p + ".downsample.weight", (c, cin, 1, 1))]
+            cin = c
+    shapes += [(n, (512,)) for n in _bn_names("bn_final")]
+    return shapes
+
+
+PARAM_SHAPES = {"densenet121": densenet121_param_shapes, "resnet18_v2": resnet18_v2_param_shapes}
+
+
+def synthetic_params(arch, seed=1234, dtype=torch.float32):
+    """Seeded synthetic weights: He-normal convs, BN gamma~U(.5,1.5), beta~N(0,.1),
+    running_mean~N(0,.1), running_var~U(.5,1.5) so activations stay O(1) through the depth."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, shape in PARAM_SHAPES[arch]():
+        if name.endswith(".weight"):
+            fan_in = shape[1] * shape[2] * shape[3]
+            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        elif name.endswith(".gamma") or name.endswith(".running_var"):
+            t = torch.rand(shape, generator=g) + 0.5
+        else:
+            t = torch.randn(shape, generator=g) * 0.1
+        if name.startswith("bn_data") and (name.endswith(".gamma") or name.endswith(".beta")):
+            # BatchNorm(scale=False, center=False): gamma fixed to 1, beta fixed to 0 (A.2)
+            t = torch.ones(shape) if name.endswith(".gamma") else torch.zeros(shape)
+        out[name] = t.to(dtype)
+    return out
+
+
+def flatten_params(arch, params):
+    return torch.cat([params[n].reshape(-1).float() for n, _ in PARAM_SHAPES[arch]()]).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _bn(x, p, prefix):
+    # inference BatchNorm with running statistics: (x - mean) / sqrt(var + eps) * gamma + beta
+    return F.batch_norm(x, p[prefix + ".running_mean"], p[prefix + ".running_var"], p[prefix + ".gamma"],
+                        p[prefix + ".beta"], training=False, eps=BN_EPS)
+
+
+def densenet121_features(x, p):
+    """x: (N,3,H,W) -> (N, 1024*ph*pw).  [UPSTREAM gluoncv densenet] as summarised in SURVEY.md §8a V1 / A.2:
+    conv7x7/2 -> BN -> relu -> maxpool3/2/1 -> dense blocks [6,12,24,16] (BN-relu-conv1x1(128)-BN-relu-conv3x3(32),
+    concat [input, new]) with transitions BN-relu-conv1x1(C/2)-avgpool2 -> BN -> relu -> AvgPool2D(7) (stride 7,
+    'valid', i.e. NOT global) -> Flatten (channel-major)."""
+    x = F.conv2d(x, p["conv0.weight"], stride=2, padding=3)
+    x = F.relu(_bn(x, p, "bn0"))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for b, nl in enumerate(DENSE_CFG):
+        for l in range(nl):
+            pre = "block%d.layer%d" % (b + 1, l + 1)
+            y = F.conv2d(F.relu(_bn(x, p, pre + ".bn1")), p[pre + ".conv1.weight"])
+            y = F.conv2d(F.relu(_bn(y, p, pre + ".bn2")), p[pre + ".conv2.weight"], padding=1)
+            x = torch.cat([x, y], dim=1)
+        if b < 3:
+            pre = "trans%d" % (b + 1)
+            x = F.conv2d(F.relu(_bn(x, p, pre + ".bn")), p[pre + ".conv.weight"])
+            x = F.avg_pool2d(x, 2, 2)
+    x = F.relu(_bn(x, p, "bn5"))
+    x = F.avg_pool2d(x, 7)  # pool_size=7 => stride 7, floor ('valid'): 7x7 -> 1x1, 16x16 -> 2x2
+    return x.flatten(1)
+
+
+def resnet18_v2_features(x, p):
+    """[UPSTREAM gluoncv resnetv2] SURVEY.md §8a V2 / A.2."""
+    x = _bn(x, p, "bn_data")
+    x = F.conv2d(x, p["conv0.weight"], stride=2, padding=3)
+    x = F.relu(_bn(x, p, "bn0"))
+    x = F.max_pool2d(x, 3, 2, 1)
+    cin = 64
+    for s, c in enumerate(RESNET_CH):
+        for b in range(2):
+            pre = "stage%d.block%d" % (s + 1, b + 1)
+            stride = 2 if (b == 0 and s > 0) else 1
+            residual = x
+            y = F.relu(_bn(x, p, pre + ".bn1"))
+            if (pre + ".downsample.weight") in p:
+                residual = F.conv2d(y, p[pre + ".downsample.weight"], stride=stride)
+            y = F.conv2d(y, p[pre + ".conv1.weight"], stride=stride, padding=1)
+            y = F.relu(_bn(y, p, pre + ".bn2"))
+            y = F.conv2d(y, p[pre + ".conv2.weight"], padding=1)
+            x = y + residual
+            cin = c
+    x = F.relu(_bn(x, p, "bn_final"))
+    return x.mean(dim=(2, 3))  # GlobalAvgPool2D + Flatten
+
+
+FEATURES = {"densenet121": densenet121_features, "resnet18_v2": resnet18_v2_features}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def dense(x, weight, bias=None):
+    """gluon nn.Dense(flatten=True): y = x W^T + b with W (out,in)."""
+    y = x.reshape(x.shape[0], -1) @ weight.t()
+    return y if bias is None else y + bias
+
+
+def time_distributed(fn, x):
+    """utils/layers.py:38-46 ('reshape' style): fold (B,T,...) -> (B*T,...), apply, unfold to (B,T,...)."""
+    B, T = x.shape[:2]
+    y = fn(x.reshape((B * T,) + tuple(x.shape[2:])))
+    return y.reshape((B, T) + tuple(y.shape[1:]))
+
+
+def gru_cell(x, h, w_ih, w_hh, b_ih, b_hh):
+    """A.3: gates [r,z,n]; n = tanh(i2h_n + r*h2h_n); h' = (1-z)*n + z*h."""
+    H = h.shape[-1]
+    i2h = x @ w_ih.t() + b_ih
+    h2h = h @ w_hh.t() + b_hh
+    r = torch.sigmoid(i2h[:, :H] + h2h[:, :H])
+    z = torch.sigmoid(i2h[:, H:2 * H] + h2h[:, H:2 * H])
+    n = torch.tanh(i2h[:, 2 * H:] + r * h2h[:, 2 * H:])
+    return (1 - z) * n + z * h
+
+
+def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
+    """A.3: gates [i,f,g,o]."""
+    H = h.shape[-1]
+    g = x @ w_ih.t() + b_ih + h @ w_hh.t() + b_hh
+    i, f = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H])
+    gg, o = torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+    c2 = f * c + i * gg
+    return o * torch.tanh(c2), c2
+
+
+def rnn_param_shapes(cell, D, H, bidirectional=True):
+    G = 3 if cell == "gru" else 4
+    shapes = []
+    for d in (["l0", "r0"] if bidirectional else ["l0"]):
+        shapes += [(d + "_i2h_weight", (G * H, D)), (d + "_h2h_weight", (G * H, H)), (d + "_i2h_bias", (G * H,)),
+                   (d + "_h2h_bias", (G * H,))]
+    return shapes
+
+
+def synthetic_rnn_params(cell, D, H, seed=4321, bidirectional=True, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, shape in rnn_param_shapes(cell, D, H, bidirectional):
+        fan = shape[1] if len(shape) == 2 else H
+        out[name] = ((torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan)).to(dtype)
+    return out
+
+
+def birnn_layer(x, p, cell="gru", H=128):
+    """mx.gluon.rnn.GRU/LSTM(H, layout='NTC', bidirectional=True), zero initial state (A.3):
+    out[:, t] = concat(h_fwd[t], h_bwd[t])."""
+    B, T, _ = x.shape
+    outs = []
+    for d, order in (("l0", range(T)), ("r0", range(T - 1, -1, -1))):
+        if (d + "_i2h_weight") not in p:
+            continue
+        w_ih, w_hh, b_ih, b_hh = (p[d + s] for s in ("_i2h_weight", "_h2h_weight", "_i2h_bias", "_h2h_bias"))
+        h = x.new_zeros(B, H)
+        c = x.new_zeros(B, H)
+        ys = [None] * T
+        for t in order:
+            if cell == "gru":
+                h = gru_cell(x[:, t], h, w_ih, w_hh, b_ih, b_hh)
+            else:
+                h, c = lstm_cell(x[:, t], h, c, w_ih, w_hh, b_ih, b_hh)
+            ys[t] = h
+        outs.append(torch.stack(ys, dim=1))
+    return torch.cat(outs, dim=2)
+
+
+def frame_model(x, arch, p, classes_w=None, classes_b=None):
+    """definitions.py:27-33: backbone -> optional Dense."""
+    f = FEATURES[arch](x, p)
+    return f if classes_w is None else dense(f, classes_w, classes_b)
+
+
+def temporal_pooling(x, feature_fn, pool, classes_w=None, classes_b=None, feats=False):
+    """definitions.py:63-72."""
+    if not feats:
+        x = time_distributed(feature_fn, x)
+    x = x.mean(dim=1) if pool == "mean" else x.max(dim=1).values
+    return x if classes_w is None else dense(x, classes_w, classes_b)
+
+
+def cnnrnn(x, feature_fn, rnn_p, cell, H, classes_w=None, classes_b=None, feats=False):
+    """definitions.py:103-110: td -> bi-RNN -> max over time -> Dense."""
+    if not feats:
+        x = time_distributed(feature_fn, x)
+    y = birnn_layer(x, rnn_p, cell, H)
+    y = y.max(dim=1).values
+    return y if classes_w is None else dense(y, classes_w, classes_b)
+
+
+def synthetic_frames(n, size=224, seed=100):
+    """Config-1 style input: u8 pixels ~ U{0..255} -> ToTensor -> Normalize (train.py:142-147)."""
+    g = torch.Generator().manual_seed(seed)
+    u8 = torch.randint(0, 256, (n, size, size, 3), generator=g, dtype=torch.uint8)
+    return u8, normalize_u8(u8)
+
+
+def normalize_u8(u8):
+    mean = torch.tensor([0.485, 0.456, 0.406])
+    std = torch.tensor([0.229, 0.224, 0.225])
+    x = u8.float().div(255.0)
+    return ((x - mean) / std).permute(0, 3, 1, 2).contiguous()

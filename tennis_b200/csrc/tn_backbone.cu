@@ -1,0 +1,443 @@
+// Per-frame CNN feature extractor: layer plans for DenseNet-121 and ResNet-18 v2 `features`
+//  expressed as launches of the tcgen05 conv GEMM + the HBM-bound
+// helpers.  Activations live in HBM as NHWC bf16; a dense block is ONE buffer of its final channel count
+// and every dense layer writes its 32 new channels in place (concat == channel offset).
+#include <math.h>
+#include <string.h>
+
+#include <memory>
+
+#include "tn_common.h"
+#include "tn_elementwise.h"
+
+namespace {
+
+using namespace tn;
+
+struct DenseLayer {
+  BnDev bn1, bn2;
+  ConvDev conv1, conv2;
+  int cin;
+};
+struct Transition {
+  BnDev bn;
+  ConvDev conv;
+};
+struct ResBlock {
+  BnDev bn1, bn2;
+  ConvDev conv1, conv2, ds;
+  bool has_ds;
+  int cin, c, stride;
+};
+
+const int kDenseCfg[4] = {6, 12, 24, 16};
+const int kGrowth = 32, kBott = 128;
+
+}  // namespace
+
+struct tn_backbone {
+  int arch = 0, device = 0;
+  tn::DeviceArena arena;
+  // stem (both archs)
+  tn::ConvDev stem;
+  tn::BnDev bn0;
+  float in_scale[3] = {1, 1, 1}, in_shift[3] = {0, 0, 0};  // ResNet-v2 bn_data folded into the input conversion
+  // DenseNet
+  std::vector<DenseLayer> layers[4];
+  Transition trans[3];
+  // ResNet
+  std::vector<ResBlock> rblocks;
+  tn::BnDev bn_final;
+  int feat_channels = 0;
+};
+
+namespace {
+
+size_t densenet_param_count() {
+  size_t n = 64 * 3 * 49 + 4 * 64;
+  int c = 64;
+  for (int b = 0; b < 4; ++b) {
+    for (int l = 0; l < kDenseCfg[b]; ++l) {
+      n += 4 * c + static_cast<size_t>(kBott) * c + 4 * kBott + static_cast<size_t>(kGrowth) * kBott * 9;
+      c += kGrowth;
+    }
+    if (b < 3) {
+      n += 4 * c + static_cast<size_t>(c / 2) * c;
+      c /= 2;
+    }
+  }
+  n += 4 * c;
+  return n;
+}
+
+size_t resnet18_param_count() {
+  size_t n = 4 * 3 + 64 * 3 * 49 + 4 * 64;
+  int cin = 64;
+  const int ch[4] = {64, 128, 256, 512};
+  for (int s = 0; s < 4; ++s) {
+    for (int b = 0; b < 2; ++b) {
+      const int c = ch[s];
+      n += 4 * cin + static_cast<size_t>(c) * cin * 9 + 4 * c + static_cast<size_t>(c) * c * 9;
+      if (b == 0 && cin != c) n += static_cast<size_t>(c) * cin;
+      cin = c;
+    }
+  }
+  n += 4 * 512;
+  return n;
+}
+
+struct Cursor {
+  const float* p;
+  size_t left;
+  const float* take(size_t n) {
+    if (n > left) return nullptr;
+    const float* r = p;
+    p += n;
+    left -= n;
+    return r;
+  }
+};
+
+bool take_bn(Cursor& cur, DeviceArena& arena, int C, BnDev* bn, std::vector<float>* hs = nullptr,
+             std::vector<float>* hb = nullptr) {
+  const float* g = cur.take(C);
+  const float* b = cur.take(C);
+  const float* m = cur.take(C);
+  const float* v = cur.take(C);
+  if (!v) return false;
+  return make_bn(arena, g, b, m, v, C, bn, hs, hb);
+}
+bool take_conv(Cursor& cur, DeviceArena& arena, int Cout, int Cin, int R, int S, int mode, ConvDev* cv) {
+  const float* w = cur.take(static_cast<size_t>(Cout) * Cin * R * S);
+  if (!w) return false;
+  return make_conv(arena, w, Cout, Cin, R, S, mode, cv);
+}
+
+struct Dims {
+  int H0, W0, Hs, Ws, Hp, Wp;
+};
+Dims stem_dims(int h, int w) {
+  Dims d;
+  d.H0 = h;
+  d.W0 = w;
+  d.Hs = (h + 6 - 7) / 2 + 1;
+  d.Ws = (w + 6 - 7) / 2 + 1;
+  d.Hp = (d.Hs + 2 - 3) / 2 + 1;
+  d.Wp = (d.Ws + 2 - 3) / 2 + 1;
+  return d;
+}
+
+// Bump allocator over the caller's workspace (dry-run when base == nullptr).
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* get(size_t count) {
+    off = align_up(off, 1024);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+ConvGemmParams conv_params(const ConvDev& cv, const __nv_bfloat16* in, int in_cstride, int n, int H, int W, int Ho,
+                           int Wo, int stride, int pad, const BnDev* pro, void* out, int out_cstride, int out_coff,
+                           const BnDev* epi, bool epi_relu) {
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = in;
+  p.in_cstride = in_cstride;
+  p.H = H;
+  p.W = W;
+  p.Cin = cv.Cin;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.R = cv.R;
+  p.S = cv.S;
+  p.stride = stride;
+  p.pad = pad;
+  p.mode = cv.mode;
+  if (pro) {
+    p.pro_scale = pro->scale;
+    p.pro_shift = pro->shift;
+    p.pro_relu = 1;
+  }
+  p.wpack = cv.wpack;
+  p.num_chunks = cv.num_chunks;
+  p.chunks_per_tap = cv.chunks_per_tap;
+  p.out = out;
+  p.out_cstride = out_cstride;
+  p.out_coff = out_coff;
+  p.out_fp32 = 0;
+  p.Cout = cv.Cout;
+  if (epi) {
+    p.epi_scale = epi->scale;
+    p.epi_shift = epi->shift;
+  }
+  p.epi_relu = epi_relu ? 1 : 0;
+  p.M = n * Ho * Wo;
+  return p;
+}
+
+struct DensePlan {
+  Dims d;
+  int Hb[4], Wb[4], ctot[4], cin0[4];
+  int ph, pw;
+};
+bool densenet_plan(int h, int w, DensePlan* pl) {
+  pl->d = stem_dims(h, w);
+  int H = pl->d.Hp, W = pl->d.Wp, c = 64;
+  for (int b = 0; b < 4; ++b) {
+    pl->Hb[b] = H;
+    pl->Wb[b] = W;
+    pl->cin0[b] = c;
+    c += kDenseCfg[b] * kGrowth;
+    pl->ctot[b] = c;
+    if (b < 3) {
+      c /= 2;
+      H /= 2;
+      W /= 2;
+    }
+  }
+  if (H < 7 || W < 7) return false;
+  pl->ph = (H - 7) / 7 + 1;
+  pl->pw = (W - 7) / 7 + 1;
+  return true;
+}
+
+int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int w, float* feats, void* feats_bf16,
+                     Bump& ws, bool dry, cudaStream_t st) {
+  DensePlan pl;
+  if (!densenet_plan(h, w, &pl)) return set_error(TN_ERR_INVALID, "input %dx%d too small for DenseNet-121", h, w);
+  const Dims& d = pl.d;
+  __nv_bfloat16* stem = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * d.Hs * d.Ws * 64);
+  __nv_bfloat16* bott = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * pl.Hb[0] * pl.Wb[0] * kBott);
+  __nv_bfloat16* blk[4];
+  for (int b = 0; b < 4; ++b) blk[b] = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * pl.Hb[b] * pl.Wb[b] * pl.ctot[b]);
+  if (dry) return TN_OK;
+
+  // stem: conv7x7/2 -> BN -> ReLU (epilogue) ; max-pool 3/2/1 into channels [0,64) of block 1
+  {
+    ConvGemmParams p = conv_params(bb->stem, in4, 4, n, d.H0, d.W0, d.Hs, d.Ws, 2, 3, nullptr, stem, 64, 0, &bb->bn0, true);
+    TN_CUDA(launch_conv_gemm(p, st));
+    TN_CUDA(launch_maxpool3s2(stem, blk[0], n, d.Hs, d.Ws, 64, d.Hp, d.Wp, pl.ctot[0], 0, st));
+  }
+  for (int b = 0; b < 4; ++b) {
+    const int H = pl.Hb[b], W = pl.Wb[b], ct = pl.ctot[b];
+    for (const DenseLayer& L : bb->layers[b]) {
+      // BN1+ReLU (prologue) -> 1x1 conv -> BN2+ReLU (epilogue) -> bottleneck
+      ConvGemmParams p1 = conv_params(L.conv1, blk[b], ct, n, H, W, H, W, 1, 0, &L.bn1, bott, kBott, 0, &L.bn2, true);
+      TN_CUDA(launch_conv_gemm(p1, st));
+      // 3x3 conv, 32 new channels written in place at channel offset cin
+      ConvGemmParams p2 = conv_params(L.conv2, bott, kBott, n, H, W, H, W, 1, 1, nullptr, blk[b], ct, L.cin, nullptr, false);
+      TN_CUDA(launch_conv_gemm(p2, st));
+    }
+    if (b < 3) {
+      // transition: BN+ReLU -> 1x1 conv -> avgpool 2x2, computed as conv1x1(avgpool(relu(bn(x))))
+      const int Ho = pl.Hb[b + 1], Wo = pl.Wb[b + 1];
+      ConvGemmParams p = conv_params(bb->trans[b].conv, blk[b], ct, n, H, W, Ho, Wo, 2, 0, &bb->trans[b].bn, blk[b + 1],
+                                     pl.ctot[b + 1], 0, nullptr, false);
+      TN_CUDA(launch_conv_gemm(p, st));
+    }
+  }
+  TN_CUDA(launch_tail_pool(blk[3], n, pl.Hb[3], pl.Wb[3], pl.ctot[3], pl.ctot[3], 7, 7, pl.ph, pl.pw, bb->bn_final.scale,
+                           bb->bn_final.shift, feats, static_cast<__nv_bfloat16*>(feats_bf16), st));
+  return TN_OK;
+}
+
+int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int w, float* feats, void* feats_bf16,
+                   Bump& ws, bool dry, cudaStream_t st) {
+  const Dims d = stem_dims(h, w);
+  if (d.Hp < 8 || d.Wp < 8) return set_error(TN_ERR_INVALID, "input %dx%d too small for ResNet-18", h, w);
+  __nv_bfloat16* stem = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * d.Hs * d.Ws * 64);
+  const size_t act = static_cast<size_t>(n) * d.Hp * d.Wp * 64;  // largest post-pool activation
+  __nv_bfloat16* xa = ws.get<__nv_bfloat16>(act);
+  __nv_bfloat16* xb = ws.get<__nv_bfloat16>(act);
+  __nv_bfloat16* tb = ws.get<__nv_bfloat16>(act);
+  __nv_bfloat16* rb = ws.get<__nv_bfloat16>(act);
+  if (dry) return TN_OK;
+  {
+    ConvGemmParams p = conv_params(bb->stem, in4, 4, n, d.H0, d.W0, d.Hs, d.Ws, 2, 3, nullptr, stem, 64, 0, &bb->bn0, true);
+    TN_CUDA(launch_conv_gemm(p, st));
+    TN_CUDA(launch_maxpool3s2(stem, xa, n, d.Hs, d.Ws, 64, d.Hp, d.Wp, 64, 0, st));
+  }
+  int H = d.Hp, W = d.Wp;
+  __nv_bfloat16* x = xa;
+  __nv_bfloat16* y = xb;
+  for (const ResBlock& B : bb->rblocks) {
+    const int Ho = (H + 2 - 3) / B.stride + 1, Wo = (W + 2 - 3) / B.stride + 1;
+    const __nv_bfloat16* res = x;
+    int res_cs = B.cin;
+    if (B.has_ds) {  // downsample acts on relu(bn1(x)) (BasicBlockV2)
+      ConvGemmParams pd = conv_params(B.ds, x, B.cin, n, H, W, Ho, Wo, B.stride, 0, &B.bn1, rb, B.c, 0, nullptr, false);
+      TN_CUDA(launch_conv_gemm(pd, st));
+      res = rb;
+      res_cs = B.c;
+    }
+    ConvGemmParams p1 = conv_params(B.conv1, x, B.cin, n, H, W, Ho, Wo, B.stride, 1, &B.bn1, tb, B.c, 0, &B.bn2, true);
+    TN_CUDA(launch_conv_gemm(p1, st));
+    ConvGemmParams p2 = conv_params(B.conv2, tb, B.c, n, Ho, Wo, Ho, Wo, 1, 1, nullptr, y, B.c, 0, nullptr, false);
+    p2.res = res;
+    p2.res_cstride = res_cs;
+    TN_CUDA(launch_conv_gemm(p2, st));
+    __nv_bfloat16* t = x;
+    x = y;
+    y = t;
+    H = Ho;
+    W = Wo;
+  }
+  // BN -> ReLU -> GlobalAvgPool -> Flatten
+  TN_CUDA(launch_tail_pool(x, n, H, W, 512, 512, H, W, 1, 1, bb->bn_final.scale, bb->bn_final.shift, feats,
+                           static_cast<__nv_bfloat16*>(feats_bf16), st));
+  return TN_OK;
+}
+
+int backbone_run(tn_backbone* bb, const void* frames, int dtype, int n, int h, int w, float* feats, void* feats_bf16,
+                 void* workspace, bool dry, size_t* need, cudaStream_t st) {
+  Bump ws{static_cast<uint8_t*>(workspace)};
+  __nv_bfloat16* in4 = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * h * w * 4);
+  if (!dry) {
+    if (dtype == TN_FRAMES_F32_NCHW) {
+      TN_CUDA(launch_convert_nchw_f32(static_cast<const float*>(frames), in4, n, h, w, bb->in_scale, bb->in_shift, st));
+    } else if (dtype == TN_FRAMES_U8_NHWC) {
+      // ToTensor (/255) + Normalize(mean,std) (train.py:142-147), then the arch's input affine
+      const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+      float s[3], b[3];
+      for (int c = 0; c < 3; ++c) {
+        const float s1 = 1.f / (255.f * stdv[c]), b1 = -mean[c] / stdv[c];
+        s[c] = s1 * bb->in_scale[c];
+        b[c] = b1 * bb->in_scale[c] + bb->in_shift[c];
+      }
+      TN_CUDA(launch_convert_nhwc_u8(static_cast<const uint8_t*>(frames), in4, n, h, w, s, b, st));
+    } else {
+      return set_error(TN_ERR_INVALID, "unknown frames dtype %d", dtype);
+    }
+  }
+  int rc = (bb->arch == TN_ARCH_DENSENET121) ? densenet_forward(bb, in4, n, h, w, feats, feats_bf16, ws, dry, st)
+                                             : resnet_forward(bb, in4, n, h, w, feats, feats_bf16, ws, dry, st);
+  if (need) *need = align_up(ws.off, 1024);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tn_backbone_param_count(int arch) {
+  if (arch == TN_ARCH_DENSENET121) return densenet_param_count();
+  if (arch == TN_ARCH_RESNET18_V2) return resnet18_param_count();
+  return 0;
+}
+
+int tn_backbone_feature_dim(int arch, int h, int w) {
+  if (arch == TN_ARCH_RESNET18_V2) return 512;
+  if (arch == TN_ARCH_DENSENET121) {
+    DensePlan pl;
+    if (!densenet_plan(h, w, &pl)) return -1;
+    return 1024 * pl.ph * pl.pw;
+  }
+  return -1;
+}
+
+int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* params, size_t n_params) {
+  if (!out || !params) return tn::set_error(TN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = tn::check_arch(device);
+  if (rc != TN_OK) return rc;
+  if (arch != TN_ARCH_DENSENET121 && arch != TN_ARCH_RESNET18_V2) return tn::set_error(TN_ERR_INVALID, "unknown arch %d", arch);
+  if (n_params != tn_backbone_param_count(arch))
+    return tn::set_error(TN_ERR_INVALID, "expected %zu parameters for arch %d, got %zu", tn_backbone_param_count(arch), arch,
+                         n_params);
+  TN_CUDA(cudaSetDevice(device));
+  std::unique_ptr<tn_backbone> bb(new tn_backbone);
+  bb->arch = arch;
+  bb->device = device;
+  Cursor cur{params, n_params};
+  bool ok = true;
+  if (arch == TN_ARCH_DENSENET121) {
+    ok = ok && take_conv(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem);
+    ok = ok && take_bn(cur, bb->arena, 64, &bb->bn0);
+    int c = 64;
+    for (int b = 0; b < 4 && ok; ++b) {
+      for (int l = 0; l < kDenseCfg[b] && ok; ++l) {
+        DenseLayer L;
+        L.cin = c;
+        ok = ok && take_bn(cur, bb->arena, c, &L.bn1);
+        ok = ok && take_conv(cur, bb->arena, kBott, c, 1, 1, tn::kModeConv, &L.conv1);
+        ok = ok && take_bn(cur, bb->arena, kBott, &L.bn2);
+        ok = ok && take_conv(cur, bb->arena, kGrowth, kBott, 3, 3, tn::kModeConv, &L.conv2);
+        bb->layers[b].push_back(L);
+        c += kGrowth;
+      }
+      if (b < 3 && ok) {
+        ok = ok && take_bn(cur, bb->arena, c, &bb->trans[b].bn);
+        ok = ok && take_conv(cur, bb->arena, c / 2, c, 1, 1, tn::kModePool2, &bb->trans[b].conv);
+        c /= 2;
+      }
+    }
+    ok = ok && take_bn(cur, bb->arena, c, &bb->bn_final);
+    bb->feat_channels = c;
+  } else {
+    tn::BnDev bnd;
+    std::vector<float> hs, hb;
+    ok = ok && take_bn(cur, bb->arena, 3, &bnd, &hs, &hb);
+    if (ok) {
+      for (int i = 0; i < 3; ++i) {
+        bb->in_scale[i] = hs[i];
+        bb->in_shift[i] = hb[i];
+      }
+    }
+    ok = ok && take_conv(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem);
+    ok = ok && take_bn(cur, bb->arena, 64, &bb->bn0);
+    int cin = 64;
+    const int ch[4] = {64, 128, 256, 512};
+    for (int s = 0; s < 4 && ok; ++s) {
+      for (int b = 0; b < 2 && ok; ++b) {
+        ResBlock B;
+        B.cin = cin;
+        B.c = ch[s];
+        B.stride = (b == 0 && s > 0) ? 2 : 1;
+        B.has_ds = (b == 0 && cin != B.c);
+        ok = ok && take_bn(cur, bb->arena, cin, &B.bn1);
+        ok = ok && take_conv(cur, bb->arena, B.c, cin, 3, 3, tn::kModeConv, &B.conv1);
+        ok = ok && take_bn(cur, bb->arena, B.c, &B.bn2);
+        ok = ok && take_conv(cur, bb->arena, B.c, B.c, 3, 3, tn::kModeConv, &B.conv2);
+        if (B.has_ds) ok = ok && take_conv(cur, bb->arena, B.c, cin, 1, 1, tn::kModeConv, &B.ds);
+        bb->rblocks.push_back(B);
+        cin = B.c;
+      }
+    }
+    ok = ok && take_bn(cur, bb->arena, 512, &bb->bn_final);
+    bb->feat_channels = 512;
+  }
+  if (!ok) {
+    if (tn::last_error().empty()) tn::set_error(TN_ERR_INVALID, "parameter blob exhausted");
+    return TN_ERR_CUDA;
+  }
+  *out = bb.release();
+  return TN_OK;
+}
+
+void tn_backbone_destroy(tn_backbone_t* bb) { delete bb; }
+
+size_t tn_backbone_workspace_bytes(const tn_backbone_t* bb, int n_frames, int h, int w) {
+  if (!bb || n_frames < 0) return 0;
+  size_t need = 0;
+  int rc = backbone_run(const_cast<tn_backbone*>(bb), nullptr, 0, n_frames, h, w, nullptr, nullptr, nullptr, true, &need, 0);
+  return rc == TN_OK ? need : 0;
+}
+
+int tn_backbone_forward(tn_backbone_t* bb, const void* frames, int frames_dtype, int n_frames, int h, int w,
+                        float* feats, void* feats_bf16, void* workspace, size_t workspace_bytes, tn_stream_t stream) {
+  if (!bb || n_frames < 0) return tn::set_error(TN_ERR_INVALID, "bad backbone handle / frame count");
+  if (n_frames == 0) return TN_OK;
+  if (!frames || !feats || !workspace) return tn::set_error(TN_ERR_INVALID, "null device pointer");
+  const size_t need = tn_backbone_workspace_bytes(bb, n_frames, h, w);
+  if (need == 0) return TN_ERR_INVALID;
+  if (workspace_bytes < need) return tn::set_error(TN_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return tn::set_error(TN_ERR_INVALID, "workspace must be 1024-byte aligned");
+  return backbone_run(bb, frames, frames_dtype, n_frames, h, w, feats, feats_bf16, workspace, false, nullptr,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

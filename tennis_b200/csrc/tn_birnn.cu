@@ -1,0 +1,154 @@
+// C-ABI for Dense / temporal pooling / the fused (bi)RNN layer.
+#include <string.h>
+
+#include <memory>
+
+#include "tn_common.h"
+#include "tn_elementwise.h"
+#include "tn_rnn.h"
+
+struct tn_birnn {
+  int device = 0, cell = 0, gates = 3, D = 0, H = 0, ndir = 1;
+  tn::DeviceArena arena;
+  tn::ConvDev proj;          // W_ih of all directions stacked: (ndir*G*H, D)
+  const float* bih = nullptr;   // [ndir*G*H]
+  const float* WhhT = nullptr;  // [ndir][H][G*H]
+  const float* bhh = nullptr;   // [ndir*G*H]
+};
+
+extern "C" {
+
+int tn_dense_forward(const float* x, const float* weight, const float* bias, float* y, int rows, int in_dim,
+                     int out_dim, tn_stream_t stream) {
+  if (rows < 0 || in_dim <= 0 || out_dim <= 0) return tn::set_error(TN_ERR_INVALID, "bad dense shape");
+  if (rows == 0) return TN_OK;
+  if (!x || !weight || !y) return tn::set_error(TN_ERR_INVALID, "null device pointer");
+  TN_CUDA(tn::launch_dense(x, weight, bias, y, rows, in_dim, out_dim, static_cast<cudaStream_t>(stream)));
+  return TN_OK;
+}
+
+int tn_temporal_pool(const float* x, float* y, int B, int T, int D, int pool, tn_stream_t stream) {
+  if (B < 0 || T <= 0 || D <= 0) return tn::set_error(TN_ERR_INVALID, "bad pool shape");
+  if (B == 0) return TN_OK;
+  if (!x || !y) return tn::set_error(TN_ERR_INVALID, "null device pointer");
+  TN_CUDA(tn::launch_temporal_pool(x, y, B, T, D, pool == TN_POOL_MEAN ? 1 : 0, static_cast<cudaStream_t>(stream)));
+  return TN_OK;
+}
+
+int tn_birnn_create(tn_birnn_t** out, int device, int cell, int D, int H, int ndir, const float* const* i2h_weight,
+                    const float* const* h2h_weight, const float* const* i2h_bias, const float* const* h2h_bias) {
+  if (!out) return tn::set_error(TN_ERR_INVALID, "null out");
+  *out = nullptr;
+  int rc = tn::check_arch(device);
+  if (rc != TN_OK) return rc;
+  if ((cell != TN_CELL_GRU && cell != TN_CELL_LSTM) || (ndir != 1 && ndir != 2) || D <= 0 || H <= 0)
+    return tn::set_error(TN_ERR_INVALID, "bad rnn config");
+  const int G = cell == TN_CELL_GRU ? 3 : 4;
+  if (D % 16 != 0) return tn::set_error(TN_ERR_INVALID, "input width %d must be a multiple of 16", D);
+  if (H % 32 != 0 || tn::rnn_scan_cluster_size(G, H) < 0) return tn::set_error(TN_ERR_INVALID, "unsupported hidden size %d", H);
+  for (int d = 0; d < ndir; ++d)
+    if (!i2h_weight[d] || !h2h_weight[d] || !i2h_bias[d] || !h2h_bias[d]) return tn::set_error(TN_ERR_INVALID, "null weight");
+  TN_CUDA(cudaSetDevice(device));
+  std::unique_ptr<tn_birnn> r(new tn_birnn);
+  r->device = device;
+  r->cell = cell;
+  r->gates = G;
+  r->D = D;
+  r->H = H;
+  r->ndir = ndir;
+  const int GH = G * H;
+  std::vector<float> wih(static_cast<size_t>(ndir) * GH * D), bih(static_cast<size_t>(ndir) * GH),
+      bhh(static_cast<size_t>(ndir) * GH), whhT(static_cast<size_t>(ndir) * H * GH);
+  for (int d = 0; d < ndir; ++d) {
+    memcpy(&wih[static_cast<size_t>(d) * GH * D], i2h_weight[d], sizeof(float) * GH * D);
+    memcpy(&bih[static_cast<size_t>(d) * GH], i2h_bias[d], sizeof(float) * GH);
+    memcpy(&bhh[static_cast<size_t>(d) * GH], h2h_bias[d], sizeof(float) * GH);
+    for (int j = 0; j < GH; ++j)
+      for (int k = 0; k < H; ++k) whhT[(static_cast<size_t>(d) * H + k) * GH + j] = h2h_weight[d][static_cast<size_t>(j) * H + k];
+  }
+  if (!tn::make_conv(r->arena, wih.data(), ndir * GH, D, 1, 1, tn::kModeConv, &r->proj)) return TN_ERR_CUDA;
+  r->bih = static_cast<const float*>(r->arena.upload(bih.data(), bih.size() * sizeof(float)));
+  r->bhh = static_cast<const float*>(r->arena.upload(bhh.data(), bhh.size() * sizeof(float)));
+  r->WhhT = static_cast<const float*>(r->arena.upload(whhT.data(), whhT.size() * sizeof(float)));
+  if (!r->bih || !r->bhh || !r->WhhT) return TN_ERR_CUDA;
+  *out = r.release();
+  return TN_OK;
+}
+
+void tn_birnn_destroy(tn_birnn_t* r) { delete r; }
+
+size_t tn_birnn_workspace_bytes(const tn_birnn_t* r, int B, int T) {
+  if (!r || B < 0 || T < 0) return 0;
+  const size_t M = static_cast<size_t>(B) * T;
+  return tn::align_up(M * r->D * sizeof(__nv_bfloat16), 1024) + tn::align_up(M * r->ndir * r->gates * r->H * sizeof(float), 1024) + 1024;
+}
+
+int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t* valid_len, int B, int T, float* y,
+                     float* ymax, float* h_final, float* c_final, void* workspace, size_t workspace_bytes,
+                     tn_stream_t stream) {
+  if (!r || B < 0 || T < 0) return tn::set_error(TN_ERR_INVALID, "bad rnn handle / shape");
+  if (B == 0 || T == 0) return TN_OK;
+  if (!x || !workspace) return tn::set_error(TN_ERR_INVALID, "null device pointer");
+  if (workspace_bytes < tn_birnn_workspace_bytes(r, B, T))
+    return tn::set_error(TN_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, tn_birnn_workspace_bytes(r, B, T));
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return tn::set_error(TN_ERR_INVALID, "workspace must be 1024-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t M = static_cast<size_t>(B) * T;
+  const int N = r->ndir * r->gates * r->H;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws);
+  float* gx = reinterpret_cast<float*>(ws + tn::align_up(M * r->D * sizeof(__nv_bfloat16), 1024));
+  const __nv_bfloat16* xin = static_cast<const __nv_bfloat16*>(x);
+  if (!x_is_bf16) {
+    TN_CUDA(tn::launch_cast_bf16(static_cast<const float*>(x), xb, M * r->D, st));
+    xin = xb;
+  }
+  // input projection for every (b,t) and both directions: one tensor-core GEMM, bias in the epilogue
+  tn::ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = xin;
+  p.in_cstride = r->D;
+  p.H = 1;
+  p.W = 1;
+  p.Cin = r->D;
+  p.Ho = 1;
+  p.Wo = 1;
+  p.R = 1;
+  p.S = 1;
+  p.stride = 1;
+  p.pad = 0;
+  p.mode = tn::kModeConv;
+  p.wpack = r->proj.wpack;
+  p.num_chunks = r->proj.num_chunks;
+  p.chunks_per_tap = r->proj.chunks_per_tap;
+  p.out = gx;
+  p.out_cstride = N;
+  p.out_coff = 0;
+  p.out_fp32 = 1;
+  p.Cout = N;
+  p.epi_shift = r->bih;
+  p.M = static_cast<int>(M);
+  TN_CUDA(tn::launch_conv_gemm(p, st));
+
+  if (y && valid_len) TN_CUDA(cudaMemsetAsync(y, 0, M * r->ndir * r->H * sizeof(float), st));
+  tn::RnnScanParams s;
+  memset(&s, 0, sizeof(s));
+  s.gates = r->gates;
+  s.B = B;
+  s.T = T;
+  s.H = r->H;
+  s.ndir = r->ndir;
+  s.reverse_dir1 = 1;
+  s.gx = gx;
+  s.WhhT = r->WhhT;
+  s.bhh = r->bhh;
+  s.valid_len = valid_len;
+  s.y = y;
+  s.ymax = ymax;
+  s.h_final = h_final;
+  s.c_final = c_final;
+  TN_CUDA(tn::launch_rnn_scan(s, st));
+  return TN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+#include "tn_common.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace tn {
+
+std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+int check_arch(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count)
+    return set_error(TN_ERR_ARCH, "no CUDA device %d (%s); tennis_b200 has no CPU fallback", device,
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+  int major = 0;
+  TN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return set_error(TN_ERR_ARCH, "device %d is sm_%d0, kernels are built for sm_100a only", device, major);
+  return TN_OK;
+}
+
+DeviceArena::~DeviceArena() {
+  for (void* p : ptrs) cudaFree(p);
+}
+void* DeviceArena::alloc(size_t bytes) {
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    set_error(TN_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  ptrs.push_back(d);
+  return d;
+}
+void* DeviceArena::upload(const void* host, size_t bytes) {
+  void* d = alloc(bytes);
+  if (!d) return nullptr;
+  cudaError_t e = cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error(TN_ERR_CUDA, "cudaMemcpy H2D(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return d;
+}
+
+bool make_bn(DeviceArena& arena, const float* gamma, const float* beta, const float* mean, const float* var, int C,
+             BnDev* out, std::vector<float>* host_scale, std::vector<float>* host_shift) {
+  std::vector<float> sc(C), sh(C);
+  for (int c = 0; c < C; ++c) {
+    // fp32 like the reference runtime: (x - mean) / sqrt(var + eps) * gamma + beta
+    float inv = 1.0f / sqrtf(var[c] + 1e-5f);
+    sc[c] = gamma[c] * inv;
+    sh[c] = beta[c] - mean[c] * sc[c];
+  }
+  out->C = C;
+  out->scale = static_cast<const float*>(arena.upload(sc.data(), C * sizeof(float)));
+  out->shift = static_cast<const float*>(arena.upload(sh.data(), C * sizeof(float)));
+  if (host_scale) *host_scale = sc;
+  if (host_shift) *host_shift = sh;
+  return out->scale && out->shift;
+}
+
+bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out) {
+  const int BN = conv_gemm_pick_bn(Cout);
+  const int ntiles = (Cout + BN - 1) / BN;
+  int cpt, nchunks;
+  if (mode == kModeStem) {
+    cpt = 1;
+    nchunks = (R + 1) / 2;
+  } else {
+    cpt = (Cin + 63) / 64;
+    nchunks = R * S * cpt;
+  }
+  const size_t bytes = static_cast<size_t>(ntiles) * nchunks * BN * 128;
+  std::vector<uint8_t> blob(bytes, 0);
+  auto put = [&](int t, int c, int n, int kk, float v) {
+    size_t off = (static_cast<size_t>(t) * nchunks + c) * BN * 128 + static_cast<size_t>(n) * 128 +
+                 ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
+    __nv_bfloat16 b = __float2bfloat16(v);
+    memcpy(&blob[off], &b, 2);
+  };
+  for (int t = 0; t < ntiles; ++t) {
+    for (int c = 0; c < nchunks; ++c) {
+      for (int n = 0; n < BN; ++n) {
+        const int co = t * BN + n;
+        if (co >= Cout) continue;
+        for (int kk = 0; kk < 64; ++kk) {
+          float v = 0.f;
+          if (mode == kModeStem) {
+            const int r = 2 * c + (kk >> 5), q = kk & 31, s = q >> 2, ch = q & 3;
+            if (r < R && s < S && ch < Cin) v = w[((static_cast<size_t>(co) * Cin + ch) * R + r) * S + s];
+          } else {
+            const int tap = c / cpt, ci = (c % cpt) * 64 + kk;
+            const int r = tap / S, s = tap % S;
+            if (ci < Cin) v = w[((static_cast<size_t>(co) * Cin + ci) * R + r) * S + s];
+          }
+          if (v != 0.f) put(t, c, n, kk, v);
+        }
+      }
+    }
+  }
+  out->Cin = Cin;
+  out->Cout = Cout;
+  out->R = R;
+  out->S = S;
+  out->num_chunks = nchunks;
+  out->chunks_per_tap = cpt;
+  out->mode = mode;
+  out->wpack = static_cast<const uint8_t*>(arena.upload(blob.data(), bytes));
+  return out->wpack != nullptr;
+}
+
+}  // namespace tn
+
+extern "C" {
+
+int tn_version(void) { return 100; }
+const char* tn_last_error(void) { return tn::last_error().c_str(); }
+int tn_device_check(int device) { return tn::check_arch(device); }
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Shared host-side helpers for the C-ABI translation units: error text, CUDA checks, device arena,
+// weight packing into the UMMA shared-memory image.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tennis_b200.h"
+#include "tn_conv_gemm.h"
+
+namespace tn {
+
+std::string& last_error();
+int set_error(int code, const char* fmt, ...);
+
+#define TN_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ::tn::set_error(TN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                                 \
+  } while (0)
+
+int check_arch(int device);  // TN_OK iff compute capability 10.x
+
+// Owns device allocations of a handle.
+struct DeviceArena {
+  std::vector<void*> ptrs;
+  ~DeviceArena();
+  // returns nullptr on failure (error text set)
+  void* upload(const void* host, size_t bytes);
+  void* alloc(size_t bytes);
+};
+
+struct BnDev {
+  const float* scale = nullptr;  // gamma / sqrt(var + eps)
+  const float* shift = nullptr;  // beta - mean * scale
+  int C = 0;
+};
+struct ConvDev {
+  const uint8_t* wpack = nullptr;
+  int Cin = 0, Cout = 0, R = 1, S = 1;
+  int num_chunks = 0, chunks_per_tap = 0;
+  int mode = kModeConv;
+};
+
+// Fold inference BatchNorm (eps 1e-5, running statistics) into scale/shift.  p -> {gamma,beta,mean,var}, each C.
+bool make_bn(DeviceArena& arena, const float* gamma, const float* beta, const float* mean, const float* var, int C,
+             BnDev* out, std::vector<float>* host_scale = nullptr, std::vector<float>* host_shift = nullptr);
+// Pack OIHW fp32 weights (Cout,Cin,R,S) into per-(n_tile, K-chunk) swizzled bf16 blobs.
+bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace tn

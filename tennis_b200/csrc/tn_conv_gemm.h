@@ -1,0 +1,51 @@
+// Parameter block + launcher of the tcgen05 implicit-GEMM convolution (see tn_conv_gemm.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace tn {
+
+enum ConvMode : int {
+  kModeConv = 0,   // generic RxS / stride / zero-pad conv (also plain GEMM: R=S=1, H=1, W=M)
+  kModePool2 = 1,  // 1x1 conv applied to the 2x2/stride-2 average of the BN+ReLU-activated input
+  kModeStem = 2,   // 7x7/2 conv on a channel-padded (C=4) NHWC image, no prologue
+};
+
+struct ConvGemmParams {
+  // input activation: NHWC bf16, channel stride in_cstride (>= Cin), channels [0, Cin) are read
+  const __nv_bfloat16* in;
+  int in_cstride;
+  int H, W, Cin;
+  // geometry
+  int Ho, Wo, R, S, stride, pad;
+  int mode;
+  // pre-activation applied while gathering A (null -> identity): y = relu?(x * scale[c] + shift[c])
+  const float* pro_scale;
+  const float* pro_shift;
+  int pro_relu;
+  // packed weights: [n_tile][chunk][BN rows x 128 B, 128B-swizzled K-major image]
+  const uint8_t* wpack;
+  int num_chunks;      // K-chunks of 64 per output tile
+  int chunks_per_tap;  // ceil(Cin / 64) (CONV / POOL2)
+  // output: NHWC, written at channel offset out_coff with channel stride out_cstride
+  void* out;
+  int out_cstride;
+  int out_coff;
+  int out_fp32;  // 0 -> bf16, 1 -> fp32
+  int Cout;      // multiple of 32
+  // epilogue: y = relu?(acc * scale[n] + shift[n] + residual)
+  const float* epi_scale;
+  const float* epi_shift;
+  int epi_relu;
+  const __nv_bfloat16* res;  // optional residual, NHWC bf16 at the output resolution
+  int res_cstride;
+  int M;  // F * Ho * Wo
+};
+
+int conv_gemm_pick_bn(int cout);
+size_t conv_gemm_wpack_bytes(int cout, int num_chunks);
+cudaError_t launch_conv_gemm(const ConvGemmParams& p, cudaStream_t stream);
+
+}  // namespace tn

@@ -1,0 +1,244 @@
+// Recurrent scan for the fused (bi)GRU / (bi)LSTM layer (Appendix A.3/A.4).
+//
+// The input projection x*W_ih^T + b_ih for all timesteps is one tensor-core GEMM (tn_conv_gemm.cu);
+// this kernel runs the serial part.  A thread-block cluster of CL CTAs owns a tile of RB batch rows of
+// one direction; CTA q keeps the W_hh^T slice of its H/CL hidden units (all gates) resident in shared
+// memory in fp32 for the whole scan, computes their gates each step, and publishes the new h slice to
+// every CTA of the cluster through distributed shared memory, followed by one cluster barrier.
+// max-over-time (CNNRNN, definitions.py:107) is accumulated in registers so (B,T,2H) need not be
+// written at all when only the pooled vector is wanted.
+//
+// valid_length semantics follow MXNet's unroll(valid_length=...) (A.4): row b runs len[b] steps; the
+// reverse direction starts at position len[b]-1; outputs past len[b] stay zero (caller pre-zeroes y);
+// the returned state is the one after step len[b]-1.
+#include "tn_rnn.h"
+
+#include <cooperative_groups.h>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+namespace tn {
+
+namespace {
+
+constexpr int kRB = 4;  // batch rows per cluster
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int G, int CL>
+__global__ void rnn_scan_kernel(const RnnScanParams p) {
+  extern __shared__ float smem_f[];
+  const int H = p.H;
+  const int HS = H / CL;   // hidden units owned by this CTA
+  const int NJ = G * HS;   // gate columns owned by this CTA == blockDim.x
+  float* Wt = smem_f;                       // [H][NJ]
+  float* hbuf = Wt + static_cast<size_t>(H) * NJ;  // [2][H][kRB]
+  float* hh = hbuf + 2 * H * kRB;           // [kRB][NJ]
+
+  const int tid = threadIdx.x;
+  const int q = (CL > 1) ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+  const int tile = blockIdx.x / CL;
+  const int dir = blockIdx.y;
+  const int b0 = tile * kRB;
+  const int GH = G * H;
+
+  // ---- stage the W_hh^T slice: column j=(g,u) <- row (g*H + q*HS + u) of W_hh ; global WhhT is [dir][H(k)][G*H]
+  {
+    const float* src = p.WhhT + static_cast<size_t>(dir) * H * GH;
+    for (int idx = tid; idx < H * NJ; idx += blockDim.x) {
+      const int k = idx / NJ;
+      const int j = idx - k * NJ;
+      const int g = j / HS, u = j - g * HS;
+      Wt[idx] = __ldg(src + static_cast<size_t>(k) * GH + g * H + q * HS + u);
+    }
+  }
+  // initial hidden state (zeros unless h0 given): hbuf[0][k][b]
+  for (int idx = tid; idx < H * kRB; idx += blockDim.x) {
+    const int k = idx / kRB, b = idx - k * kRB;
+    float v = 0.f;
+    if (p.h0 && b0 + b < p.B) v = p.h0[(static_cast<size_t>(dir) * p.B + b0 + b) * H + k];
+    hbuf[idx] = v;
+    hbuf[H * kRB + idx] = v;
+  }
+  const int j_gate = tid / HS;        // gate of my column
+  const int j_unit = tid - j_gate * HS;
+  const float bhh = __ldg(p.bhh + static_cast<size_t>(dir) * GH + j_gate * H + q * HS + j_unit);
+
+  // ---- phase-2 items: (b,u) pairs, item = tid + n*blockDim  (kRB*HS items, blockDim = G*HS threads)
+  constexpr int IPT = (kRB + G - 1) / G;
+  int it_b[IPT], it_u[IPT], it_len[IPT];
+  float it_c[IPT], it_h[IPT], it_max[IPT];
+  int maxlen = 0;
+#pragma unroll
+  for (int n = 0; n < IPT; ++n) {
+    const int item = tid + n * blockDim.x;
+    it_b[n] = -1;
+    it_u[n] = 0;
+    it_len[n] = 0;
+    it_c[n] = 0.f;
+    it_h[n] = 0.f;
+    it_max[n] = -INFINITY;
+    if (item < kRB * HS) {
+      const int b = item / HS, u = item - b * HS;
+      if (b0 + b < p.B) {
+        it_b[n] = b;
+        it_u[n] = u;
+        it_len[n] = p.valid_len ? min(max(p.valid_len[b0 + b], 0), p.T) : p.T;
+        if (p.c0) it_c[n] = p.c0[(static_cast<size_t>(dir) * p.B + b0 + b) * H + q * HS + u];
+        if (p.h0) it_h[n] = p.h0[(static_cast<size_t>(dir) * p.B + b0 + b) * H + q * HS + u];
+      }
+    }
+  }
+  for (int b = 0; b < kRB; ++b) {
+    if (b0 + b < p.B) maxlen = max(maxlen, p.valid_len ? min(max(p.valid_len[b0 + b], 0), p.T) : p.T);
+  }
+  if (CL > 1) cg::this_cluster().sync(); else __syncthreads();
+
+  const int gx_row = p.ndir * GH;  // floats per (b,t) row of gx
+  for (int s = 0; s < maxlen; ++s) {
+    const float* hcur = hbuf + (s & 1) * H * kRB;
+    float* hnext_local = hbuf + ((s + 1) & 1) * H * kRB;
+
+    // prefetch this step's input-projection gates (latency hidden behind the matvec)
+    float gxv[IPT][G];
+#pragma unroll
+    for (int n = 0; n < IPT; ++n) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) gxv[n][g] = 0.f;
+      if (it_b[n] >= 0 && s < it_len[n]) {
+        const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : it_len[n] - 1 - s;
+        const float* gp = p.gx + (static_cast<size_t>(b0 + it_b[n]) * p.T + pos) * gx_row + dir * GH + q * HS + it_u[n];
+#pragma unroll
+        for (int g = 0; g < G; ++g) gxv[n][g] = __ldg(gp + g * H);
+      }
+    }
+
+    // phase 1: hh[b][j] = sum_k Wt[k][j] * h[k][b] + bhh[j]
+    float acc[kRB];
+#pragma unroll
+    for (int b = 0; b < kRB; ++b) acc[b] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) {
+      const float w = Wt[k * NJ + tid];
+      const float4 hv = *reinterpret_cast<const float4*>(hcur + k * kRB);
+      acc[0] = fmaf(w, hv.x, acc[0]);
+      acc[1] = fmaf(w, hv.y, acc[1]);
+      acc[2] = fmaf(w, hv.z, acc[2]);
+      acc[3] = fmaf(w, hv.w, acc[3]);
+    }
+#pragma unroll
+    for (int b = 0; b < kRB; ++b) hh[b * NJ + tid] = acc[b] + bhh;
+    __syncthreads();
+
+    // phase 2: gate math for my (b,u) items
+#pragma unroll
+    for (int n = 0; n < IPT; ++n) {
+      if (it_b[n] < 0) continue;
+      const int b = it_b[n], u = it_u[n];
+      float hnew = it_h[n];
+      if (s < it_len[n]) {
+        if (G == 3) {  // GRU, gate order [r, z, n]
+          const float r = sigmoidf_(gxv[n][0] + hh[b * NJ + 0 * HS + u]);
+          const float z = sigmoidf_(gxv[n][1] + hh[b * NJ + 1 * HS + u]);
+          const float nn = tanhf(gxv[n][2] + r * hh[b * NJ + 2 * HS + u]);
+          hnew = (1.f - z) * nn + z * it_h[n];
+        } else {  // LSTM, gate order [i, f, g, o]
+          const float ig = sigmoidf_(gxv[n][0] + hh[b * NJ + 0 * HS + u]);
+          const float fg = sigmoidf_(gxv[n][1] + hh[b * NJ + 1 * HS + u]);
+          const float gg = tanhf(gxv[n][2] + hh[b * NJ + 2 * HS + u]);
+          const float og = sigmoidf_(gxv[n][3] + hh[b * NJ + 3 * HS + u]);
+          it_c[n] = fg * it_c[n] + ig * gg;
+          hnew = og * tanhf(it_c[n]);
+        }
+        it_h[n] = hnew;
+        it_max[n] = fmaxf(it_max[n], hnew);
+        if (p.y) {
+          const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : it_len[n] - 1 - s;
+          p.y[(static_cast<size_t>(b0 + b) * p.T + pos) * (p.ndir * H) + dir * H + q * HS + u] = hnew;
+        }
+      }
+      // publish (frozen rows re-publish their last state so both buffers stay coherent)
+      const int hidx = (q * HS + u) * kRB + b;
+      if (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int r = 0; r < CL; ++r) cluster.map_shared_rank(hnext_local, r)[hidx] = hnew;
+      } else {
+        hnext_local[hidx] = hnew;
+      }
+    }
+    if (CL > 1) cg::this_cluster().sync(); else __syncthreads();
+  }
+
+  // ---- outputs
+#pragma unroll
+  for (int n = 0; n < IPT; ++n) {
+    if (it_b[n] < 0) continue;
+    const size_t o = (static_cast<size_t>(b0 + it_b[n])) * (p.ndir * H) + dir * H + q * HS + it_u[n];
+    if (p.ymax) p.ymax[o] = it_max[n];
+    const size_t so = (static_cast<size_t>(dir) * p.B + b0 + it_b[n]) * H + q * HS + it_u[n];
+    if (p.h_final) p.h_final[so] = it_h[n];
+    if (G == 4 && p.c_final) p.c_final[so] = it_c[n];
+  }
+}
+
+template <int G, int CL>
+cudaError_t launch_t(const RnnScanParams& p, cudaStream_t st) {
+  const int HS = p.H / CL;
+  const int NJ = G * HS;
+  const size_t smem = (static_cast<size_t>(p.H) * NJ + 2 * p.H * kRB + kRB * NJ) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(rnn_scan_kernel<G, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  const int tiles = (p.B + kRB - 1) / kRB;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * CL, p.ndir, 1);
+  cfg.blockDim = dim3(NJ, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CL > 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, rnn_scan_kernel<G, CL>, p);
+}
+
+}  // namespace
+
+int rnn_scan_cluster_size(int G, int H) {
+  // smallest power-of-two cluster whose per-CTA W_hh^T slice (+ state) fits in 224 KB of shared memory
+  for (int cl = 1; cl <= 8; cl *= 2) {
+    const size_t nj = static_cast<size_t>(G) * (H / cl);
+    const size_t bytes = (static_cast<size_t>(H) * nj + 2 * H * kRB + kRB * nj) * sizeof(float);
+    if (H % cl == 0 && bytes <= 224 * 1024 && nj <= 1024) return cl;
+  }
+  return -1;
+}
+
+cudaError_t launch_rnn_scan(const RnnScanParams& p, cudaStream_t st) {
+  if (p.B == 0 || p.T == 0) return cudaSuccess;
+  const int G = p.gates;
+  const int cl = rnn_scan_cluster_size(G, p.H);
+  if (cl < 0 || (G != 3 && G != 4)) return cudaErrorInvalidValue;
+  if (G == 3) {
+    switch (cl) {
+      case 1: return launch_t<3, 1>(p, st);
+      case 2: return launch_t<3, 2>(p, st);
+      case 4: return launch_t<3, 4>(p, st);
+      default: return launch_t<3, 8>(p, st);
+    }
+  } else {
+    switch (cl) {
+      case 1: return launch_t<4, 1>(p, st);
+      case 2: return launch_t<4, 2>(p, st);
+      case 4: return launch_t<4, 4>(p, st);
+      default: return launch_t<4, 8>(p, st);
+    }
+  }
+}
+
+}  // namespace tn

@@ -1,0 +1,203 @@
+"""Thin, torch-tensor-facing wrappers over the C ABI.  Tensors are containers only: every op below hands raw
+device pointers + the current CUDA stream to libtennis_b200.so.  No op has a PyTorch/CPU fallback."""
+import ctypes
+from ctypes import c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import check, dptr, lib, stream_ptr
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.TennisB200Error("tennis_b200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+def _host_f32(t):
+    return None if t is None else t.detach().to("cpu", torch.float32).contiguous()
+
+
+def _workspace(nbytes, device):
+    # torch's caching allocator returns >=512-byte aligned blocks; over-allocate and align to 1024 ourselves
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    return buf, buf.data_ptr() + off
+
+
+class Conv:
+    """One fused convolution (tn_conv_*): [BN+ReLU prologue] -> conv -> [scale/shift(+ReLU), residual] epilogue."""
+
+    def __init__(self, weight, mode=_lib.MODE_CONV, pro_scale=None, pro_shift=None, epi_scale=None, epi_shift=None,
+                 device=0):
+        w = _host_f32(weight)
+        self.Cout, self.Cin, self.R, self.S = w.shape
+        self.mode = mode
+        keep = [w] + [_host_f32(t) for t in (pro_scale, pro_shift, epi_scale, epi_shift)]
+        self._h = c_void_p()
+        check(lib().tn_conv_create(ctypes.byref(self._h), device, dptr(keep[0]), self.Cout, self.Cin, self.R, self.S,
+                                   mode, dptr(keep[1]), dptr(keep[2]), dptr(keep[3]), dptr(keep[4])))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().tn_conv_destroy(self._h)
+            self._h = c_void_p()
+
+    def out_hw(self, H, W, stride, pad):
+        if self.mode == _lib.MODE_POOL2:
+            return H // 2, W // 2
+        return (H + 2 * pad - self.R) // stride + 1, (W + 2 * pad - self.S) // stride + 1
+
+    def __call__(self, x, stride=1, pad=0, pro_relu=True, epi_relu=False, out=None, out_coff=0, out_fp32=False,
+                 residual=None):
+        """x: (n,H,W,C) bf16 NHWC cuda tensor; returns / fills `out` (n,Ho,Wo,Cs)."""
+        _require_cuda(x, out, residual)
+        n, H, W, cs = x.shape
+        Ho, Wo = self.out_hw(H, W, stride, pad)
+        if out is None:
+            out = torch.empty((n, Ho, Wo, self.Cout), dtype=torch.float32 if out_fp32 else torch.bfloat16,
+                              device=x.device)
+        check(lib().tn_conv_forward(self._h, dptr(x), cs, n, H, W, stride, pad, int(pro_relu), int(epi_relu), dptr(out),
+                                    out.shape[3], out_coff, int(out.dtype == torch.float32), dptr(residual),
+                                    0 if residual is None else residual.shape[3], stream_ptr()))
+        return out
+
+
+def frames_to_nhwc4(frames):
+    _require_cuda(frames)
+    n, c, h, w = frames.shape
+    assert c == 3 and frames.dtype == torch.float32
+    out = torch.empty((n, h, w, 4), dtype=torch.bfloat16, device=frames.device)
+    check(lib().tn_frames_to_nhwc4(dptr(frames.contiguous()), dptr(out), n, h, w, stream_ptr()))
+    return out
+
+
+class Backbone:
+    """DenseNet-121 / ResNet-18 v2 `.features` (tn_backbone_*)."""
+
+    ARCH = {"densenet121": _lib.ARCH_DENSENET121, "resnet18_v2": _lib.ARCH_RESNET18_V2}
+
+    def __init__(self, arch, flat_params, device=0):
+        self.arch_name = arch.lower()
+        self.arch = self.ARCH[self.arch_name]
+        self.device = device
+        flat = _host_f32(flat_params)
+        self._h = c_void_p()
+        check(lib().tn_backbone_create(ctypes.byref(self._h), self.arch, device, dptr(flat), flat.numel()))
+        self._ws = None
+        self._ws_key = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().tn_backbone_destroy(self._h)
+            self._h = c_void_p()
+
+    def feature_dim(self, h, w):
+        return lib().tn_backbone_feature_dim(self.arch, h, w)
+
+    def workspace_bytes(self, n, h, w):
+        return lib().tn_backbone_workspace_bytes(self._h, n, h, w)
+
+    def _get_ws(self, n, h, w, device):
+        need = self.workspace_bytes(n, h, w)
+        if need == 0:
+            raise _lib.TennisB200Error("unsupported input %dx%d for %s" % (h, w, self.arch_name))
+        if self._ws is None or self._ws_key[0] < need or self._ws_key[1] != device:
+            self._ws = None
+            self._ws = _workspace(need, device)
+            self._ws_key = (need, device)
+        return self._ws[1], self._ws_key[0]
+
+    def __call__(self, frames, want_bf16=False):
+        """frames: (n,3,H,W) fp32 normalised NCHW, or (n,H,W,3) uint8 NHWC -> (n,D) fp32 [, (n,D) bf16]."""
+        _require_cuda(frames)
+        frames = frames.contiguous()
+        if frames.dtype == torch.uint8:
+            n, h, w, c = frames.shape
+            dt = _lib.FRAMES_U8_NHWC
+        else:
+            n, c, h, w = frames.shape
+            dt = _lib.FRAMES_F32_NCHW
+            assert frames.dtype == torch.float32
+        assert c == 3
+        D = self.feature_dim(h, w)
+        feats = torch.empty((n, D), dtype=torch.float32, device=frames.device)
+        fb = torch.empty((n, D), dtype=torch.bfloat16, device=frames.device) if want_bf16 else None
+        if n:
+            ws_ptr, ws_bytes = self._get_ws(n, h, w, frames.device)
+            check(lib().tn_backbone_forward(self._h, dptr(frames), dt, n, h, w, dptr(feats), dptr(fb), c_void_p(ws_ptr),
+                                            ws_bytes, stream_ptr()))
+        return (feats, fb) if want_bf16 else feats
+
+
+def dense(x, weight, bias=None):
+    _require_cuda(x, weight, bias)
+    x2 = x.reshape(x.shape[0], -1).contiguous().float()
+    out_dim, in_dim = weight.shape
+    assert x2.shape[1] == in_dim
+    y = torch.empty((x2.shape[0], out_dim), dtype=torch.float32, device=x.device)
+    check(lib().tn_dense_forward(dptr(x2), dptr(weight.contiguous()), dptr(None if bias is None else bias.contiguous()),
+                                 dptr(y), x2.shape[0], in_dim, out_dim, stream_ptr()))
+    return y
+
+
+def temporal_pool(x, pool="max"):
+    _require_cuda(x)
+    B, T, D = x.shape
+    x = x.contiguous().float()
+    y = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    check(lib().tn_temporal_pool(dptr(x), dptr(y), B, T, D, _lib.POOL_MEAN if pool == "mean" else _lib.POOL_MAX,
+                                 stream_ptr()))
+    return y
+
+
+class BiRNN:
+    """Fused (bi)directional GRU/LSTM layer (tn_birnn_*).  params: dict with Gluon names l0_*/r0_*."""
+
+    def __init__(self, cell, D, H, params, bidirectional=True, device=0):
+        self.cell, self.D, self.H = cell, D, H
+        self.ndir = 2 if bidirectional else 1
+        dirs = ["l0", "r0"][: self.ndir]
+        keep = {}
+        arrs = []
+        for suffix in ("_i2h_weight", "_h2h_weight", "_i2h_bias", "_h2h_bias"):
+            arr = (c_void_p * 2)()
+            for i, d in enumerate(dirs):
+                t = _host_f32(params[d + suffix])
+                keep[d + suffix] = t
+                arr[i] = t.data_ptr()
+            arrs.append(arr)
+        self._h = c_void_p()
+        check(lib().tn_birnn_create(ctypes.byref(self._h), device, _lib.CELL_GRU if cell == "gru" else _lib.CELL_LSTM, D,
+                                    H, self.ndir, arrs[0], arrs[1], arrs[2], arrs[3]))
+        self._ws = None
+        self._ws_bytes = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().tn_birnn_destroy(self._h)
+            self._h = c_void_p()
+
+    def __call__(self, x, valid_len=None, want_y=True, want_max=False, want_state=False):
+        """x: (B,T,D) fp32 or bf16 cuda.  Returns dict(y, ymax, h, c) with the requested entries."""
+        _require_cuda(x, valid_len)
+        B, T, D = x.shape
+        assert D == self.D
+        x = x.contiguous()
+        dev = x.device
+        y = torch.empty((B, T, self.ndir * self.H), dtype=torch.float32, device=dev) if want_y else None
+        ymax = torch.empty((B, self.ndir * self.H), dtype=torch.float32, device=dev) if want_max else None
+        h = torch.empty((self.ndir, B, self.H), dtype=torch.float32, device=dev) if want_state else None
+        c = torch.empty((self.ndir, B, self.H), dtype=torch.float32, device=dev) if (want_state and self.cell == "lstm") else None
+        vl = None if valid_len is None else valid_len.to(torch.int32).contiguous()
+        if B and T:
+            need = lib().tn_birnn_workspace_bytes(self._h, B, T)
+            if self._ws is None or self._ws_bytes < need:
+                self._ws = None
+                self._ws = _workspace(need, dev)
+                self._ws_bytes = need
+            check(lib().tn_birnn_forward(self._h, dptr(x), int(x.dtype == torch.bfloat16), dptr(vl), B, T, dptr(y),
+                                         dptr(ymax), dptr(h), dptr(c), c_void_p(self._ws[1]), self._ws_bytes,
+                                         stream_ptr()))
+        return {"y": y, "ymax": ymax, "h": h, "c": c}

@@ -1,0 +1,84 @@
+"""CUDA backbone / RNN head (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# bf16 activations + fp32 accumulation through 120 conv layers: tolerance on O(1) features, stated per test.
+FEAT_TOL = {"densenet121": 6e-2, "resnet18_v2": 6e-2}
+
+
+@pytest.mark.parametrize("arch,size,n", [("densenet121", 224, 3), ("resnet18_v2", 224, 3), ("densenet121", 256, 1)])
+def test_backbone_features_match_oracle(arch, size, n):
+    from oracle import vision as O
+    from tennis_b200 import ops
+    p = O.synthetic_params(arch, seed=1234)
+    _, x = O.synthetic_frames(n, size, seed=100)
+    with torch.no_grad():
+        ref = O.FEATURES[arch](x, p)
+    bb = ops.Backbone(arch, O.flatten_params(arch, p))
+    out, out_bf = bb(x.cuda(), want_bf16=True)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    err = (out.cpu() - ref).abs()
+    scale = ref.abs().max().item()
+    print("%s %d: max|ref|=%.4f max err=%.5f mean err=%.6f" % (arch, size, scale, err.max().item(), err.mean().item()))
+    assert err.max().item() < FEAT_TOL[arch] * max(1.0, scale)
+    assert (out_bf.float().cpu() - out.cpu()).abs().max().item() <= 1e-2 * max(1.0, scale)
+
+
+def test_backbone_u8_input_matches_f32_input():
+    from oracle import vision as O
+    from tennis_b200 import ops
+    p = O.synthetic_params("densenet121", seed=1234)
+    u8, x = O.synthetic_frames(2, 224, seed=7)
+    bb = ops.Backbone("densenet121", O.flatten_params("densenet121", p))
+    a = bb(x.cuda())
+    b = bb(u8.cuda())
+    torch.cuda.synchronize()
+    assert (a - b).abs().max().item() < 3e-2
+
+
+def test_backbone_batch_independence():
+    """Frames are independent: a frame's features do not depend on its batch position / neighbours (bit-exact)."""
+    from oracle import vision as O
+    from tennis_b200 import ops
+    p = O.synthetic_params("densenet121", seed=1234)
+    _, x = O.synthetic_frames(5, 224, seed=11)
+    bb = ops.Backbone("densenet121", O.flatten_params("densenet121", p))
+    full = bb(x.cuda()).clone()
+    part = bb(x[3:5].cuda()).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(full[3:5], part)
+
+
+@pytest.mark.parametrize("cell", ["gru", "lstm"])
+@pytest.mark.parametrize("B,T,D,H", [(5, 7, 64, 128), (64, 32, 1024, 128), (3, 9, 256, 256)])
+def test_birnn_matches_oracle(cell, B, T, D, H):
+    from oracle import vision as O
+    from tennis_b200 import ops
+    p = O.synthetic_rnn_params(cell, D, H, seed=4321)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, T, D, generator=g).relu()
+    with torch.no_grad():
+        ref = O.birnn_layer(x, p, cell, H)
+    rnn = ops.BiRNN(cell, D, H, p)
+    out = rnn(x.cuda(), want_y=True, want_max=True)
+    torch.cuda.synchronize()
+    err = (out["y"].cpu() - ref).abs().max().item()
+    print("birnn %s B%d T%d D%d H%d: max err %.5f" % (cell, B, T, D, H, err))
+    assert err < 2e-2  # bf16 input projection, fp32 recurrence
+    assert (out["ymax"].cpu() - ref.max(dim=1).values).abs().max().item() < 2e-2
+
+
+def test_dense_and_pool():
+    from tennis_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(37, 1024, generator=g)
+    w = torch.randn(11, 1024, generator=g) * 0.03
+    b = torch.randn(11, generator=g)
+    y = ops.dense(x.cuda(), w.cuda(), b.cuda())
+    assert (y.cpu() - (x @ w.t() + b)).abs().max().item() < 1e-4
+    z = torch.randn(4, 6, 50, generator=g)
+    assert torch.equal(ops.temporal_pool(z.cuda(), "max").cpu(), z.max(dim=1).values)
+    assert (ops.temporal_pool(z.cuda(), "mean").cpu() - z.mean(dim=1)).abs().max().item() < 1e-6
