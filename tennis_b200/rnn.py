@@ -1,0 +1,58 @@
+"""mx.gluon.rnn.GRU / LSTM layer stand-ins (layout 'NTC'), running tn_birnn_forward."""
+from . import ops
+from .gluon import Block, Parameter
+
+
+class _RNNLayer(Block):
+    _cell = None
+    _gates = 0
+
+    def __init__(self, hidden_size, num_layers=1, layout='NTC', bidirectional=False, input_size=0, **kw):
+        super(_RNNLayer, self).__init__(**kw)
+        if num_layers != 1 or layout != 'NTC':
+            raise NotImplementedError("hot path uses 1 layer, layout='NTC' (definitions.py:94-96)")
+        self._hidden_size, self._input_size, self._bidirectional = hidden_size, input_size, bidirectional
+        G, H = self._gates, hidden_size
+        for d in (['l0', 'r0'] if bidirectional else ['l0']):
+            self._reg_params[d + '_i2h_weight'] = Parameter(d + '_i2h_weight', (G * H, input_size))
+            self._reg_params[d + '_h2h_weight'] = Parameter(d + '_h2h_weight', (G * H, H))
+            self._reg_params[d + '_i2h_bias'] = Parameter(d + '_i2h_bias', (G * H,), init='zeros')
+            self._reg_params[d + '_h2h_bias'] = Parameter(d + '_h2h_bias', (G * H,), init='zeros')
+        self._engine = None
+        self._engine_key = None
+
+    def _get_engine(self, x):
+        D = x.shape[2]
+        for n, p in self._reg_params.items():
+            if p._data is None and n.endswith('_i2h_weight'):
+                p._finish_deferred((self._gates * self._hidden_size, D))
+                p.reset_ctx(x.device)
+        key = (x.device.index or 0,) + tuple(p._version for p in self._reg_params.values())
+        if self._engine is None or self._engine_key != key:
+            params = {n: p.data() for n, p in self._reg_params.items()}
+            self._engine = ops.BiRNN(self._cell, D, self._hidden_size, params, self._bidirectional, device=x.device.index or 0)
+            self._engine_key = key
+        return self._engine
+
+    @staticmethod
+    def _pick_input(x):
+        twin = getattr(x, "_tn_bf16", None)
+        return twin if twin is not None else x
+
+    def forward(self, x):
+        """(B,T,D) -> (B,T,ndir*H)."""
+        ops._require_cuda(x)
+        return self._get_engine(x)(self._pick_input(x), want_y=True)["y"]
+
+    def forward_max(self, x):
+        """max over time of the layer output, fused into the scan: (B,T,D) -> (B,ndir*H) (definitions.py:106-107)."""
+        ops._require_cuda(x)
+        return self._get_engine(x)(self._pick_input(x), want_y=False, want_max=True)["ymax"]
+
+
+class GRU(_RNNLayer):
+    _cell, _gates = 'gru', 3
+
+
+class LSTM(_RNNLayer):
+    _cell, _gates = 'lstm', 4
