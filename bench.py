@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of record: frames/s of the 224x224 CNN + bi-GRU event detector forward (BASELINE.json configs[1]:
+64 clips x 32 frames per GPU, DenseNet-121 features -> BiGRU(128) -> max over time -> Dense(11)).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, NCCL)
+
+ours      : one step = one forward of the whole batch through libtennis_b200.so.  `value` times the step with the
+            clips already resident in HBM; `e2e` times the same model through the public host-facing call
+            (pinned host clips -> H2D -> forward -> logits D2H).  N>1: weak scaling, 64 clips per GPU, frames sharded
+            by rank, one NCCL all-gather of per-frame features before the temporal head.
+reference : the reference's own implementation is MXNet/Gluon on the CPU (evaluate.py --num_gpus 0); MXNet cannot be
+            installed offline, so this arm times the CPU oracle port (oracle/, torch fp32, all host threads) on a
+            bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIPS_PER_GPU, T, SIZE, CLASSES, HIDDEN = 64, 32, 224, 11, 128
+ARCH = "densenet121"
+FLOP_PER_FRAME = 5.666e9  # conv layers of DenseNet-121 @224^2, SURVEY.md §8d / BASELINE.md §3
+WORKLOAD = "configs[1]: CNN+GRU event detector fwd, %d clips x %d frames @%dx%d per GPU" % (CLIPS_PER_GPU, T, SIZE, SIZE)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def build_oracle_model():
+    import torch
+    from oracle import vision as O
+    p = O.synthetic_params(ARCH, seed=1234)
+    rp = O.synthetic_rnn_params("gru", 1024, HIDDEN, seed=4321)
+    g = torch.Generator().manual_seed(77)
+    cw = (torch.rand(CLASSES, 2 * HIDDEN, generator=g) * 2 - 1) * 0.07
+    cb = torch.zeros(CLASSES)
+    return O, p, rp, cw, cb
+
+
+def oracle_forward(O, p, rp, cw, cb, clips):
+    import torch
+    with torch.no_grad():
+        return O.cnnrnn(clips, lambda x: O.FEATURES[ARCH](x, p), rp, "gru", HIDDEN, cw, cb)
+
+
+def time_cpu_port(budget_s, clips_per_step=1, steps=None, warmup=1):
+    """Times the CPU oracle port on a bounded sample: `clips_per_step` 32-frame clips per step."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, p, rp, cw, cb = build_oracle_model()
+    g = torch.Generator().manual_seed(100)
+    clips = torch.randn(clips_per_step, T, 3, SIZE, SIZE, generator=g)
+    for _ in range(warmup):
+        oracle_forward(O, p, rp, cw, cb, clips)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        oracle_forward(O, p, rp, cw, cb, clips)
+        times.append(time.perf_counter() - t0)
+        if steps is not None and len(times) >= steps:
+            break
+        if steps is None and (time.perf_counter() - t_start) >= budget_s:
+            break
+    total = sum(times)
+    return {"frames_per_s": clips_per_step * T * len(times) / total, "ms_per_step": 1e3 * total / len(times),
+            "steps": len(times), "cores": torch.get_num_threads(), "clips_per_step": clips_per_step}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = time_cpu_port(0.0, clips_per_step=2, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    sample = "%d steps x %d clips (%d frames) of the %s workload; CPU oracle port (torch fp32), MXNet not installable offline" % (
+        r["steps"], r["clips_per_step"], r["clips_per_step"] * T, ARCH)
+    line = {
+        "impl": "reference", "metric": "frames/sec (224x224 CNN+GRU fwd)", "value": r["frames_per_s"], "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arch": ARCH, "sample": sample},
+        "cpu_baseline": {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def build_model(device):
+    """CNNRNN(FrameModel(DenseNet121.features, 11), 11, hidden 128, 'gru') with the seeded synthetic weights the
+    oracle uses (train.py:204-236 assembly)."""
+    import torch
+    from oracle import vision as O  # weights generator only (shared seeds with the parity tests)
+    from tennis_b200 import model_zoo
+    from tennis_b200.models.vision.definitions import CNNRNN, FrameModel
+    backbone = model_zoo.get_model("DenseNet121", pretrained=False).features
+    model = CNNRNN(FrameModel(backbone, CLASSES), CLASSES, hidden_size=HIDDEN, type="gru")
+    model.initialize(ctx=device)
+    p = O.synthetic_params(ARCH, seed=1234)
+    for k, v in p.items():
+        model.td.model._reg_params[k].set_data(v)
+    rp = O.synthetic_rnn_params("gru", 1024, HIDDEN, seed=4321)
+    for k, v in rp.items():
+        prm = model.rnn._reg_params[k]
+        prm.shape = tuple(v.shape)
+        prm._data = v.to(device).contiguous()
+        prm._version += 1
+    g = torch.Generator().manual_seed(77)
+    model.classes.weight.shape = (CLASSES, 2 * HIDDEN)
+    model.classes.weight._data = ((torch.rand(CLASSES, 2 * HIDDEN, generator=g) * 2 - 1) * 0.07).to(device)
+    model.classes.bias._data = torch.zeros(CLASSES, device=device)
+    model.collect_params().reset_ctx(device)
+    model.hybridize()
+    return model
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from tennis_b200 import _lib
+    from tennis_b200.parallel import HostPipeline, ShardedCNNRNN
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: tennis_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.check(_lib.lib().tn_device_check(local_rank))
+
+    model = build_model(device)
+    sharded = ShardedCNNRNN(model)
+    pipe = HostPipeline(sharded, chunks=4)
+
+    B = CLIPS_PER_GPU
+    g = torch.Generator().manual_seed(100 + rank)
+    clips_host = torch.empty((B, T, 3, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    for i in range(B):  # synthetic normalised pixels (config 1 recipe), generated per clip to bound host memory
+        clips_host[i] = torch.randn(T, 3, SIZE, SIZE, generator=g)
+    clips_dev = clips_host.to(device, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(max(3, args.warmup)):
+        logits = sharded(clips_dev)
+    barrier()
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        logits = sharded(clips_dev)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = _lib.profile_read(reset=True)
+    _lib.profile_enable(False)
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    frames_total = B * T * world * args.steps
+    value = frames_total / (ms_total * 1e-3)
+    finite = bool(torch.isfinite(logits).all().item())
+
+    # ---- end to end from pinned host memory (e2e)
+    for _ in range(2):
+        out = pipe(clips_host)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        out = pipe(clips_host)
+    f1.record()
+    barrier()
+    t2 = torch.tensor([f0.elapsed_time(f1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = frames_total / (t2.item() * 1e-3)
+    h2d = clips_host.numel() * clips_host.element_size()
+    d2h = out.numel() * out.element_size()
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        conv_ms = prof["conv_ms"]
+        conv_launches = prof["conv_launches"]
+        flops = FLOP_PER_FRAME * B * T * args.steps  # algorithmic conv FLOPs executed by this rank's conv-GEMM launches
+        achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        cpu = time_cpu_port(budget_s=12.0, clips_per_step=1, warmup=1)
+        line = {
+            "metric": "frames/sec (224x224 CNN+GRU fwd)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arch": ARCH, "head": "BiGRU(128)+max+Dense(11)",
+                       "global_clips": B * world, "frames_per_step": B * T * world,
+                       "parallelism": "frame-sharded dp%d, NCCL all-gather of features" % world,
+                       "l2": "inputs %.2f GB per GPU per step > 126 MB L2, no flush needed" % (h2d / 1e9),
+                       "outputs_finite": finite},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), %d launches/step, %.2f ms/step summed over "
+                                   "CUDA events on the launch stream" % (conv_launches // max(1, args.steps),
+                                                                         conv_ms / max(1, args.steps)),
+                         "peak_source": "bf16_tflops_sustained, " + peak_src,
+                         "algorithmic": "5.666 GFLOP/frame x %d frames/step" % (B * T)},
+            "cpu_baseline": {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"], "kind": "port",
+                             "sample": "%d x 1 clip (32 frames) through the torch-fp32 CPU oracle of the same model" % cpu["steps"]},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "pinned host fp32 clips -> 4-chunk H2D/compute pipeline -> logits.cpu()"},
+            "gpu_launches": int(prof["conv_launches"] + prof["other_launches"]),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # not launched under torchrun: re-launch ourselves with one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

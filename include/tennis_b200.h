@@ -44,6 +44,13 @@ int tn_version(void);
 const char* tn_last_error(void); /* thread-local, valid until the next call on this thread */
 int tn_device_check(int device);  /* TN_OK iff `device` is an sm_100 part */
 
+/* Launch accounting for benchmarks: kernels launched by this library are always counted; with timing_on, every
+ * launch is additionally bracketed by CUDA events on its stream.  tn_profile_read sums them (ms) per kernel family:
+ * the tcgen05 conv-GEMM vs everything else. */
+int tn_profile_enable(int timing_on);
+int tn_profile_read(double* conv_gemm_ms, long long* conv_gemm_launches, double* other_ms, long long* other_launches,
+                    int reset);
+
 /* ------------------------------------------------------------------ per-frame CNN backbone
  * Replaces gluoncv.model_zoo.get_model(name).features as called at train.py:204, evaluate.py:125,
  * train_gnmt.py:150 and wrapped at models/vision/definitions.py:22,30 (FrameModel.backbone).

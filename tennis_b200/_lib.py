@@ -30,6 +30,9 @@ SIGNATURES = {
     "tn_version": (c_int, []),
     "tn_last_error": (c_char_p, []),
     "tn_device_check": (c_int, [c_int]),
+    "tn_profile_enable": (c_int, [c_int]),
+    "tn_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), POINTER(ctypes.c_double),
+                                POINTER(ctypes.c_longlong), c_int]),
     "tn_backbone_param_count": (c_size_t, [c_int]),
     "tn_backbone_feature_dim": (c_int, [c_int, c_int, c_int]),
     "tn_backbone_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_size_t]),
@@ -88,3 +91,15 @@ def stream_ptr(stream=None):
 def dptr(t):
     """Device (or host) address of a torch tensor / None."""
     return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def profile_enable(on=True):
+    check(lib().tn_profile_enable(int(on)))
+
+
+def profile_read(reset=True):
+    """-> dict(conv_ms, conv_launches, other_ms, other_launches) accumulated since the last reset."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    na, nb = ctypes.c_longlong(), ctypes.c_longlong()
+    check(lib().tn_profile_read(ctypes.byref(a), ctypes.byref(na), ctypes.byref(b), ctypes.byref(nb), int(reset)))
+    return {"conv_ms": a.value, "conv_launches": na.value, "other_ms": b.value, "other_launches": nb.value}

@@ -123,9 +123,85 @@ bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int
   return out->wpack != nullptr;
 }
 
+// ---------------------------------------------------------------- launch counters / event timing
+namespace {
+struct ProfState {
+  bool timing = false;
+  long long launches[2] = {0, 0};
+  std::vector<cudaEvent_t> begin[2], end[2];
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+ProfState& prof() {
+  static ProfState s;
+  return s;
+}
+}  // namespace
+
+void prof_begin(int kind, cudaStream_t st) {
+  ProfState& s = prof();
+  s.launches[kind]++;
+  if (!s.timing) return;
+  cudaEvent_t e = s.get();
+  cudaEventRecord(e, st);
+  s.begin[kind].push_back(e);
+}
+void prof_end(int kind, cudaStream_t st) {
+  ProfState& s = prof();
+  if (!s.timing) return;
+  cudaEvent_t e = s.get();
+  cudaEventRecord(e, st);
+  s.end[kind].push_back(e);
+}
+
 }  // namespace tn
 
 extern "C" {
+
+int tn_profile_enable(int timing_on) {
+  tn::prof().timing = timing_on != 0;
+  return TN_OK;
+}
+
+int tn_profile_read(double* conv_gemm_ms, long long* conv_gemm_launches, double* other_ms, long long* other_launches,
+                    int reset) {
+  tn::ProfState& s = tn::prof();
+  double ms[2] = {0, 0};
+  for (int k = 0; k < 2; ++k) {
+    const size_t n = s.begin[k].size() < s.end[k].size() ? s.begin[k].size() : s.end[k].size();
+    for (size_t i = 0; i < n; ++i) {
+      cudaError_t e = cudaEventSynchronize(s.end[k][i]);
+      if (e != cudaSuccess) return tn::set_error(TN_ERR_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+      float t = 0.f;
+      cudaEventElapsedTime(&t, s.begin[k][i], s.end[k][i]);
+      ms[k] += t;
+    }
+  }
+  if (conv_gemm_ms) *conv_gemm_ms = ms[0];
+  if (other_ms) *other_ms = ms[1];
+  if (conv_gemm_launches) *conv_gemm_launches = s.launches[0];
+  if (other_launches) *other_launches = s.launches[1];
+  if (reset) {
+    for (int k = 0; k < 2; ++k) {
+      for (cudaEvent_t e : s.begin[k]) s.pool.push_back(e);
+      for (cudaEvent_t e : s.end[k]) s.pool.push_back(e);
+      s.begin[k].clear();
+      s.end[k].clear();
+      s.launches[k] = 0;
+    }
+  }
+  return TN_OK;
+}
+
 
 int tn_version(void) { return 100; }
 const char* tn_last_error(void) { return tn::last_error().c_str(); }

@@ -55,6 +55,17 @@ bool make_bn(DeviceArena& arena, const float* gamma, const float* beta, const fl
 // Pack OIHW fp32 weights (Cout,Cin,R,S) into per-(n_tile, K-chunk) swizzled bf16 blobs.
 bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out);
 
+// ---- optional per-launch device timing (bench.py roofline): CUDA events on the launch stream around each kernel.
+enum ProfKind : int { kProfConvGemm = 0, kProfOther = 1 };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+struct ProfScope {
+  int kind;
+  cudaStream_t st;
+  ProfScope(int k, cudaStream_t s) : kind(k), st(s) { prof_begin(kind, st); }
+  ~ProfScope() { prof_end(kind, st); }
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace tn

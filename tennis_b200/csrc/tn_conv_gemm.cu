@@ -20,6 +20,7 @@
 // input feeds a 1x1 conv -- avg-pool and a 1x1 conv commute, so the GEMM runs on 4x fewer rows),
 // STEM (7x7/2 on a channel-padded NHWC4 image; K-chunk = two filter rows of 8 px * 4 ch).
 #include "tn_conv_gemm.h"
+#include "tn_common.h"
 #include "tn_ptx.cuh"
 
 #include <stdio.h>
@@ -407,6 +408,7 @@ size_t conv_gemm_wpack_bytes(int cout, int num_chunks) {
 }
 
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, cudaStream_t stream) {
+  ProfScope prof_scope(kProfConvGemm, stream);
   switch (conv_gemm_pick_bn(p.Cout)) {
     case 32: return launch_bn<32>(p, stream);
     case 64: return launch_bn<64>(p, stream);

@@ -1,6 +1,7 @@
 // HBM-bound helpers around the conv GEMMs: layout conversion, max-pool, the BN+ReLU+avg-pool tail,
 // small dense layers and temporal pooling.  All are 16-byte-vectorised, coalesced along channels.
 #include "tn_elementwise.h"
+#include "tn_common.h"
 #include "tn_ptx.cuh"
 
 namespace tn {
@@ -42,6 +43,7 @@ cudaError_t launch_convert_nchw_f32(const float* in, __nv_bfloat16* out, int n, 
   float s[3] = {1, 1, 1}, b[3] = {0, 0, 0};
   if (scale3) { s[0] = scale3[0]; s[1] = scale3[1]; s[2] = scale3[2]; }
   if (shift3) { b[0] = shift3[0]; b[1] = shift3[1]; b[2] = shift3[2]; }
+  ProfScope prof_scope(kProfOther, st);
   convert_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, total, h * w, s[0], s[1],
                                                                                       s[2], b[0], b[1], b[2]);
   return cudaGetLastError();
@@ -51,6 +53,7 @@ cudaError_t launch_convert_nhwc_u8(const uint8_t* in, __nv_bfloat16* out, int n,
                                    const float* shift3, cudaStream_t st) {
   size_t total = static_cast<size_t>(n) * h * w;
   if (total == 0) return cudaSuccess;
+  ProfScope prof_scope(kProfOther, st);
   convert_nhwc_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
       in, out, total, scale3[0], scale3[1], scale3[2], shift3[0], shift3[1], shift3[2]);
   return cudaGetLastError();
@@ -97,6 +100,7 @@ cudaError_t launch_maxpool3s2(const __nv_bfloat16* in, __nv_bfloat16* out, int n
                               int out_cstride, int out_coff, cudaStream_t st) {
   size_t total = static_cast<size_t>(n) * Ho * Wo * (C / 8);
   if (total == 0) return cudaSuccess;
+  ProfScope prof_scope(kProfOther, st);
   maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, out, n, H, W, C, Ho, Wo, out_cstride,
                                                                                out_coff);
   return cudaGetLastError();
@@ -154,6 +158,7 @@ cudaError_t launch_tail_pool(const __nv_bfloat16* in, int n, int H, int W, int C
                              cudaStream_t st) {
   size_t total = static_cast<size_t>(n) * ph * pw * (C / 8);
   if (total == 0) return cudaSuccess;
+  ProfScope prof_scope(kProfOther, st);
   tail_pool_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(in, n, H, W, C, cstride, kh, kw, ph, pw,
                                                                               scale, shift, feats, feats_bf16);
   return cudaGetLastError();
@@ -193,6 +198,7 @@ cudaError_t launch_dense(const float* x, const float* W, const float* b, float* 
                          cudaStream_t st) {
   size_t total = static_cast<size_t>(rows) * out_dim;
   if (total == 0) return cudaSuccess;
+  ProfScope prof_scope(kProfOther, st);
   dense_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, st>>>(x, W, b, y, rows, in_dim, out_dim);
   return cudaGetLastError();
 }
@@ -215,6 +221,7 @@ __global__ void temporal_pool_kernel(const float* __restrict__ x, float* __restr
 cudaError_t launch_temporal_pool(const float* x, float* y, int B, int T, int D, int mean, cudaStream_t st) {
   size_t total = static_cast<size_t>(B) * D;
   if (total == 0) return cudaSuccess;
+  ProfScope prof_scope(kProfOther, st);
   temporal_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, y, B, T, D, mean);
   return cudaGetLastError();
 }
@@ -232,6 +239,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 cudaError_t launch_cast_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   size_t threads = (n + 3) / 4;
+  ProfScope prof_scope(kProfOther, st);
   cast_bf16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(x, y, n);
   return cudaGetLastError();
 }

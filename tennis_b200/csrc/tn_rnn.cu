@@ -13,6 +13,8 @@
 // the returned state is the one after step len[b]-1.
 #include "tn_rnn.h"
 
+#include "tn_common.h"
+
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -224,6 +226,7 @@ cudaError_t launch_rnn_scan(const RnnScanParams& p, cudaStream_t st) {
   const int G = p.gates;
   const int cl = rnn_scan_cluster_size(G, p.H);
   if (cl < 0 || (G != 3 && G != 4)) return cudaErrorInvalidValue;
+  ProfScope prof_scope(kProfOther, st);
   if (G == 3) {
     switch (cl) {
       case 1: return launch_t<3, 1>(p, st);

@@ -40,9 +40,12 @@ class Conv:
                                    mode, dptr(keep[1]), dptr(keep[2]), dptr(keep[3]), dptr(keep[4])))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().tn_conv_destroy(self._h)
-            self._h = c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().tn_conv_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
 
     def out_hw(self, H, W, stride, pad):
         if self.mode == _lib.MODE_POOL2:
@@ -89,9 +92,12 @@ class Backbone:
         self._ws_key = None
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().tn_backbone_destroy(self._h)
-            self._h = c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().tn_backbone_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
 
     def feature_dim(self, h, w):
         return lib().tn_backbone_feature_dim(self.arch, h, w)
@@ -175,9 +181,12 @@ class BiRNN:
         self._ws_bytes = 0
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().tn_birnn_destroy(self._h)
-            self._h = c_void_p()
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().tn_birnn_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
 
     def __call__(self, x, valid_len=None, want_y=True, want_max=False, want_state=False):
         """x: (B,T,D) fp32 or bf16 cuda.  Returns dict(y, ymax, h, c) with the requested entries."""
