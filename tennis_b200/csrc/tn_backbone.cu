@@ -8,6 +8,7 @@
 #include <memory>
 
 #include "tn_common.h"
+#include "tn_conv3x3.h"
 #include "tn_elementwise.h"
 
 namespace {
@@ -17,6 +18,7 @@ using namespace tn;
 struct DenseLayer {
   BnDev bn1, bn2;
   ConvDev conv1, conv2;
+  Conv3x3Dev conv2h;  // same weights, packed for the halo kernel
   int cin;
 };
 struct Transition {
@@ -49,6 +51,7 @@ struct tn_backbone {
   std::vector<ResBlock> rblocks;
   tn::BnDev bn_final;
   int feat_channels = 0;
+  int num_sms = 148;
 };
 
 namespace {
@@ -211,7 +214,8 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
   if (!densenet_plan(h, w, &pl)) return set_error(TN_ERR_INVALID, "input %dx%d too small for DenseNet-121", h, w);
   const Dims& d = pl.d;
   __nv_bfloat16* stem = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * d.Hs * d.Ws * 64);
-  __nv_bfloat16* bott = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * pl.Hb[0] * pl.Wb[0] * kBott);
+  // bottleneck buffer: zero-padded (n, H+2, W+2, 128) layout for the halo 3x3 kernel
+  __nv_bfloat16* bott = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * (pl.Hb[0] + 2) * (pl.Wb[0] + 2) * kBott);
   __nv_bfloat16* blk[4];
   for (int b = 0; b < 4; ++b) blk[b] = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * pl.Hb[b] * pl.Wb[b] * pl.ctot[b]);
   if (dry) return TN_OK;
@@ -224,13 +228,20 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
   }
   for (int b = 0; b < 4; ++b) {
     const int H = pl.Hb[b], W = pl.Wb[b], ct = pl.ctot[b];
+    const bool halo = conv3x3_halo_supported(H, W) && static_cast<long long>(n) * (H + 2) * (W + 2) < (1ll << 31) - 4096;
+    if (halo) TN_CUDA(launch_zero_border(bott, n, H + 2, W + 2, kBott, st));
     for (const DenseLayer& L : bb->layers[b]) {
       // BN1+ReLU (prologue) -> 1x1 conv -> BN2+ReLU (epilogue) -> bottleneck
       ConvGemmParams p1 = conv_params(L.conv1, blk[b], ct, n, H, W, H, W, 1, 0, &L.bn1, bott, kBott, 0, &L.bn2, true);
+      p1.out_pad = halo ? 1 : 0;
       TN_CUDA(launch_conv_gemm(p1, st));
       // 3x3 conv, 32 new channels written in place at channel offset cin
-      ConvGemmParams p2 = conv_params(L.conv2, bott, kBott, n, H, W, H, W, 1, 1, nullptr, blk[b], ct, L.cin, nullptr, false);
-      TN_CUDA(launch_conv_gemm(p2, st));
+      if (halo) {
+        TN_CUDA(launch_conv3x3_halo(L.conv2h, bott, n, H, W, blk[b], ct, L.cin, bb->num_sms, st));
+      } else {
+        ConvGemmParams p2 = conv_params(L.conv2, bott, kBott, n, H, W, H, W, 1, 1, nullptr, blk[b], ct, L.cin, nullptr, false);
+        TN_CUDA(launch_conv_gemm(p2, st));
+      }
     }
     if (b < 3) {
       // transition: BN+ReLU -> 1x1 conv -> avgpool 2x2, computed as conv1x1(avgpool(relu(bn(x))))
@@ -352,6 +363,7 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
   std::unique_ptr<tn_backbone> bb(new tn_backbone);
   bb->arch = arch;
   bb->device = device;
+  TN_CUDA(cudaDeviceGetAttribute(&bb->num_sms, cudaDevAttrMultiProcessorCount, device));
   Cursor cur{params, n_params};
   bool ok = true;
   if (arch == TN_ARCH_DENSENET121) {
@@ -365,7 +377,9 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
         ok = ok && take_bn(cur, bb->arena, c, &L.bn1);
         ok = ok && take_conv(cur, bb->arena, kBott, c, 1, 1, tn::kModeConv, &L.conv1);
         ok = ok && take_bn(cur, bb->arena, kBott, &L.bn2);
+        const float* w2 = cur.p;
         ok = ok && take_conv(cur, bb->arena, kGrowth, kBott, 3, 3, tn::kModeConv, &L.conv2);
+        ok = ok && make_conv3x3(bb->arena, w2, &L.conv2h);
         bb->layers[b].push_back(L);
         c += kGrowth;
       }

@@ -309,6 +309,15 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvGemmParam
   {
     const int m = m0 + warp * 32 + lane;
     const bool row_ok = m < p.M;
+    size_t orow = static_cast<size_t>(m);  // output row (pixel) index
+    if (p.out_pad && row_ok) {
+      const int hw = p.Ho * p.Wo;
+      const int f = m / hw;
+      const int rem = m - f * hw;
+      const int oy = rem / p.Wo;
+      const int ox = rem - oy * p.Wo;
+      orow = (static_cast<size_t>(f) * (p.Ho + 2) + oy + 1) * (p.Wo + 2) + ox + 1;
+    }
     const int ncol_tile = min(BN, p.Cout - n_tile * BN);
     for (int cb = 0; cb * 32 < ncol_tile; ++cb) {
       uint32_t v[32];
@@ -346,13 +355,12 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvGemmParam
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (p.out_fp32) {
-          float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_cstride +
+          float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_cstride +
                                                 p.out_coff + n0);
 #pragma unroll
           for (int q = 0; q < 8; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         } else {
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) +
-                                              static_cast<size_t>(m) * p.out_cstride + p.out_coff + n0);
+          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_cstride + p.out_coff + n0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             o[q] = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),

@@ -34,6 +34,7 @@ struct ConvGemmParams {
   int out_cstride;
   int out_coff;
   int out_fp32;  // 0 -> bf16, 1 -> fp32
+  int out_pad;   // 1 -> output rows address a zero-padded (F, Ho+2, Wo+2, C) buffer (interior pixels only)
   int Cout;      // multiple of 32
   // epilogue: y = relu?(acc * scale[n] + shift[n] + residual)
   const float* epi_scale;
