@@ -1,44 +1,63 @@
 // Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM).
 //
-// One kernel covers every contraction on the CNN path (SURVEY.md §2.2 K1/K2 and the GRU input
-// projection of K4):  D[M = pixels, N = C_out] = A[M, K = taps*C_in] * W[N, K]^T
-//   * A is never materialised: 128 producer threads gather the NHWC bf16 activation rows for one
-//     (tap, 64-channel) K-chunk straight from HBM/L2 with 16-byte loads, apply the *consumer's*
-//     pre-activation BatchNorm+ReLU in registers (DenseNet/ResNet-v2 put BN+ReLU in front of every
-//     conv, so it cannot be folded into the producer layer), and write the chunk into shared memory in
-//     the UMMA 128-byte-swizzled K-major layout.
-//   * W is pre-packed on the host into exactly that shared-memory image, one contiguous blob per
-//     K-chunk, and brought in with a single bulk async copy (TMA engine, UBLKCP) that signals an
-//     mbarrier with its byte count.
-//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x (chunk/16) and commits to the
-//     stage's "empty" mbarrier; the ring is NSTAGE deep.
-//   * epilogue: tcgen05.ld the fp32 accumulators, apply the folded BN2 scale/shift (+ReLU) or bias,
-//     optional residual add, and store bf16/fp32 NHWC at a channel offset -> DenseNet's concat is
-//     "write your 32 channels into the block buffer in place".
+// One kernel covers every contraction on the CNN path that needs a *transformed* A operand (SURVEY.md §2.2
+// K1/K2 and the GRU input projection of K4):  D[M = pixels, N = C_out] = A[M, K = taps*C_in] * W[N, K]^T
 //
-// Modes: CONV (generic RxS, stride, zero padding), POOL2 (transition: 2x2 average of the activated
-// input feeds a 1x1 conv -- avg-pool and a 1x1 conv commute, so the GEMM runs on 4x fewer rows),
-// STEM (7x7/2 on a channel-padded NHWC4 image; K-chunk = two filter rows of 8 px * 4 ch).
+// Persistent, warp-specialised CTA (one per SM), 13 warps:
+//   warps 0-7   PRODUCERS  gather the NHWC bf16 activation rows of one (tap, 64-channel) K-chunk from HBM/L2 with
+//               16-byte loads (3 chunks in flight per thread), apply the *consumer's* pre-activation BatchNorm+ReLU
+//               in fp32 registers (DenseNet/ResNet-v2 put BN+ReLU in front of every conv, so it cannot be folded into
+//               the producing layer) and write the chunk into shared memory in the UMMA 128-byte-swizzled K-major
+//               layout; one elected lane per warp arrives on the stage's "full" mbarrier.
+//               W is pre-packed on the host into exactly that shared-memory image; it is either kept RESIDENT in
+//               shared memory for the whole kernel (K <= 256: loaded once per CTA) or streamed through the stage ring,
+//               in both cases by bulk async copies (TMA engine, UBLKCP) that signal an mbarrier with their byte count.
+//   warp 8      MMA ISSUER one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x (chunk/16), commits each
+//               stage to its "empty" mbarrier and each finished tile to "acc_full".  Accumulators are double-buffered
+//               in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 9-12  EPILOGUE   tcgen05.ld -> per-warp shared-memory staging (row-per-thread -> coalesced re-read) ->
+//               folded BN2 scale/shift (+residual) (+ReLU) -> bf16/fp32 NHWC stores at a channel offset (DenseNet's
+//               concat is "write your channels into the block buffer in place"), optionally into a zero-padded
+//               (H+2, W+2) layout for the halo 3x3 kernel.
+//
+// Modes: CONV (generic RxS, stride, zero padding), POOL2 (transition: 2x2 average of the activated input feeds a
+// 1x1 conv -- avg-pool and a 1x1 conv commute, so the GEMM runs on 4x fewer rows), STEM (7x7/2 on a channel-padded
+// NHWC4 image; K-chunk = two filter rows of 8 px * 4 ch).
 #include "tn_conv_gemm.h"
-#include "tn_common.h"
-#include "tn_ptx.cuh"
 
 #include <stdio.h>
+
+#include "tn_common.h"
+#include "tn_ptx.cuh"
 
 namespace tn {
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kProducerWarps = 8;
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kEpiWarp0 = kProducerWarps + 1;
+constexpr int kEpiWarps = 4;  // one per TMEM lane quarter (13 warps total keeps 128 registers per thread)
+constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps) * 32;  // 416
 constexpr int kBM = 128;
-constexpr int kABytes = kBM * 128;  // 128 rows x 64 bf16
+constexpr int kABytes = kBM * 128;          // 128 rows x 64 bf16
+constexpr int kRowsPerThread = 4;           // 128 rows x 8 groups / 256 threads
+constexpr int kStageRowBytes = 144;         // epilogue staging: 32 fp32 + 16 B pad per row
+constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowBytes;
+constexpr int kMaxResidentChunks = 4;
+constexpr int kSmemLimit = 227 * 1024;
 
-template <int BN>
+template <int BN, bool RESIDENT>
 struct Cfg {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kNStage = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
-  static constexpr int kSmem = kNStage * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStage = RESIDENT ? kABytes : (kABytes + kBBytes);
+  static constexpr int kFixed = 1024 /*align*/ + kStagingBytes + 2 * BN * 4 /*epi scale/shift*/ + 512 /*barriers*/ +
+                                (RESIDENT ? kMaxResidentChunks * kBBytes : 0);
+  static constexpr int kNStageRaw = (kSmemLimit - kFixed) / kStage;
+  static constexpr int kNStage = kNStageRaw > 8 ? 8 : kNStageRaw;
+  static constexpr int kSmem = kFixed + kNStage * kStage;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(kNStage >= 3, "not enough shared memory for the stage ring");
 };
 
 __device__ __forceinline__ uint4 ldg128(const void* p) {
@@ -57,32 +76,48 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-
-// y = relu?(x*scale+shift) on 8 packed bf16
-__device__ __forceinline__ uint4 bn_act8(uint4 x, const float (&sc)[8], const float (&sh)[8], bool relu) {
-  uint32_t in[4] = {x.x, x.y, x.z, x.w};
-  uint32_t out[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 f = unpack_bf16x2(in[j]);
-    float a = fmaf(f.x, sc[2 * j], sh[2 * j]);
-    float b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-    if (relu) {
-      a = fmaxf(a, 0.f);
-      b = fmaxf(b, 0.f);
-    }
-    out[j] = pack_bf16x2(a, b);
-  }
-  return make_uint4(out[0], out[1], out[2], out[3]);
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
-__device__ __forceinline__ void bn_act8_accum(uint4 x, const float (&sc)[8], const float (&sh)[8], bool relu,
-                                              float (&acc)[8]) {
-  uint32_t in[4] = {x.x, x.y, x.z, x.w};
+// pack two fp32 into bf16x2 (lo = a, hi = b), optionally with ReLU fused into the conversion
+__device__ __forceinline__ uint32_t cvt_pack(float a, float b, bool relu) {
+  uint32_t r;
+  if (relu)
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+struct ScaleShift8 {
+  float sc[8], sh[8];
+};
+__device__ __forceinline__ void load_ss8(const float* scale, const float* shift, int ch, ScaleShift8& s) {
+  const float4* s4 = reinterpret_cast<const float4*>(scale + ch);
+  const float4* h4 = reinterpret_cast<const float4*>(shift + ch);
+  float4 s0 = __ldg(s4), s1 = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
+  s.sc[0] = s0.x; s.sc[1] = s0.y; s.sc[2] = s0.z; s.sc[3] = s0.w; s.sc[4] = s1.x; s.sc[5] = s1.y; s.sc[6] = s1.z; s.sc[7] = s1.w;
+  s.sh[0] = h0.x; s.sh[1] = h0.y; s.sh[2] = h0.z; s.sh[3] = h0.w; s.sh[4] = h1.x; s.sh[5] = h1.y; s.sh[6] = h1.z; s.sh[7] = h1.w;
+}
+// y = relu?(x*scale+shift) on 8 packed bf16, fp32 math, single rounding back to bf16
+__device__ __forceinline__ uint4 bn_act8(uint4 x, const ScaleShift8& s, bool relu) {
+  uint4 o;
+  o.x = cvt_pack(fmaf(bf_lo(x.x), s.sc[0], s.sh[0]), fmaf(bf_hi(x.x), s.sc[1], s.sh[1]), relu);
+  o.y = cvt_pack(fmaf(bf_lo(x.y), s.sc[2], s.sh[2]), fmaf(bf_hi(x.y), s.sc[3], s.sh[3]), relu);
+  o.z = cvt_pack(fmaf(bf_lo(x.z), s.sc[4], s.sh[4]), fmaf(bf_hi(x.z), s.sc[5], s.sh[5]), relu);
+  o.w = cvt_pack(fmaf(bf_lo(x.w), s.sc[6], s.sh[6]), fmaf(bf_hi(x.w), s.sc[7], s.sh[7]), relu);
+  return o;
+}
+__device__ __forceinline__ void bn_act8_accum(uint4 x, const ScaleShift8& s, bool relu, float (&acc)[8]) {
+  const uint32_t in[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float2 f = unpack_bf16x2(in[j]);
-    float a = fmaf(f.x, sc[2 * j], sh[2 * j]);
-    float b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+    float a = fmaf(bf_lo(in[j]), s.sc[2 * j], s.sh[2 * j]);
+    float b = fmaf(bf_hi(in[j]), s.sc[2 * j + 1], s.sh[2 * j + 1]);
     if (relu) {
       a = fmaxf(a, 0.f);
       b = fmaxf(b, 0.f);
@@ -92,310 +127,427 @@ __device__ __forceinline__ void bn_act8_accum(uint4 x, const float (&sc)[8], con
   }
 }
 
-template <int BN, int MODE>
-__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const ConvGemmParams p) {
-  using C = Cfg<BN>;
+template <int BN, int MODE, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmParams p) {
+  using C = Cfg<BN, RESIDENT>;
+  constexpr int NS = C::kNStage;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  const uint32_t smem_base = smem_u32(smem);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kNStage * C::kStage);
-  uint64_t* empty_bar = full_bar + C::kNStage;
-  uint64_t* accum_bar = empty_bar + C::kNStage;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sStage = smem;                                        // NS x kStage  (A [+ B])
+  uint8_t* sBres = sStage + NS * C::kStage;                      // resident weights (RESIDENT only)
+  uint8_t* sStaging = sBres + (RESIDENT ? kMaxResidentChunks * C::kBBytes : 0);
+  float* sEpiScale = reinterpret_cast<float*>(sStaging + kStagingBytes);
+  float* sEpiShift = sEpiScale + BN;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpiShift + BN);  // [NS]
+  uint64_t* empty_bar = full_bar + NS;                              // [NS]
+  uint64_t* acc_full = empty_bar + NS;                              // [2]
+  uint64_t* acc_empty = acc_full + 2;                               // [2]
+  uint64_t* w_full = acc_empty + 2;                                 // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  const int n_tile = blockIdx.y;
+  const int num_m_tiles = (p.M + kBM - 1) / kBM;
+  const int nchunks = p.num_chunks;
 
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < C::kNStage; ++s) {
-      mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], kProducerWarps + (RESIDENT ? 0 : 1));
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps);
+    }
+    mbar_init(w_full, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc<BN>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<C::kTmemCols>(tmem_slot);
+  // epilogue constants of this N tile
+  for (int i = tid; i < BN; i += kThreads) {
+    const int n = n_tile * BN + i;
+    sEpiScale[i] = (p.epi_scale != nullptr && n < p.Cout) ? p.epi_scale[n] : 1.f;
+    sEpiShift[i] = (p.epi_shift != nullptr && n < p.Cout) ? p.epi_shift[n] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint8_t* wtile = p.wpack + static_cast<size_t>(n_tile) * nchunks * C::kBBytes;
 
-  const int m0 = blockIdx.x * kBM;
-  const int n_tile = blockIdx.y;
-  const uint8_t* wtile = p.wpack + static_cast<size_t>(n_tile) * p.num_chunks * C::kBBytes;
-
-  // ---- per-thread producer geometry: rows (tid>>3)+16*i, 16-byte K-group g = tid&7
-  const int g = tid & 7;
-  const int rbase = tid >> 3;
-  const uint32_t a_off = static_cast<uint32_t>(rbase * 128 + ((g ^ (rbase & 7)) << 4));  // + i*2048
-  int pix[8];  // input pixel index of the (0,0) tap
-  int pos[8];  // (iy0 << 16) | (ix0 & 0xffff)
-  {
+  if (warp < kProducerWarps) {
+    // ================================================================ PRODUCERS
+    if (RESIDENT && tid == 0) {
+      mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nchunks * C::kBBytes));
+      for (int c = 0; c < nchunks; ++c)
+        bulk_g2s(sBres + c * C::kBBytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, w_full);
+    }
+    const int g = tid & 7;
+    const int rbase = tid >> 3;  // 0..31 ; rows rbase + 32*i
+    const uint32_t a_off = static_cast<uint32_t>(rbase * 128 + ((g ^ (rbase & 7)) << 4));  // + i*4096
+    const bool has_pro = p.pro_scale != nullptr;
+    const bool pro_relu = p.pro_relu != 0;
     const int hw = p.Ho * p.Wo;
+
+    constexpr int PD = (MODE == kModePool2) ? 1 : 3;  // chunks of global loads in flight per thread
+    constexpr int NL = (MODE == kModePool2) ? 4 : 1;  // 16-byte loads per row unit
+    uint4 regs[PD][kRowsPerThread][NL];
+    uint32_t okmask[PD];
+
+    // load cursor (runs PD items ahead of the store cursor)
+    int l_tile = blockIdx.x, l_c = 0;
+    int pix[kRowsPerThread], pos[kRowsPerThread];
+    // 1x1 / stride 1 / no padding: input pixel == output pixel, no div/mod needed
+    const bool ident = (MODE == kModeConv) && p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0;
+    auto set_geometry = [&](int tile) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rbase + 16 * i;
-      if (m < p.M) {
-        const int f = m / hw;
-        const int rem = m - f * hw;
-        const int oy = rem / p.Wo;
-        const int ox = rem - oy * p.Wo;
-        const int iy0 = oy * p.stride - p.pad;
-        const int ix0 = ox * p.stride - p.pad;
-        pix[i] = (f * p.H + iy0) * p.W + ix0;
-        pos[i] = (iy0 << 16) | (ix0 & 0xffff);
-      } else {
-        pix[i] = 0;
-        pos[i] = (-20000 << 16);  // every tap out of bounds -> zero row
-      }
-    }
-  }
-
-  const uint32_t idesc = umma_idesc_bf16_m128(BN);
-  const bool has_pro = p.pro_scale != nullptr;
-  const bool pro_relu = p.pro_relu != 0;
-
-  uint4 regs[8];
-  uint32_t okmask = 0;
-
-  // Issue the global loads of chunk c into registers (MODE CONV / STEM); consumed one iteration later.
-  auto load_chunk = [&](int c) {
-    okmask = 0;
-    if (MODE == kModeConv) {
-      const int tap = c / p.chunks_per_tap;
-      const int kc = (c - tap * p.chunks_per_tap) * 64;
-      const int r = tap / p.S;
-      const int s = tap - r * p.S;
-      const int ch = kc + g * 8;
-      const bool ch_ok = ch < p.Cin;
-      const int dpix = r * p.W + s;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int iy = (pos[i] >> 16) + r;
-        const int ix = static_cast<int>(static_cast<short>(pos[i] & 0xffff)) + s;
-        const bool ok = ch_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        if (ok) {
-          regs[i] = ldg128(p.in + static_cast<size_t>(pix[i] + dpix) * p.in_cstride + ch);
-          okmask |= 1u << i;
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const int m = tile * kBM + rbase + 32 * i;
+        if (ident && m < p.M) {
+          pix[i] = m;
+          pos[i] = 0;
+        } else if (m < p.M) {
+          const int f = m / hw;
+          const int rem = m - f * hw;
+          const int oy = rem / p.Wo;
+          const int ox = rem - oy * p.Wo;
+          const int iy0 = oy * p.stride - p.pad;
+          const int ix0 = ox * p.stride - p.pad;
+          pix[i] = (f * p.H + iy0) * p.W + ix0;
+          pos[i] = (iy0 << 16) | (ix0 & 0xffff);
         } else {
-          regs[i] = make_uint4(0, 0, 0, 0);
+          pix[i] = 0;
+          pos[i] = (-20000 << 16);  // every tap out of bounds -> zero row
         }
       }
-    } else if (MODE == kModeStem) {
-      // chunk c = filter rows 2c, 2c+1 ; group g -> row 2c+(g>>2), pixels ix0+2*(g&3), +1 ; 4 ch (8 B) per pixel
-      const int r = 2 * c + (g >> 2);
-      const int s = 2 * (g & 3);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int iy = (pos[i] >> 16) + r;
-        const int ix = static_cast<int>(static_cast<short>(pos[i] & 0xffff)) + s;
-        const bool row_ok = r < p.R && iy >= 0 && iy < p.H;
-        uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
-        const __nv_bfloat16* src = p.in + static_cast<size_t>(pix[i] + r * p.W + s) * 4;
-        if (row_ok && ix >= 0 && ix < p.W) a = ldg64(src);
-        if (row_ok && ix + 1 >= 0 && ix + 1 < p.W) b = ldg64(src + 4);
-        regs[i] = make_uint4(a.x, a.y, b.x, b.y);
-      }
-    }
-  };
+    };
+    if (l_tile < num_m_tiles) set_geometry(l_tile);
 
-  auto store_chunk = [&](int c, uint32_t a_stage) {
-    if (MODE == kModeConv) {
-      float sc[8], sh[8];
-      if (has_pro) {
-        const int kc = (c % p.chunks_per_tap) * 64;
+    auto load_item = [&](uint4 (&r)[kRowsPerThread][NL], uint32_t& ok) {
+      const int c = l_c;
+      ok = 0;
+      if (MODE == kModeConv) {
+        const int tap = c / p.chunks_per_tap;
+        const int kc = (c - tap * p.chunks_per_tap) * 64;
+        const int fr = tap / p.S;
+        const int fs = tap - fr * p.S;
         const int ch = kc + g * 8;
-        if (ch < p.Cin) {
-          const float4* s4 = reinterpret_cast<const float4*>(p.pro_scale + ch);
-          const float4* h4 = reinterpret_cast<const float4*>(p.pro_shift + ch);
-          float4 s0 = __ldg(s4), s1 = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
-          sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-          sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+        const bool ch_ok = ch < p.Cin;
+        const int dpix = fr * p.W + fs;
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          const int iy = (pos[i] >> 16) + fr;
+          const int ix = static_cast<int>(static_cast<short>(pos[i] & 0xffff)) + fs;
+          const bool v = ch_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+          if (v) {
+            r[i][0] = ldg128(p.in + static_cast<size_t>(pix[i] + dpix) * p.in_cstride + ch);
+            ok |= 1u << i;
+          } else {
+            r[i][0] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      } else if (MODE == kModeStem) {
+        // chunk c = filter rows 2c, 2c+1 ; group g -> row 2c+(g>>2), pixels ix0+2*(g&3), +1 ; 4 ch (8 B) per pixel
+        const int fr = 2 * c + (g >> 2);
+        const int fs = 2 * (g & 3);
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          const int iy = (pos[i] >> 16) + fr;
+          const int ix = static_cast<int>(static_cast<short>(pos[i] & 0xffff)) + fs;
+          const bool row_ok = fr < p.R && iy >= 0 && iy < p.H;
+          uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
+          const __nv_bfloat16* src = p.in + static_cast<size_t>(pix[i] + fr * p.W + fs) * 4;
+          if (row_ok && ix >= 0 && ix < p.W) a = ldg64(src);
+          if (row_ok && ix + 1 >= 0 && ix + 1 < p.W) b = ldg64(src + 4);
+          r[i][0] = make_uint4(a.x, a.y, b.x, b.y);
+        }
+      } else {  // kModePool2: four pixels of the 2x2 window
+        const int ch = c * 64 + g * 8;
+        const bool ch_ok = ch < p.Cin;
+        const size_t rowstep = static_cast<size_t>(p.W) * p.in_cstride;
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          if (ch_ok && (pos[i] >> 16) >= 0) {
+            const __nv_bfloat16* src = p.in + static_cast<size_t>(pix[i]) * p.in_cstride + ch;
+            r[i][0] = ldg128(src);
+            r[i][NL > 1 ? 1 : 0] = ldg128(src + p.in_cstride);
+            r[i][NL > 2 ? 2 : 0] = ldg128(src + rowstep);
+            r[i][NL > 3 ? 3 : 0] = ldg128(src + rowstep + p.in_cstride);
+            ok |= 1u << i;
+          }
+        }
+      }
+      // advance the load cursor
+      if (++l_c == nchunks) {
+        l_c = 0;
+        l_tile += gridDim.x;
+        if (l_tile < num_m_tiles) set_geometry(l_tile);
+      }
+    };
+
+    const int my_tiles = (blockIdx.x < num_m_tiles) ? (num_m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int nitems = my_tiles * nchunks;
+
+    int s_c = 0, s_stage = 0;
+    uint32_t s_phase = 1;  // parity to wait for on the stage's "empty" barrier (first pass over the ring: free)
+    auto store_item = [&](const uint4 (&r)[kRowsPerThread][NL], uint32_t ok) {
+      const int c = s_c;
+      const int stage = s_stage;
+      mbar_wait(&empty_bar[stage], s_phase);  // UMMAs that read this stage have retired
+      uint8_t* st_base = sStage + stage * C::kStage;
+      const uint32_t a_stage = smem_u32(st_base);
+      if (!RESIDENT && tid == 0) {
+        mbar_arrive_expect_tx(&full_bar[stage], C::kBBytes);
+        bulk_g2s(st_base + kABytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &full_bar[stage]);
+      }
+      if (MODE == kModeConv) {
+        if (has_pro) {
+          const int ch = (c % p.chunks_per_tap) * 64 + g * 8;
+          ScaleShift8 ss;
+          if (ch < p.Cin) load_ss8(p.pro_scale, p.pro_shift, ch, ss);
+#pragma unroll
+          for (int i = 0; i < kRowsPerThread; ++i) {
+            uint4 v = r[i][0];
+            if ((ok >> i) & 1u) v = bn_act8(v, ss, pro_relu);
+            sts128(a_stage + a_off + i * 4096, v);
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 0.f; }
+          for (int i = 0; i < kRowsPerThread; ++i) sts128(a_stage + a_off + i * 4096, r[i][0]);
+        }
+      } else if (MODE == kModeStem) {
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) sts128(a_stage + a_off + i * 4096, r[i][0]);
+      } else {
+        const int ch = c * 64 + g * 8;
+        ScaleShift8 ss;
+        if (ch < p.Cin) load_ss8(p.pro_scale, p.pro_shift, ch, ss);
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          uint4 out = make_uint4(0, 0, 0, 0);
+          if ((ok >> i) & 1u) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < NL; ++q) bn_act8_accum(r[i][q], ss, pro_relu, acc);
+            out.x = cvt_pack(acc[0] * 0.25f, acc[1] * 0.25f, false);
+            out.y = cvt_pack(acc[2] * 0.25f, acc[3] * 0.25f, false);
+            out.z = cvt_pack(acc[4] * 0.25f, acc[5] * 0.25f, false);
+            out.w = cvt_pack(acc[6] * 0.25f, acc[7] * 0.25f, false);
+          }
+          sts128(a_stage + a_off + i * 4096, out);
         }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint4 v = regs[i];
-        if (has_pro && ((okmask >> i) & 1u)) v = bn_act8(v, sc, sh, pro_relu);
-        sts128(a_stage + a_off + i * 2048, v);
+      fence_proxy_async_smem();  // my generic-proxy writes -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (++s_c == nchunks) s_c = 0;
+      if (++s_stage == NS) {
+        s_stage = 0;
+        s_phase ^= 1u;
       }
-    } else if (MODE == kModeStem) {
+    };
+
+    // software pipeline: PD items of loads in flight
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sts128(a_stage + a_off + i * 2048, regs[i]);
-    } else {  // kModePool2: 1x1 conv on the 2x2 average of the activated input (R=S=1, stride 2 geometry)
-      const int kc = c * 64;
-      const int ch = kc + g * 8;
-      const bool ch_ok = ch < p.Cin;
-      float sc[8], sh[8];
-      if (ch_ok) {
-        const float4* s4 = reinterpret_cast<const float4*>(p.pro_scale + ch);
-        const float4* h4 = reinterpret_cast<const float4*>(p.pro_shift + ch);
-        float4 s0 = __ldg(s4), s1 = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
-        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-        sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
-      } else {
+    for (int j = 0; j < PD; ++j)
+      if (j < nitems) load_item(regs[j], okmask[j]);
+    for (int base = 0; base < nitems; base += PD) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 0.f; }
-      }
-#pragma unroll 2
-      for (int i = 0; i < 8; ++i) {
-        uint4 out = make_uint4(0, 0, 0, 0);
-        if (ch_ok && (pos[i] >> 16) >= 0) {
-          const __nv_bfloat16* src = p.in + static_cast<size_t>(pix[i]) * p.in_cstride + ch;
-          const size_t rowstep = static_cast<size_t>(p.W) * p.in_cstride;
-          uint4 v00 = ldg128(src), v01 = ldg128(src + p.in_cstride);
-          uint4 v10 = ldg128(src + rowstep), v11 = ldg128(src + rowstep + p.in_cstride);
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          bn_act8_accum(v00, sc, sh, pro_relu, acc);
-          bn_act8_accum(v01, sc, sh, pro_relu, acc);
-          bn_act8_accum(v10, sc, sh, pro_relu, acc);
-          bn_act8_accum(v11, sc, sh, pro_relu, acc);
-          out.x = pack_bf16x2(acc[0] * 0.25f, acc[1] * 0.25f);
-          out.y = pack_bf16x2(acc[2] * 0.25f, acc[3] * 0.25f);
-          out.z = pack_bf16x2(acc[4] * 0.25f, acc[5] * 0.25f);
-          out.w = pack_bf16x2(acc[6] * 0.25f, acc[7] * 0.25f);
+      for (int j = 0; j < PD; ++j) {
+        const int idx = base + j;
+        if (idx < nitems) {
+          store_item(regs[j], okmask[j]);
+          if (idx + PD < nitems) load_item(regs[j], okmask[j]);
         }
-        sts128(a_stage + a_off + i * 2048, out);
       }
     }
-  };
-
-  // ---------------------------------------------------------------- main loop over K-chunks
-  const int nchunks = p.num_chunks;
-  if (MODE != kModePool2) load_chunk(0);
-  for (int c = 0; c < nchunks; ++c) {
-    const int stage = c % C::kNStage;
-    const int round = c / C::kNStage;
-    const uint32_t a_stage = smem_base + stage * C::kStage;
-    uint8_t* b_stage = smem + stage * C::kStage + kABytes;
-    if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1);  // UMMAs that read this stage are done
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&full_bar[stage], C::kBBytes);
-      bulk_g2s(b_stage, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &full_bar[stage]);
-    }
-    store_chunk(c, a_stage);
-    if (MODE != kModePool2 && c + 1 < nchunks) load_chunk(c + 1);  // in flight across the sync + MMA issue
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(&full_bar[stage], round & 1);  // weights landed
-      tc_fence_after();
-      int kv;
-      if (MODE == kModeStem) {
-        kv = (2 * c + 1 < p.R) ? 64 : 32;
-      } else {
-        const int kc = (c % p.chunks_per_tap) * 64;
-        kv = min(64, p.Cin - kc);
+  } else if (warp == kMmaWarp) {
+    // ================================================================ MMA ISSUER
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m128(BN);
+      if (RESIDENT) mbar_wait(w_full, 0);
+      int stage = 0, tcount = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++tcount) {
+        const int ab = tcount & 1;
+        mbar_wait(&acc_empty[ab], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * BN;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          int kv;
+          if (MODE == kModeStem) {
+            kv = (2 * c + 1 < p.R) ? 64 : 32;
+          } else {
+            const int kc = (c % p.chunks_per_tap) * 64;
+            kv = min(64, p.Cin - kc);
+          }
+          const uint32_t a_addr = smem_u32(sStage + stage * C::kStage);
+          const uint32_t b_addr = RESIDENT ? smem_u32(sBres + c * C::kBBytes) : a_addr + kABytes;
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db = umma_desc_sw128(b_addr);
+          for (int k = 0; k < kv / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&acc_full[ab]);
       }
-      const uint64_t da = umma_desc_sw128(a_stage);
-      const uint64_t db = umma_desc_sw128(a_stage + kABytes);
-      for (int k = 0; k < kv / 16; ++k) {
-        umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
-      }
-      umma_commit(&empty_bar[stage]);
-      if (c == nchunks - 1) umma_commit(accum_bar);
     }
-  }
-
-  // ---------------------------------------------------------------- epilogue
-  mbar_wait(accum_bar, 0);
-  tc_fence_after();
-  {
-    const int m = m0 + warp * 32 + lane;
-    const bool row_ok = m < p.M;
-    size_t orow = static_cast<size_t>(m);  // output row (pixel) index
-    if (p.out_pad && row_ok) {
-      const int hw = p.Ho * p.Wo;
-      const int f = m / hw;
-      const int rem = m - f * hw;
-      const int oy = rem / p.Wo;
-      const int ox = rem - oy * p.Wo;
-      orow = (static_cast<size_t>(f) * (p.Ho + 2) + oy + 1) * (p.Wo + 2) + ox + 1;
-    }
+  } else {
+    // ================================================================ EPILOGUE (TMEM lane quarter = warp % 4)
+    // kEpiWarps == 8: warps (e, e+4) share a lane quarter and split the tile's 32-column blocks between them.
+    const int ew = warp - kEpiWarp0;
+    const int qw = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t stg_addr = smem_u32(sStaging + ew * 32 * kStageRowBytes);
     const int ncol_tile = min(BN, p.Cout - n_tile * BN);
-    for (int cb = 0; cb * 32 < ncol_tile; ++cb) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + cb * 32, v);
-      tmem_ld_wait();
-      const int n0 = n_tile * BN + cb * 32;
-      if (row_ok) {
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.epi_scale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= __ldg(p.epi_scale + n0 + j);
+    const int ncb = (ncol_tile + 31) / 32;
+    const int ncb_half = (kEpiWarps == 8) ? (ncb + 1) / 2 : ncb;
+    const int cb_begin = half * ncb_half;
+    const int cb_end = min(ncb, cb_begin + ncb_half);
+    const bool relu = p.epi_relu != 0;
+    const bool has_scale = p.epi_scale != nullptr;
+    const int esz = p.out_fp32 ? 4 : 2;
+    const int cpg = p.out_fp32 ? 1 : 2;  // column blocks per 128-byte staging row
+    const int hw = p.Ho * p.Wo;
+    const int sub = lane & 7;            // phase B: 8 lanes x 16 B per row, 4 rows per instruction
+    const int rsel = lane >> 3;
+    uint8_t* out_base = static_cast<uint8_t*>(p.out) + (static_cast<size_t>(p.out_coff) + n_tile * BN) * esz + sub * 16;
+    const size_t out_row_bytes = static_cast<size_t>(p.out_cstride) * esz;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1;
+      // output row of MY accumulator row (lane); -1 = past the end
+      const int m = tile * kBM + qw * 32 + lane;
+      int orow = -1;
+      if (m < p.M) {
+        orow = m;
+        if (p.out_pad) {
+          const int f = m / hw;
+          const int rem = m - f * hw;
+          const int oy = rem / p.Wo;
+          const int ox = rem - oy * p.Wo;
+          orow = (f * (p.Ho + 2) + oy + 1) * (p.Wo + 2) + ox + 1;
         }
-        if (p.epi_shift != nullptr) {
+      }
+      mbar_wait(&acc_full[ab], (tcount >> 1) & 1);
+      tc_fence_after();
+      if (cb_begin >= cb_end) {  // nothing to read for this warp (narrow tile): release immediately
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        continue;
+      }
+      for (int cb0 = cb_begin; cb0 < cb_end; cb0 += cpg) {
+        // ---- phase A: my row -> 128-byte staging row, epilogue math applied, output dtype
+        for (int u = 0; u < cpg && cb0 + u < cb_end; ++u) {
+          const int cb = cb0 + u;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * BN + cb * 32, v);
+          tmem_ld_wait();
+          if (cb + 1 == cb_end) {  // last read of this accumulator by this warp: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          }
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __ldg(p.epi_shift + n0 + j);
-        }
-        if (p.res != nullptr) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + static_cast<size_t>(m) * p.res_cstride + n0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 rv = __ldg(r4 + q);
-            uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 t = unpack_bf16x2(w[j]);
-              f[q * 8 + 2 * j] += t.x;
-              f[q * 8 + 2 * j + 1] += t.y;
+          for (int q = 0; q < 8; ++q) {
+            const float4 sh = *reinterpret_cast<const float4*>(sEpiShift + cb * 32 + 4 * q);
+            if (has_scale) {
+              const float4 sc = *reinterpret_cast<const float4*>(sEpiScale + cb * 32 + 4 * q);
+              f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x);
+              f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y);
+              f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z);
+              f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w);
+            } else {
+              f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + sh.x;
+              f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + sh.y;
+              f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + sh.z;
+              f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + sh.w;
             }
           }
-        }
-        if (p.epi_relu) {
+          if (p.res != nullptr && m < p.M) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.res + static_cast<size_t>(m) * p.res_cstride + n_tile * BN + cb * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.out_fp32) {
-          float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.out_cstride +
-                                                p.out_coff + n0);
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = __ldg(r4 + q);
+              f[8 * q + 0] += bf_lo(rv.x); f[8 * q + 1] += bf_hi(rv.x); f[8 * q + 2] += bf_lo(rv.y); f[8 * q + 3] += bf_hi(rv.y);
+              f[8 * q + 4] += bf_lo(rv.z); f[8 * q + 5] += bf_hi(rv.z); f[8 * q + 6] += bf_lo(rv.w); f[8 * q + 7] += bf_hi(rv.w);
+            }
+          }
+          if (p.out_fp32) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        } else {
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.out_cstride + p.out_coff + n0);
+            for (int q = 0; q < 8; ++q) {
+              float a = f[4 * q], b = f[4 * q + 1], c = f[4 * q + 2], d = f[4 * q + 3];
+              if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); c = fmaxf(c, 0.f); d = fmaxf(d, 0.f); }
+              sts128(stg_addr + lane * kStageRowBytes + q * 16,
+                     make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d)));
+            }
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            o[q] = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
-                              pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+            for (int q = 0; q < 4; ++q)
+              sts128(stg_addr + lane * kStageRowBytes + u * 64 + q * 16,
+                     make_uint4(cvt_pack(f[8 * q], f[8 * q + 1], relu), cvt_pack(f[8 * q + 2], f[8 * q + 3], relu),
+                                cvt_pack(f[8 * q + 4], f[8 * q + 5], relu), cvt_pack(f[8 * q + 6], f[8 * q + 7], relu)));
           }
         }
+        __syncwarp();
+        // ---- phase B: coalesced 16-byte stores, 8 lanes per 128-byte row segment
+        const int group_cols = min(cpg, cb_end - cb0) * 32;          // columns staged in this group
+        const bool lane_has_data = sub * 16 < group_cols * esz;
+        uint8_t* gp = out_base + static_cast<size_t>(cb0) * 32 * esz;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = rsel + 4 * j;
+          const int orr = __shfl_sync(0xffffffffu, orow, rr);
+          if (orr >= 0 && lane_has_data) {
+            const uint4 val = lds128(stg_addr + rr * kStageRowBytes + sub * 16);
+            *reinterpret_cast<uint4*>(gp + static_cast<size_t>(orr) * out_row_bytes) = val;
+          }
+        }
+        __syncwarp();  // staging rows are rewritten by the next group
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<BN>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
-template <int BN, int MODE>
-cudaError_t launch_t(const ConvGemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN>;
+template <int BN, int MODE, bool RESIDENT>
+cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<BN, RESIDENT>;
   static bool configured = false;  // per instantiation; handles are single-device (see tennis_b200.h)
   if (!configured) {
-    cudaError_t e =
-        cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((p.M + kBM - 1) / kBM, (p.Cout + BN - 1) / BN);
-  conv_gemm_kernel<BN, MODE><<<grid, kThreads, C::kSmem, stream>>>(p);
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  int gx = num_sms / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > m_tiles) gx = m_tiles;
+  dim3 grid(gx, n_tiles);
+  conv_gemm_kernel<BN, MODE, RESIDENT><<<grid, kThreads, C::kSmem, stream>>>(p);
   return cudaGetLastError();
 }
 
 template <int BN>
-cudaError_t launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
+cudaError_t launch_bn(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  const bool resident = p.num_chunks <= kMaxResidentChunks && BN <= 128;
   switch (p.mode) {
-    case kModeConv: return launch_t<BN, kModeConv>(p, stream);
-    case kModePool2: return launch_t<BN, kModePool2>(p, stream);
-    case kModeStem: return launch_t<BN, kModeStem>(p, stream);
+    case kModeConv:
+      return resident ? launch_t<BN, kModeConv, true>(p, num_sms, stream) : launch_t<BN, kModeConv, false>(p, num_sms, stream);
+    case kModePool2: return launch_t<BN, kModePool2, false>(p, num_sms, stream);
+    case kModeStem:
+      return resident ? launch_t<BN, kModeStem, true>(p, num_sms, stream) : launch_t<BN, kModeStem, false>(p, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -416,12 +568,20 @@ size_t conv_gemm_wpack_bytes(int cout, int num_chunks) {
 }
 
 cudaError_t launch_conv_gemm(const ConvGemmParams& p, cudaStream_t stream) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  if (p.M <= 0) return cudaSuccess;
   ProfScope prof_scope(kProfConvGemm, stream);
   switch (conv_gemm_pick_bn(p.Cout)) {
-    case 32: return launch_bn<32>(p, stream);
-    case 64: return launch_bn<64>(p, stream);
-    case 128: return launch_bn<128>(p, stream);
-    default: return launch_bn<256>(p, stream);
+    case 32: return launch_bn<32>(p, num_sms, stream);
+    case 64: return launch_bn<64>(p, num_sms, stream);
+    case 128: return launch_bn<128>(p, num_sms, stream);
+    default: return launch_bn<256>(p, num_sms, stream);
   }
 }
 
