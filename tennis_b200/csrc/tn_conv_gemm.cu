@@ -25,7 +25,9 @@
 // NHWC4 image; K-chunk = two filter rows of 8 px * 4 ch).
 #include "tn_conv_gemm.h"
 
+#include <cuda.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "tn_common.h"
 #include "tn_ptx.cuh"
@@ -38,7 +40,9 @@ constexpr int kProducerWarps = 8;
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kEpiWarp0 = kProducerWarps + 1;
 constexpr int kEpiWarps = 4;  // one per TMEM lane quarter (13 warps total keeps 128 registers per thread)
-constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps) * 32;  // 416
+constexpr int kTmaWarp = kEpiWarp0 + kEpiWarps;  // only active in the TMA-fed 1x1 mode
+constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps + 1) * 32;  // 448 (14 warps: <= 4 per scheduler -> 128 regs)
+constexpr int kModeTma = 3;  // internal: 1x1 / stride 1 conv whose A tiles are fetched by TMA and transformed in place
 constexpr int kBM = 128;
 constexpr int kABytes = kBM * 128;          // 128 rows x 64 bf16
 constexpr int kRowsPerThread = 4;           // 128 rows x 8 groups / 256 threads
@@ -51,7 +55,7 @@ template <int BN, bool RESIDENT>
 struct Cfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStage = RESIDENT ? kABytes : (kABytes + kBBytes);
-  static constexpr int kFixed = 1024 /*align*/ + kStagingBytes + 2 * BN * 4 /*epi scale/shift*/ + 512 /*barriers*/ +
+  static constexpr int kFixed = 1024 /*align*/ + kStagingBytes + 2 * BN * 4 /*epi scale/shift*/ + 1024 /*barriers*/ +
                                 (RESIDENT ? kMaxResidentChunks * kBBytes : 0);
   static constexpr int kNStageRaw = (kSmemLimit - kFixed) / kStage;
   static constexpr int kNStage = kNStageRaw > 8 ? 8 : kNStageRaw;
@@ -128,7 +132,7 @@ __device__ __forceinline__ void bn_act8_accum(uint4 x, const ScaleShift8& s, boo
 }
 
 template <int BN, int MODE, bool RESIDENT>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmParams p) {
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmParams p, const __grid_constant__ CUtensorMap tmap) {
   using C = Cfg<BN, RESIDENT>;
   constexpr int NS = C::kNStage;
   extern __shared__ uint8_t smem_raw[];
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
   uint64_t* acc_full = empty_bar + NS;                              // [2]
   uint64_t* acc_empty = acc_full + 2;                               // [2]
   uint64_t* w_full = acc_empty + 2;                                 // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* tma_full = w_full + 1;                                  // [NS] (TMA mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tma_full + NS);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -154,8 +159,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full_bar[s], kProducerWarps + (RESIDENT ? 0 : 1));
+      mbar_init(&full_bar[s], kProducerWarps + ((RESIDENT || MODE == kModeTma) ? 0 : 1));
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&tma_full[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -177,7 +183,71 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
   const uint32_t tmem_base = *tmem_slot;
   const uint8_t* wtile = p.wpack + static_cast<size_t>(n_tile) * nchunks * C::kBBytes;
 
-  if (warp < kProducerWarps) {
+  const bool has_pro_any = p.pro_scale != nullptr;
+  if (MODE == kModeTma && warp < kProducerWarps) {
+    // ================================================================ TRANSFORMERS (TMA mode)
+    // The raw 128x64 bf16 tile landed in its final swizzled position; apply BN+ReLU in place.
+    if (has_pro_any) {
+      const int j = tid & 7;
+      const int rbase = tid >> 3;
+      const int g = j ^ (rbase & 7);  // channel group stored at 16-byte slot j of my rows
+      const uint32_t my_off = static_cast<uint32_t>(rbase * 128 + (j << 4));  // + i*4096
+      const bool pro_relu = p.pro_relu != 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c) {
+          const int ch = c * 64 + g * 8;
+          ScaleShift8 ss;
+          const bool ch_ok = ch < p.Cin;
+          if (ch_ok) load_ss8(p.pro_scale, p.pro_shift, ch, ss);
+          mbar_wait(&tma_full[stage], phase);
+          const uint32_t a_stage = smem_u32(sStage + stage * C::kStage);
+          if (ch_ok) {
+            uint4 v[kRowsPerThread];
+#pragma unroll
+            for (int i = 0; i < kRowsPerThread; ++i) v[i] = lds128(a_stage + my_off + i * 4096);
+#pragma unroll
+            for (int i = 0; i < kRowsPerThread; ++i) sts128(a_stage + my_off + i * 4096, bn_act8(v[i], ss, pro_relu));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (MODE == kModeTma && warp == kTmaWarp) {
+    // ================================================================ TMA PRODUCER (TMA mode)
+    if (lane == 0) {
+      if (RESIDENT) {
+        mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nchunks * C::kBBytes));
+        for (int c = 0; c < nchunks; ++c)
+          bulk_g2s(sBres + c * C::kBBytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, w_full);
+      }
+      int stage = 0;
+      uint32_t phase = 1;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&empty_bar[stage], phase);
+          uint8_t* st_base = sStage + stage * C::kStage;
+          mbar_arrive_expect_tx(&tma_full[stage], static_cast<uint32_t>(kABytes + (RESIDENT ? 0 : C::kBBytes)));
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+              ::"r"(smem_u32(st_base)), "l"(&tmap), "r"(c * 64), "r"(tile * kBM), "r"(smem_u32(&tma_full[stage]))
+              : "memory");
+          if (!RESIDENT) bulk_g2s(st_base + kABytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &tma_full[stage]);
+          if (++stage == NS) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp < kProducerWarps) {
     // ================================================================ PRODUCERS
     if (RESIDENT && tid == 0) {
       mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nchunks * C::kBBytes));
@@ -376,7 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * BN;
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&full_bar[stage], phase);
+          if (MODE == kModeTma && !has_pro_any) mbar_wait(&tma_full[stage], phase);
+          else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           int kv;
           if (MODE == kModeStem) {
@@ -399,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
         umma_commit(&acc_full[ab]);
       }
     }
-  } else {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
     // ================================================================ EPILOGUE (TMEM lane quarter = warp % 4)
     // kEpiWarps == 8: warps (e, e+4) share a lane quarter and split the tile's 32-column blocks between them.
     const int ew = warp - kEpiWarp0;
@@ -520,9 +591,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
   if (warp == kMmaWarp) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
 template <int BN, int MODE, bool RESIDENT>
 cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, RESIDENT>;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (MODE == kModeTma) {
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.in_cstride), static_cast<cuuint64_t>(p.M)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.in_cstride) * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kBM)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p.in), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
   static bool configured = false;  // per instantiation; handles are single-device (see tennis_b200.h)
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
@@ -535,13 +633,20 @@ cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   if (gx < 1) gx = 1;
   if (gx > m_tiles) gx = m_tiles;
   dim3 grid(gx, n_tiles);
-  conv_gemm_kernel<BN, MODE, RESIDENT><<<grid, kThreads, C::kSmem, stream>>>(p);
+  conv_gemm_kernel<BN, MODE, RESIDENT><<<grid, kThreads, C::kSmem, stream>>>(p, tmap);
   return cudaGetLastError();
 }
 
 template <int BN>
 cudaError_t launch_bn(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   const bool resident = p.num_chunks <= kMaxResidentChunks && BN <= 128;
+  // 1x1 / stride-1 convs (every DenseNet bottleneck conv, the RNN input projection): A tiles are plain 2-D boxes of the
+  // activation matrix -> TMA fetches them, the producer warps only apply BN+ReLU in place
+  const bool tma_ok = p.mode == kModeConv && p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.H == p.Ho &&
+                      p.W == p.Wo && (p.in_cstride % 64) == 0 && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
+                      p.num_chunks * 64 <= p.in_cstride;
+  if (tma_ok)
+    return resident ? launch_t<BN, kModeTma, true>(p, num_sms, stream) : launch_t<BN, kModeTma, false>(p, num_sms, stream);
   switch (p.mode) {
     case kModeConv:
       return resident ? launch_t<BN, kModeConv, true>(p, num_sms, stream) : launch_t<BN, kModeConv, false>(p, num_sms, stream);
