@@ -115,6 +115,14 @@ bool take_conv(Cursor& cur, DeviceArena& arena, int Cout, int Cin, int R, int S,
   if (!w) return false;
   return make_conv(arena, w, Cout, Cin, R, S, mode, cv);
 }
+// conv followed (in parameter order) by the BatchNorm whose scale is folded into its weights; the shift stays in `bn`
+bool take_conv_bn(Cursor& cur, DeviceArena& arena, int Cout, int Cin, int R, int S, int mode, ConvDev* cv, BnDev* bn) {
+  const float* w = cur.take(static_cast<size_t>(Cout) * Cin * R * S);
+  if (!w) return false;
+  std::vector<float> hs, hb;
+  if (!take_bn(cur, arena, Cout, bn, &hs, &hb)) return false;
+  return make_conv(arena, w, Cout, Cin, R, S, mode, cv, hs.data());
+}
 
 struct Dims {
   int H0, W0, Hs, Ws, Hp, Wp;
@@ -173,10 +181,7 @@ ConvGemmParams conv_params(const ConvDev& cv, const __nv_bfloat16* in, int in_cs
   p.out_coff = out_coff;
   p.out_fp32 = 0;
   p.Cout = cv.Cout;
-  if (epi) {
-    p.epi_scale = epi->scale;
-    p.epi_shift = epi->shift;
-  }
+  if (epi) p.epi_shift = epi->shift;  // epi->scale is already folded into the packed weights
   p.epi_relu = epi_relu ? 1 : 0;
   p.M = n * Ho * Wo;
   return p;
@@ -367,16 +372,14 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
   Cursor cur{params, n_params};
   bool ok = true;
   if (arch == TN_ARCH_DENSENET121) {
-    ok = ok && take_conv(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem);
-    ok = ok && take_bn(cur, bb->arena, 64, &bb->bn0);
+    ok = ok && take_conv_bn(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem, &bb->bn0);
     int c = 64;
     for (int b = 0; b < 4 && ok; ++b) {
       for (int l = 0; l < kDenseCfg[b] && ok; ++l) {
         DenseLayer L;
         L.cin = c;
         ok = ok && take_bn(cur, bb->arena, c, &L.bn1);
-        ok = ok && take_conv(cur, bb->arena, kBott, c, 1, 1, tn::kModeConv, &L.conv1);
-        ok = ok && take_bn(cur, bb->arena, kBott, &L.bn2);
+        ok = ok && take_conv_bn(cur, bb->arena, kBott, c, 1, 1, tn::kModeConv, &L.conv1, &L.bn2);
         const float* w2 = cur.p;
         ok = ok && take_conv(cur, bb->arena, kGrowth, kBott, 3, 3, tn::kModeConv, &L.conv2);
         ok = ok && make_conv3x3(bb->arena, w2, &L.conv2h);
@@ -401,8 +404,7 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
         bb->in_shift[i] = hb[i];
       }
     }
-    ok = ok && take_conv(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem);
-    ok = ok && take_bn(cur, bb->arena, 64, &bb->bn0);
+    ok = ok && take_conv_bn(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem, &bb->bn0);
     int cin = 64;
     const int ch[4] = {64, 128, 256, 512};
     for (int s = 0; s < 4 && ok; ++s) {
@@ -413,8 +415,7 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
         B.stride = (b == 0 && s > 0) ? 2 : 1;
         B.has_ds = (b == 0 && cin != B.c);
         ok = ok && take_bn(cur, bb->arena, cin, &B.bn1);
-        ok = ok && take_conv(cur, bb->arena, B.c, cin, 3, 3, tn::kModeConv, &B.conv1);
-        ok = ok && take_bn(cur, bb->arena, B.c, &B.bn2);
+        ok = ok && take_conv_bn(cur, bb->arena, B.c, cin, 3, 3, tn::kModeConv, &B.conv1, &B.bn2);
         ok = ok && take_conv(cur, bb->arena, B.c, B.c, 3, 3, tn::kModeConv, &B.conv2);
         if (B.has_ds) ok = ok && take_conv(cur, bb->arena, B.c, cin, 1, 1, tn::kModeConv, &B.ds);
         bb->rblocks.push_back(B);

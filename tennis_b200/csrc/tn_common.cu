@@ -73,7 +73,8 @@ bool make_bn(DeviceArena& arena, const float* gamma, const float* beta, const fl
   return out->scale && out->shift;
 }
 
-bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out) {
+bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out,
+               const float* fold_scale) {
   const int BN = conv_gemm_pick_bn(Cout);
   const int ntiles = (Cout + BN - 1) / BN;
   int cpt, nchunks;
@@ -107,6 +108,7 @@ bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int
             const int r = tap / S, s = tap % S;
             if (ci < Cin) v = w[((static_cast<size_t>(co) * Cin + ci) * R + r) * S + s];
           }
+          if (fold_scale) v *= fold_scale[co];
           if (v != 0.f) put(t, c, n, kk, v);
         }
       }

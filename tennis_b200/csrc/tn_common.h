@@ -53,7 +53,9 @@ struct ConvDev {
 bool make_bn(DeviceArena& arena, const float* gamma, const float* beta, const float* mean, const float* var, int C,
              BnDev* out, std::vector<float>* host_scale = nullptr, std::vector<float>* host_shift = nullptr);
 // Pack OIHW fp32 weights (Cout,Cin,R,S) into per-(n_tile, K-chunk) swizzled bf16 blobs.
-bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out);
+// `fold_scale` (optional, host, Cout): per-output-channel scale multiplied into the weights (folded BatchNorm gamma/sigma).
+bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out,
+               const float* fold_scale = nullptr);
 
 // ---- optional per-launch device timing (bench.py roofline): CUDA events on the launch stream around each kernel.
 enum ProfKind : int { kProfConvGemm = 0, kProfOther = 1 };

@@ -30,17 +30,22 @@ int tn_conv_create(tn_conv_t** out, int device, const float* weight, int Cout, i
   } else {
     return tn::set_error(TN_ERR_INVALID, "unknown conv mode %d", mode);
   }
+  std::vector<float> zero_shift;
+  if (epi_scale && !epi_shift) {
+    zero_shift.assign(Cout, 0.f);
+    epi_shift = zero_shift.data();
+  }
   if ((pro_scale == nullptr) != (pro_shift == nullptr)) return tn::set_error(TN_ERR_INVALID, "prologue scale/shift must come together");
   TN_CUDA(cudaSetDevice(device));
   std::unique_ptr<tn_conv> c(new tn_conv);
   c->device = device;
-  if (!tn::make_conv(c->arena, weight, Cout, Cin, R, S, mode, &c->cv)) return TN_ERR_CUDA;
+  if (!tn::make_conv(c->arena, weight, Cout, Cin, R, S, mode, &c->cv, epi_scale)) return TN_ERR_CUDA;
   auto up = [&](const float* h, int n) -> const float* {
     return h ? static_cast<const float*>(c->arena.upload(h, n * sizeof(float))) : nullptr;
   };
   c->pro_scale = up(pro_scale, Cin);
   c->pro_shift = up(pro_shift, Cin);
-  c->epi_scale = up(epi_scale, Cout);
+  c->epi_scale = nullptr;  // folded into the packed weights
   c->epi_shift = up(epi_shift, Cout);
   *out = c.release();
   return TN_OK;

@@ -39,15 +39,22 @@ namespace {
 constexpr int kProducerWarps = 8;
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kEpiWarp0 = kProducerWarps + 1;
-constexpr int kEpiWarps = 4;  // one per TMEM lane quarter (13 warps total keeps 128 registers per thread)
-constexpr int kTmaWarp = kEpiWarp0 + kEpiWarps;  // only active in the TMA-fed 1x1 mode
-constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps + 1) * 32;  // 448 (14 warps: <= 4 per scheduler -> 128 regs)
 constexpr int kModeTma = 3;  // internal: 1x1 / stride 1 conv whose A tiles are fetched by TMA and transformed in place
+// Warp budget.  Gather modes: 8 producers + MMA + 4 epilogue = 13 warps (<= 4 per scheduler -> 128 registers/thread for
+// the 3-deep register prefetch).  TMA mode: 8 transformers + MMA + 8 epilogue + TMA = 18 warps (96 registers/thread).
+template <int MODE>
+struct Warps {
+  static constexpr int kEpi = (MODE == kModeTma) ? 8 : 4;
+  static constexpr int kTma = kEpiWarp0 + kEpi;  // TMA warp index (TMA mode only)
+  static constexpr int kThreads = (kProducerWarps + 1 + kEpi + (MODE == kModeTma ? 1 : 0)) * 32;
+};
+constexpr int kMaxEpiWarps = 8;
 constexpr int kBM = 128;
 constexpr int kABytes = kBM * 128;          // 128 rows x 64 bf16
 constexpr int kRowsPerThread = 4;           // 128 rows x 8 groups / 256 threads
 constexpr int kStageRowBytes = 144;         // epilogue staging: 32 fp32 + 16 B pad per row
-constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowBytes;
+constexpr int kStagingBytes = kMaxEpiWarps * 32 * kStageRowBytes;
+constexpr int kOnesBytes = 1024;            // 8 rows x 128 B, aliased by all 16 row groups (SBO = 0)
 constexpr int kMaxResidentChunks = 4;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -55,7 +62,7 @@ template <int BN, bool RESIDENT>
 struct Cfg {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStage = RESIDENT ? kABytes : (kABytes + kBBytes);
-  static constexpr int kFixed = 1024 /*align*/ + kStagingBytes + 2 * BN * 4 /*epi scale/shift*/ + 1024 /*barriers*/ +
+  static constexpr int kFixed = 1024 /*align*/ + kStagingBytes + kOnesBytes + kBBytes /*bias operand*/ + 1024 /*barriers*/ +
                                 (RESIDENT ? kMaxResidentChunks * kBBytes : 0);
   static constexpr int kNStageRaw = (kSmemLimit - kFixed) / kStage;
   static constexpr int kNStage = kNStageRaw > 8 ? 8 : kNStageRaw;
@@ -132,17 +139,20 @@ __device__ __forceinline__ void bn_act8_accum(uint4 x, const ScaleShift8& s, boo
 }
 
 template <int BN, int MODE, bool RESIDENT>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(const ConvGemmParams p, const __grid_constant__ CUtensorMap tmap) {
   using C = Cfg<BN, RESIDENT>;
   constexpr int NS = C::kNStage;
+  constexpr int kEpiWarps = Warps<MODE>::kEpi;
+  constexpr int kThreads = Warps<MODE>::kThreads;
+  constexpr int kTmaWarp = Warps<MODE>::kTma;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sStage = smem;                                        // NS x kStage  (A [+ B])
   uint8_t* sBres = sStage + NS * C::kStage;                      // resident weights (RESIDENT only)
-  uint8_t* sStaging = sBres + (RESIDENT ? kMaxResidentChunks * C::kBBytes : 0);
-  float* sEpiScale = reinterpret_cast<float*>(sStaging + kStagingBytes);
-  float* sEpiShift = sEpiScale + BN;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpiShift + BN);  // [NS]
+  uint8_t* sOnes = sBres + (RESIDENT ? kMaxResidentChunks * C::kBBytes : 0);  // A operand of the bias MMA (1024-B aligned)
+  uint8_t* sBias = sOnes + kOnesBytes;                              // B operand of the bias MMA: BN rows x 128 B
+  uint8_t* sStaging = sBias + C::kBBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStaging + kStagingBytes);  // [NS]
   uint64_t* empty_bar = full_bar + NS;                              // [NS]
   uint64_t* acc_full = empty_bar + NS;                              // [2]
   uint64_t* acc_empty = acc_full + 2;                               // [2]
@@ -171,11 +181,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc<C::kTmemCols>(tmem_slot);
-  // epilogue constants of this N tile
-  for (int i = tid; i < BN; i += kThreads) {
-    const int n = n_tile * BN + i;
-    sEpiScale[i] = (p.epi_scale != nullptr && n < p.Cout) ? p.epi_scale[n] : 1.f;
-    sEpiShift[i] = (p.epi_shift != nullptr && n < p.Cout) ? p.epi_shift[n] : 0.f;
+  // Per-channel shift (folded BN beta / bias) is added BY THE TENSOR CORE: one extra K=16 UMMA per tile with
+  // A = [1 1 0 ... 0] for every row and B[n] = [hi(shift[n]) lo(shift[n]) 0 ... 0] (bf16 hi/lo split keeps ~16 bits).
+  const bool has_shift = p.epi_shift != nullptr;
+  if (has_shift) {
+    for (int i = tid; i < kOnesBytes / 16; i += kThreads) {  // 8 rows x 8 chunks; row r's K-chunk 0 lives at slot (r & 7)
+      const int r = i >> 3, slot = i & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (slot == (r & 7)) v.x = 0x3F803F80u;  // (1.0, 1.0) bf16
+      *reinterpret_cast<uint4*>(sOnes + i * 16) = v;
+    }
+    for (int i = tid; i < BN * 8; i += kThreads) {
+      const int r = i >> 3, slot = i & 7;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      const int n = n_tile * BN + r;
+      if (slot == (r & 7) && n < p.Cout) {
+        const float sh = p.epi_shift[n];
+        const __nv_bfloat16 hi = __float2bfloat16(sh);
+        const __nv_bfloat16 lo = __float2bfloat16(sh - __bfloat162float(hi));
+        v.x = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+      }
+      *reinterpret_cast<uint4*>(sBias + i * 16) = v;
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -467,6 +495,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
             phase ^= 1u;
           }
         }
+        if (has_shift) {
+          // SBO = 0: all sixteen 8-row groups of the A operand alias the same 8 "ones" rows
+          const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes)) & ~(static_cast<uint64_t>(0x3FFF) << 32);
+          umma_bf16_ss(d_tmem, d_ones, umma_desc_sw128(smem_u32(sBias)), idesc, 1u);
+        }
         umma_commit(&acc_full[ab]);
       }
     }
@@ -483,7 +516,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
     const int cb_begin = half * ncb_half;
     const int cb_end = min(ncb, cb_begin + ncb_half);
     const bool relu = p.epi_relu != 0;
-    const bool has_scale = p.epi_scale != nullptr;
     const int esz = p.out_fp32 ? 4 : 2;
     const int cpg = p.out_fp32 ? 1 : 2;  // column blocks per 128-byte staging row
     const int hw = p.Ho * p.Wo;
@@ -528,21 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const ConvGemmPa
           }
           float f[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 sh = *reinterpret_cast<const float4*>(sEpiShift + cb * 32 + 4 * q);
-            if (has_scale) {
-              const float4 sc = *reinterpret_cast<const float4*>(sEpiScale + cb * 32 + 4 * q);
-              f[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x);
-              f[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y);
-              f[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z);
-              f[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w);
-            } else {
-              f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + sh.x;
-              f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + sh.y;
-              f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + sh.z;
-              f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + sh.w;
-            }
-          }
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.res != nullptr && m < p.M) {
             const uint4* r4 = reinterpret_cast<const uint4*>(p.res + static_cast<size_t>(m) * p.res_cstride + n_tile * BN + cb * 32);
 #pragma unroll
@@ -617,7 +635,7 @@ cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kBM)};
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p.in), gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
@@ -633,26 +651,29 @@ cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   if (gx < 1) gx = 1;
   if (gx > m_tiles) gx = m_tiles;
   dim3 grid(gx, n_tiles);
-  conv_gemm_kernel<BN, MODE, RESIDENT><<<grid, kThreads, C::kSmem, stream>>>(p, tmap);
+  conv_gemm_kernel<BN, MODE, RESIDENT><<<grid, Warps<MODE>::kThreads, C::kSmem, stream>>>(p, tmap);
   return cudaGetLastError();
 }
 
 template <int BN>
 cudaError_t launch_bn(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  const bool resident = p.num_chunks <= kMaxResidentChunks && BN <= 128;
   // 1x1 / stride-1 convs (every DenseNet bottleneck conv, the RNN input projection): A tiles are plain 2-D boxes of the
   // activation matrix -> TMA fetches them, the producer warps only apply BN+ReLU in place
   const bool tma_ok = p.mode == kModeConv && p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.H == p.Ho &&
                       p.W == p.Wo && (p.in_cstride % 64) == 0 && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
                       p.num_chunks * 64 <= p.in_cstride;
-  if (tma_ok)
-    return resident ? launch_t<BN, kModeTma, true>(p, num_sms, stream) : launch_t<BN, kModeTma, false>(p, num_sms, stream);
+  if constexpr (BN <= 128) {
+    if (p.num_chunks <= kMaxResidentChunks) {  // weights stay resident in shared memory
+      if (tma_ok) return launch_t<BN, kModeTma, true>(p, num_sms, stream);
+      if (p.mode == kModeConv) return launch_t<BN, kModeConv, true>(p, num_sms, stream);
+      if (p.mode == kModeStem) return launch_t<BN, kModeStem, true>(p, num_sms, stream);
+    }
+  }
+  if (tma_ok) return launch_t<BN, kModeTma, false>(p, num_sms, stream);
   switch (p.mode) {
-    case kModeConv:
-      return resident ? launch_t<BN, kModeConv, true>(p, num_sms, stream) : launch_t<BN, kModeConv, false>(p, num_sms, stream);
+    case kModeConv: return launch_t<BN, kModeConv, false>(p, num_sms, stream);
     case kModePool2: return launch_t<BN, kModePool2, false>(p, num_sms, stream);
-    case kModeStem:
-      return resident ? launch_t<BN, kModeStem, true>(p, num_sms, stream) : launch_t<BN, kModeStem, false>(p, num_sms, stream);
+    case kModeStem: return launch_t<BN, kModeStem, false>(p, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -681,6 +702,7 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, cudaStream_t stream) {
     if (num_sms <= 0) num_sms = 148;
   }
   if (p.M <= 0) return cudaSuccess;
+  if (p.epi_scale != nullptr) return cudaErrorInvalidValue;  // per-channel scales are folded into the packed weights
   ProfScope prof_scope(kProfConvGemm, stream);
   switch (conv_gemm_pick_bn(p.Cout)) {
     case 32: return launch_bn<32>(p, num_sms, stream);

@@ -36,8 +36,8 @@ struct ConvGemmParams {
   int out_fp32;  // 0 -> bf16, 1 -> fp32
   int out_pad;   // 1 -> output rows address a zero-padded (F, Ho+2, Wo+2, C) buffer (interior pixels only)
   int Cout;      // multiple of 32
-  // epilogue: y = relu?(acc * scale[n] + shift[n] + residual)
-  const float* epi_scale;
+  // epilogue: y = relu?(acc + shift[n] + residual); a per-channel scale must be folded into the packed weights
+  const float* epi_scale;  // must be null
   const float* epi_shift;
   int epi_relu;
   const __nv_bfloat16* res;  // optional residual, NHWC bf16 at the output resolution

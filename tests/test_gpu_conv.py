@@ -30,9 +30,11 @@ def _ref_conv(x_nhwc, w, stride, pad, pro=None, pro_relu=True, epi=None, epi_rel
     a = a.permute(0, 3, 1, 2)
     if pool2:
         a = _bf(F.avg_pool2d(a, 2, 2))
-    y = F.conv2d(a, _bf(w), stride=1 if pool2 else stride, padding=0 if pool2 else pad).permute(0, 2, 3, 1)
+    # the library folds the epilogue scale (BN gamma/sigma) into the weights BEFORE rounding them to bf16
+    wq = _bf(w if epi is None else w * epi[0].reshape(-1, 1, 1, 1))
+    y = F.conv2d(a, wq, stride=1 if pool2 else stride, padding=0 if pool2 else pad).permute(0, 2, 3, 1)
     if epi is not None:
-        y = y * epi[0] + epi[1]
+        y = y + epi[1]
     if residual is not None:
         y = y + residual
     if epi_relu:
@@ -131,7 +133,7 @@ def test_conv_stem():
     conv = ops.Conv(w, mode=_lib.MODE_STEM, epi_scale=es[0], epi_shift=es[1])
     y = conv(x4, stride=2, pad=3, epi_relu=True, out_fp32=True)
     torch.cuda.synchronize()
-    ref = (F.conv2d(frames, _bf(w), stride=2, padding=3).permute(0, 2, 3, 1) * es[0] + es[1]).relu()
+    ref = (F.conv2d(frames, _bf(w * es[0].reshape(-1, 1, 1, 1)), stride=2, padding=3).permute(0, 2, 3, 1) + es[1]).relu()
     assert y.shape == ref.shape
     assert (y.cpu() - ref).abs().max().item() < 3e-3
 
