@@ -1,0 +1,113 @@
+"""CPU-only: pin the oracle (a) against independent implementations shipped in this image (torchvision's DenseNet-121
+graph, torch.nn.GRU / LSTM) and (b) against the committed golden fixtures (tests/golden, made by tools/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vision as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "vision_oracle.npz")
+
+
+def _torchvision_densenet_with(p):
+    tv = pytest.importorskip("torchvision")
+    m = tv.models.densenet121(weights=None).eval()
+    sd = {}
+
+    def bn(dst, src):
+        sd[dst + ".weight"] = p[src + ".gamma"]
+        sd[dst + ".bias"] = p[src + ".beta"]
+        sd[dst + ".running_mean"] = p[src + ".running_mean"]
+        sd[dst + ".running_var"] = p[src + ".running_var"]
+
+    sd["features.conv0.weight"] = p["conv0.weight"]
+    bn("features.norm0", "bn0")
+    for b, nl in enumerate(O.DENSE_CFG):
+        for l in range(nl):
+            src = "block%d.layer%d" % (b + 1, l + 1)
+            dst = "features.denseblock%d.denselayer%d" % (b + 1, l + 1)
+            bn(dst + ".norm1", src + ".bn1")
+            sd[dst + ".conv1.weight"] = p[src + ".conv1.weight"]
+            bn(dst + ".norm2", src + ".bn2")
+            sd[dst + ".conv2.weight"] = p[src + ".conv2.weight"]
+        if b < 3:
+            bn("features.transition%d.norm" % (b + 1), "trans%d.bn" % (b + 1))
+            sd["features.transition%d.conv.weight" % (b + 1)] = p["trans%d.conv.weight" % (b + 1)]
+    bn("features.norm5", "bn5")
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert all(k.startswith("classifier") or k.endswith("num_batches_tracked") for k in missing), missing
+    assert not unexpected
+    return m
+
+
+def test_densenet_oracle_matches_torchvision_graph():
+    p = O.synthetic_params("densenet121", seed=1234)
+    tvm = _torchvision_densenet_with(p)
+    _, x = O.synthetic_frames(1, 224, seed=5)
+    with torch.no_grad():
+        mine = O.densenet121_features(x, p)
+        ref = torch.nn.functional.avg_pool2d(torch.relu(tvm.features(x)), 7).flatten(1)
+    assert mine.shape == (1, 1024)
+    assert torch.allclose(mine, ref, rtol=1e-4, atol=1e-4), (mine - ref).abs().max()
+
+
+def test_feature_width_follows_crop_size():
+    """AvgPool2D(7) is stride 7 / valid, not global: 224 -> 1024-d, 512 -> 4096-d (train.py:259,261)."""
+    p = O.synthetic_params("densenet121", seed=1)
+    with torch.no_grad():
+        assert O.densenet121_features(torch.zeros(1, 3, 224, 224), p).shape == (1, 1024)
+        assert O.densenet121_features(torch.zeros(1, 3, 512, 512), p).shape == (1, 4096)
+        assert O.resnet18_v2_features(torch.zeros(1, 3, 224, 224), O.synthetic_params("resnet18_v2", 1)).shape == (1, 512)
+
+
+@pytest.mark.parametrize("cell", ["gru", "lstm"])
+def test_birnn_oracle_matches_torch_nn(cell):
+    D, H, B, T = 24, 16, 3, 6
+    p = O.synthetic_rnn_params(cell, D, H, seed=9)
+    mod = (torch.nn.GRU if cell == "gru" else torch.nn.LSTM)(D, H, batch_first=True, bidirectional=True)
+    with torch.no_grad():
+        for d, suf in (("l0", ""), ("r0", "_reverse")):
+            getattr(mod, "weight_ih_l0" + suf).copy_(p[d + "_i2h_weight"])
+            getattr(mod, "weight_hh_l0" + suf).copy_(p[d + "_h2h_weight"])
+            getattr(mod, "bias_ih_l0" + suf).copy_(p[d + "_i2h_bias"])
+            getattr(mod, "bias_hh_l0" + suf).copy_(p[d + "_h2h_bias"])
+        x = torch.randn(B, T, D, generator=torch.Generator().manual_seed(1))
+        ref, _ = mod(x)
+        mine = O.birnn_layer(x, p, cell, H)
+    assert torch.allclose(mine, ref, atol=1e-5), (mine - ref).abs().max()
+
+
+def test_time_distributed_shape_kat():
+    """The reference's only executable check (definitions.py:156-168): (3,2,3,2,2) -> Conv2D(4,k=2) -> (3,2,4,1,1)."""
+    w = torch.randn(4, 3, 2, 2)
+    y = O.time_distributed(lambda t: torch.relu(torch.nn.functional.conv2d(t, w)), torch.ones(3, 2, 3, 2, 2))
+    assert y.shape == (3, 2, 4, 1, 1)
+
+
+def test_param_counts_match_survey_inventory():
+    n = sum(int(np.prod(s)) for k, s in O.densenet121_param_shapes() if not k.endswith(("running_mean", "running_var")))
+    assert n == 6953856  # SURVEY.md Appendix B (torchvision restatement)
+    assert O.flatten_params("densenet121", O.synthetic_params("densenet121")).numel() == 7037504
+
+
+def test_oracle_reproduces_golden_fixtures():
+    gold = np.load(GOLD)
+    with torch.no_grad():
+        _, x = O.synthetic_frames(2, 224, seed=100)
+        for arch in ("densenet121", "resnet18_v2"):
+            f = O.FEATURES[arch](x, O.synthetic_params(arch, seed=1234)).numpy()
+            ref = gold[arch + "_feats"]
+            assert np.abs(f - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max()), arch
+        g = torch.Generator().manual_seed(3)
+        feats = torch.randn(3, 5, 64, generator=g).relu()
+        for cell in ("gru", "lstm"):
+            y = O.birnn_layer(feats, O.synthetic_rnn_params(cell, 64, 128, seed=4321), cell, 128).numpy()
+            assert np.abs(y - gold["birnn_%s_y" % cell]).max() < 1e-5
+        gg = torch.Generator().manual_seed(77)
+        cw = (torch.rand(11, 256, generator=gg) * 2 - 1) * 0.07
+        logits = O.cnnrnn(feats, None, O.synthetic_rnn_params("gru", 64, 128, seed=4321), "gru", 128, cw, torch.zeros(11),
+                          feats=True).numpy()
+        assert np.abs(logits - gold["cnnrnn_feats_logits"]).max() < 1e-5
+        assert np.abs(O.temporal_pooling(feats, None, "mean", feats=True).numpy() - gold["temporal_pool_mean"]).max() < 1e-6
