@@ -111,12 +111,46 @@ int tn_temporal_pool(const float* x, float* y, int B, int T, int D, int pool, tn
 int tn_birnn_create(tn_birnn_t** out, int device, int cell, int D, int H, int ndir, const float* const* i2h_weight,
                     const float* const* h2h_weight, const float* const* i2h_bias, const float* const* h2h_bias);
 void tn_birnn_destroy(tn_birnn_t* r);
+/* on=1: compute the input projection in split-bf16 (x = hi + lo, three tensor-core products): ~fp32-accurate gates for the
+ * captioner's encoder, where token ids must match; default 0 (plain bf16 operands, fp32 accumulate). */
+int tn_birnn_set_precise(tn_birnn_t* r, int on);
 size_t tn_birnn_workspace_bytes(const tn_birnn_t* r, int B, int T);
 /* x: device (B,T,D) fp32, or bf16 when x_is_bf16; valid_len: device int32 (B) or NULL;
  * y (B,T,ndir*H) / ymax (B,ndir*H) / h_final, c_final (ndir,B,H): device fp32, each may be NULL. */
 int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t* valid_len, int B, int T, float* y,
                      float* ymax, float* h_final, float* c_final, void* workspace, size_t workspace_bytes,
                      tn_stream_t stream);
+
+/* ------------------------------------------------------------------ GNMT decoder + beam search
+ * Replaces GNMTDecoder (models/captioning/gnmt.py:163-404) + gluonnlp NMTModel.decode_step/decode_seq glue
+ * (tgt_embed, tgt_proj) and gluonnlp BeamSearchSampler/BeamSearchScorer as driven by
+ * BeamSearchTranslator.translate (utils/translation.py:42-82).  The encoder (gnmt.py:136-160) is tn_birnn_forward
+ * with valid_len.  Host fp32 weights, Gluon layouts: per decoder layer i2h_weight (G*H, in_l) with in_0 = E+H,
+ * in_l = 2H; h2h_weight (G*H, H); biases (G*H); attention query projection (H,H) (scaled Luong: query projected and
+ * divided by sqrt(H), keys/values are the raw encoder memory); tgt_embed (V,E); tgt_proj weight (V,H) + bias (V). */
+int tn_gnmt_create(tn_gnmt_t** out, int device, int cell, int H, int E, int V, int num_layers, int use_residual,
+                   const float* const* i2h_weight, const float* const* h2h_weight, const float* const* i2h_bias,
+                   const float* const* h2h_bias, const float* query_weight, const float* embed_weight,
+                   const float* proj_weight, const float* proj_bias);
+void tn_gnmt_destroy(tn_gnmt_t* g);
+size_t tn_gnmt_workspace_bytes(const tn_gnmt_t* g, int rows, int max_len);
+/* One step for R rows (model.decode_step, translation.py:52): step_ids device float (R); h_in/c_in device (L,R,H);
+ * att_in (R,H); mem (R/rows_per_mem, T, H); src_len device int32 or NULL; outputs logits (R,V), states. */
+int tn_gnmt_decode_step(tn_gnmt_t* g, const float* step_ids, const float* h_in, const float* c_in, const float* att_in,
+                        const float* mem, const int32_t* src_len, int rows_per_mem, int R, int T, float* logits,
+                        float* h_out, float* c_out, float* att_out, void* workspace, size_t workspace_bytes,
+                        tn_stream_t stream);
+/* Teacher-forced decode (model.decode_seq, gnmt.py:254-304; train_gnmt.py:280,331): tgt_ids device float (B,T_tgt),
+ * tgt_valid_len device int32 (B) or NULL, h0/c0 (L,B,H), logits (B,T_tgt,V). */
+int tn_gnmt_decode_seq(tn_gnmt_t* g, const float* tgt_ids, const int32_t* tgt_valid_len, const float* h0,
+                       const float* c0, const float* mem, const int32_t* src_len, int B, int T_src, int T_tgt,
+                       float* logits, void* workspace, size_t workspace_bytes, tn_stream_t stream);
+/* Beam search (translator.translate after the encoder): samples device int32 (B,beam,max_len+2) of which the first
+ * *out_len columns are the reference's result, scores device (B,beam) descending, valid_len device int32 (B,beam). */
+int tn_gnmt_beam_search(tn_gnmt_t* g, const float* mem, const int32_t* src_len, const float* h0, const float* c0, int B,
+                        int T, int beam, int max_len, float alpha, float K, int bos, int eos, int32_t* samples,
+                        float* scores, int32_t* valid_len, int* out_len, void* workspace, size_t workspace_bytes,
+                        tn_stream_t stream);
 
 #ifdef __cplusplus
 }

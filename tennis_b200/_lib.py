@@ -51,6 +51,7 @@ SIGNATURES = {
     "tn_birnn_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p),
                                 POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "tn_birnn_destroy": (None, [c_void_p]),
+    "tn_birnn_set_precise": (c_int, [c_void_p, c_int]),
     "tn_birnn_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "tn_birnn_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -103,3 +104,19 @@ def profile_read(reset=True):
     na, nb = ctypes.c_longlong(), ctypes.c_longlong()
     check(lib().tn_profile_read(ctypes.byref(a), ctypes.byref(na), ctypes.byref(b), ctypes.byref(nb), int(reset)))
     return {"conv_ms": a.value, "conv_launches": na.value, "other_ms": b.value, "other_launches": nb.value}
+
+
+SIGNATURES.update({
+    "tn_gnmt_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p),
+                               POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+    "tn_gnmt_destroy": (None, [c_void_p]),
+    "tn_gnmt_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "tn_gnmt_decode_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tn_gnmt_decode_seq": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tn_gnmt_beam_search": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int),
+                                    c_void_p, c_size_t, c_void_p]),
+})

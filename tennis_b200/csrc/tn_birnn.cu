@@ -11,6 +11,8 @@ struct tn_birnn {
   int device = 0, cell = 0, gates = 3, D = 0, H = 0, ndir = 1;
   tn::DeviceArena arena;
   tn::ConvDev proj;          // W_ih of all directions stacked: (ndir*G*H, D)
+  tn::ConvDev proj3;         // the same weights split into bf16 hi/lo parts along K: [hi | hi | lo]  (ndir*G*H, 3D)
+  int precise = 0;           // 1 -> input projection in split-bf16 (x = hi + lo): ~16 mantissa bits instead of 8
   const float* bih = nullptr;   // [ndir*G*H]
   const float* WhhT = nullptr;  // [ndir][H][G*H]
   const float* bhh = nullptr;   // [ndir*G*H]
@@ -67,6 +69,19 @@ int tn_birnn_create(tn_birnn_t** out, int device, int cell, int D, int H, int nd
       for (int k = 0; k < H; ++k) whhT[(static_cast<size_t>(d) * H + k) * GH + j] = h2h_weight[d][static_cast<size_t>(j) * H + k];
   }
   if (!tn::make_conv(r->arena, wih.data(), ndir * GH, D, 1, 1, tn::kModeConv, &r->proj)) return TN_ERR_CUDA;
+  {
+    // x W^T ~= x_hi W_hi^T + x_lo W_hi^T + x_hi W_lo^T as ONE GEMM over K' = 3D: A' = [x_hi | x_lo | x_hi], W' = [W_hi | W_hi | W_lo]
+    std::vector<float> w3(static_cast<size_t>(ndir) * GH * 3 * D);
+    for (size_t n = 0; n < static_cast<size_t>(ndir) * GH; ++n)
+      for (int k = 0; k < D; ++k) {
+        const float w = wih[n * D + k];
+        const float hi = __bfloat162float(__float2bfloat16(w));
+        w3[n * 3 * D + k] = hi;
+        w3[n * 3 * D + D + k] = hi;
+        w3[n * 3 * D + 2 * D + k] = w - hi;
+      }
+    if (!tn::make_conv(r->arena, w3.data(), ndir * GH, 3 * D, 1, 1, tn::kModeConv, &r->proj3)) return TN_ERR_CUDA;
+  }
   r->bih = static_cast<const float*>(r->arena.upload(bih.data(), bih.size() * sizeof(float)));
   r->bhh = static_cast<const float*>(r->arena.upload(bhh.data(), bhh.size() * sizeof(float)));
   r->WhhT = static_cast<const float*>(r->arena.upload(whhT.data(), whhT.size() * sizeof(float)));
@@ -77,10 +92,16 @@ int tn_birnn_create(tn_birnn_t** out, int device, int cell, int D, int H, int nd
 
 void tn_birnn_destroy(tn_birnn_t* r) { delete r; }
 
+int tn_birnn_set_precise(tn_birnn_t* r, int on) {
+  if (!r) return tn::set_error(TN_ERR_INVALID, "null handle");
+  r->precise = on ? 1 : 0;
+  return TN_OK;
+}
+
 size_t tn_birnn_workspace_bytes(const tn_birnn_t* r, int B, int T) {
   if (!r || B < 0 || T < 0) return 0;
   const size_t M = static_cast<size_t>(B) * T;
-  return tn::align_up(M * r->D * sizeof(__nv_bfloat16), 1024) + tn::align_up(M * r->ndir * r->gates * r->H * sizeof(float), 1024) + 1024;
+  return tn::align_up(M * 3 * r->D * sizeof(__nv_bfloat16), 1024) + tn::align_up(M * r->ndir * r->gates * r->H * sizeof(float), 1024) + 1024;
 }
 
 int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t* valid_len, int B, int T, float* y,
@@ -97,9 +118,15 @@ int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t*
   const int N = r->ndir * r->gates * r->H;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws);
-  float* gx = reinterpret_cast<float*>(ws + tn::align_up(M * r->D * sizeof(__nv_bfloat16), 1024));
+  float* gx = reinterpret_cast<float*>(ws + tn::align_up(M * 3 * r->D * sizeof(__nv_bfloat16), 1024));
   const __nv_bfloat16* xin = static_cast<const __nv_bfloat16*>(x);
-  if (!x_is_bf16) {
+  const bool precise = r->precise && !x_is_bf16;
+  const int Dk = precise ? 3 * r->D : r->D;
+  const tn::ConvDev& proj = precise ? r->proj3 : r->proj;
+  if (precise) {
+    TN_CUDA(tn::launch_split3_bf16(static_cast<const float*>(x), xb, M, r->D, st));
+    xin = xb;
+  } else if (!x_is_bf16) {
     TN_CUDA(tn::launch_cast_bf16(static_cast<const float*>(x), xb, M * r->D, st));
     xin = xb;
   }
@@ -107,10 +134,10 @@ int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t*
   tn::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   p.in = xin;
-  p.in_cstride = r->D;
+  p.in_cstride = Dk;
   p.H = 1;
   p.W = 1;
-  p.Cin = r->D;
+  p.Cin = Dk;
   p.Ho = 1;
   p.Wo = 1;
   p.R = 1;
@@ -118,9 +145,9 @@ int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t*
   p.stride = 1;
   p.pad = 0;
   p.mode = tn::kModeConv;
-  p.wpack = r->proj.wpack;
-  p.num_chunks = r->proj.num_chunks;
-  p.chunks_per_tap = r->proj.chunks_per_tap;
+  p.wpack = proj.wpack;
+  p.num_chunks = proj.num_chunks;
+  p.chunks_per_tap = proj.chunks_per_tap;
   p.out = gx;
   p.out_cstride = N;
   p.out_coff = 0;

@@ -244,4 +244,25 @@ cudaError_t launch_cast_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStr
   return cudaGetLastError();
 }
 
+// split-bf16 operand for the "precise" input projection: row m -> [hi(x) | lo(x) | hi(x)]
+__global__ void split3_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t M, int D) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * D) return;
+  const size_t m = i / D;
+  const int k = static_cast<int>(i - m * D);
+  const float v = x[i];
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+  __nv_bfloat16* row = y + m * 3 * D;
+  row[k] = hi;
+  row[D + k] = lo;
+  row[2 * D + k] = hi;
+}
+cudaError_t launch_split3_bf16(const float* x, __nv_bfloat16* y, size_t M, int D, cudaStream_t st) {
+  if (M == 0) return cudaSuccess;
+  ProfScope prof_scope(kProfOther, st);
+  split3_bf16_kernel<<<static_cast<unsigned>((M * D + 255) / 256), 256, 0, st>>>(x, y, M, D);
+  return cudaGetLastError();
+}
+
 }  // namespace tn

@@ -19,5 +19,7 @@ cudaError_t launch_dense(const float* x, const float* W, const float* b, float* 
                          cudaStream_t st);
 cudaError_t launch_temporal_pool(const float* x, float* y, int B, int T, int D, int mean, cudaStream_t st);
 cudaError_t launch_cast_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t st);
+// (M,D) fp32 -> (M,3D) bf16 rows [hi | lo | hi] with hi = bf16(x), lo = bf16(x - hi)
+cudaError_t launch_split3_bf16(const float* x, __nv_bfloat16* y, size_t M, int D, cudaStream_t st);
 
 }  // namespace tn

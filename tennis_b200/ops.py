@@ -161,7 +161,7 @@ def temporal_pool(x, pool="max"):
 class BiRNN:
     """Fused (bi)directional GRU/LSTM layer (tn_birnn_*).  params: dict with Gluon names l0_*/r0_*."""
 
-    def __init__(self, cell, D, H, params, bidirectional=True, device=0):
+    def __init__(self, cell, D, H, params, bidirectional=True, device=0, precise=False):
         self.cell, self.D, self.H = cell, D, H
         self.ndir = 2 if bidirectional else 1
         dirs = ["l0", "r0"][: self.ndir]
@@ -177,6 +177,8 @@ class BiRNN:
         self._h = c_void_p()
         check(lib().tn_birnn_create(ctypes.byref(self._h), device, _lib.CELL_GRU if cell == "gru" else _lib.CELL_LSTM, D,
                                     H, self.ndir, arrs[0], arrs[1], arrs[2], arrs[3]))
+        if precise:
+            check(lib().tn_birnn_set_precise(self._h, 1))
         self._ws = None
         self._ws_bytes = 0
 
@@ -210,3 +212,94 @@ class BiRNN:
                                          dptr(ymax), dptr(h), dptr(c), c_void_p(self._ws[1]), self._ws_bytes,
                                          stream_ptr()))
         return {"y": y, "ymax": ymax, "h": h, "c": c}
+
+
+class GNMTDecoderEngine:
+    """GNMT decoder + target embedding/projection + beam search on the device (tn_gnmt_*)."""
+
+    def __init__(self, cell, H, E, V, layer_params, query_weight, embed_weight, proj_weight, proj_bias, use_residual=False,
+                 device=0):
+        """layer_params: list (per decoder layer) of dicts with i2h_weight/h2h_weight/i2h_bias/h2h_bias."""
+        self.cell, self.H, self.E, self.V, self.L = cell, H, E, V, len(layer_params)
+        keep = []
+        arrs = []
+        for name in ("i2h_weight", "h2h_weight", "i2h_bias", "h2h_bias"):
+            arr = (c_void_p * self.L)()
+            for i, lp in enumerate(layer_params):
+                t = _host_f32(lp[name])
+                keep.append(t)
+                arr[i] = t.data_ptr()
+            arrs.append(arr)
+        others = [_host_f32(t) for t in (query_weight, embed_weight, proj_weight, proj_bias)]
+        self._h = c_void_p()
+        check(lib().tn_gnmt_create(ctypes.byref(self._h), device, _lib.CELL_GRU if cell == "gru" else _lib.CELL_LSTM, H, E,
+                                   V, self.L, int(use_residual), arrs[0], arrs[1], arrs[2], arrs[3], dptr(others[0]),
+                                   dptr(others[1]), dptr(others[2]), dptr(others[3])))
+        self._ws = None
+        self._ws_bytes = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().tn_gnmt_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:
+            pass
+
+    def _workspace(self, rows, max_len, device):
+        need = lib().tn_gnmt_workspace_bytes(self._h, rows, max_len)
+        if self._ws is None or self._ws_bytes < need:
+            self._ws = None
+            self._ws = _workspace(need, device)
+            self._ws_bytes = need
+        return c_void_p(self._ws[1]), self._ws_bytes
+
+    @staticmethod
+    def _i32(t):
+        return None if t is None else t.to(torch.int32).contiguous()
+
+    def decode_step(self, step_ids, h, c, att, mem, src_len, rows_per_mem=1):
+        """step_ids (R,) float; h/c (L,R,H); att (R,H); mem (R/rows_per_mem,T,H) -> logits (R,V), h', c', att'."""
+        _require_cuda(step_ids, h, c, att, mem, src_len)
+        R, T = step_ids.shape[0], mem.shape[1]
+        dev = mem.device
+        logits = torch.empty((R, self.V), dtype=torch.float32, device=dev)
+        h2, att2 = torch.empty_like(h), torch.empty_like(att)
+        c2 = torch.empty_like(c) if c is not None else None
+        ws, wsb = self._workspace(R, 1, dev)
+        sl = self._i32(src_len)
+        check(lib().tn_gnmt_decode_step(self._h, dptr(step_ids.float().contiguous()), dptr(h.contiguous()),
+                                        dptr(None if c is None else c.contiguous()), dptr(att.contiguous()),
+                                        dptr(mem.contiguous()), dptr(sl), rows_per_mem, R, T, dptr(logits), dptr(h2), dptr(c2),
+                                        dptr(att2), ws, wsb, stream_ptr()))
+        return logits, h2, c2, att2
+
+    def decode_seq(self, tgt_ids, tgt_valid_len, h0, c0, mem, src_len):
+        """tgt_ids (B,T_tgt) float; h0/c0 (L,B,H) -> logits (B,T_tgt,V)."""
+        _require_cuda(tgt_ids, h0, c0, mem, src_len, tgt_valid_len)
+        B, Tt = tgt_ids.shape
+        T = mem.shape[1]
+        logits = torch.empty((B, Tt, self.V), dtype=torch.float32, device=mem.device)
+        ws, wsb = self._workspace(B, Tt, mem.device)
+        tv, sl = self._i32(tgt_valid_len), self._i32(src_len)
+        check(lib().tn_gnmt_decode_seq(self._h, dptr(tgt_ids.float().contiguous()), dptr(tv), dptr(h0.contiguous()),
+                                       dptr(None if c0 is None else c0.contiguous()), dptr(mem.contiguous()), dptr(sl), B, T, Tt,
+                                       dptr(logits), ws, wsb, stream_ptr()))
+        return logits
+
+    def beam_search(self, mem, src_len, h0, c0, beam, max_len, alpha, K, bos, eos):
+        """-> samples (B,beam,L) int32, scores (B,beam), valid_length (B,beam) int32 (BeamSearchSampler's result)."""
+        _require_cuda(mem, src_len, h0, c0)
+        B, T = mem.shape[0], mem.shape[1]
+        dev = mem.device
+        samples = torch.empty((B, beam, max_len + 2), dtype=torch.int32, device=dev)
+        scores = torch.empty((B, beam), dtype=torch.float32, device=dev)
+        vlen = torch.empty((B, beam), dtype=torch.int32, device=dev)
+        out_len = ctypes.c_int(0)
+        ws, wsb = self._workspace(B * beam, max_len, dev)
+        sl = self._i32(src_len)
+        check(lib().tn_gnmt_beam_search(self._h, dptr(mem.contiguous()), dptr(sl), dptr(h0.contiguous()),
+                                        dptr(None if c0 is None else c0.contiguous()), B, T, beam, max_len, float(alpha),
+                                        float(K), bos, eos, dptr(samples), dptr(scores), dptr(vlen), ctypes.byref(out_len), ws,
+                                        wsb, stream_ptr()))
+        return samples[:, :, : out_len.value].contiguous(), scores, vlen
