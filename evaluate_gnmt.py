@@ -1,0 +1,104 @@
+"""Captioner evaluation (same CLI surface as the reference's evaluate_gnmt.py; its two latent bugs -- undefined
+transform_train, evaluate() arity -- are fixed).
+
+    python evaluate_gnmt.py --feats_model 0006 --cell_type lstm --beam_size 5 --synthetic
+"""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+from absl import app, flags
+
+from tennis_b200 import cli
+from tennis_b200.dataset import TennisSet
+from tennis_b200.metrics.vision import compute_bleu
+from tennis_b200.models.captioning.gnmt import BeamSearchScorer
+from tennis_b200.utils.captioning import get_comp_str, get_dataloaders, write_sentences
+from tennis_b200.utils.translation import BeamSearchTranslator
+from tennis_b200.vocab import load_embedding_file
+
+cli.define_captioner_flags(training=False)
+FLAGS = flags.FLAGS
+
+
+def masked_ce_host(logits, labels, vl):
+    """MaskedSoftmaxCELoss (A.8) on the logits copied back to the host -- evaluation-only bookkeeping, not the hot path."""
+    logp = torch.log_softmax(logits.float().cpu(), dim=-1)
+    ce = -logp.gather(-1, labels.long().cpu().unsqueeze(-1)).squeeze(-1)
+    T = logits.shape[1]
+    w = (torch.arange(T).reshape(1, T) < vl.cpu().reshape(-1, 1)).float()
+    return (ce * w).mean(dim=1)
+
+
+def run_eval(data_loader, model, translator, vocab, ctx):
+    translation_out, all_ids = [], []
+    avg_loss, denom, ntok = 0.0, 0, 0
+    tic = time.time()
+    for src, tgt, src_vl, tgt_vl, inst_ids in data_loader:
+        src, tgt = src.to(ctx).float(), tgt.to(ctx).float()
+        src_vl, tgt_vl = src_vl.to(ctx), tgt_vl.to(ctx)
+        out, _ = model(src, tgt[:, :-1], src_vl, tgt_vl - 1)
+        loss = masked_ce_host(out, tgt[:, 1:], tgt_vl - 1).mean().item()
+        all_ids.extend(inst_ids.tolist())
+        avg_loss += loss * (tgt.shape[1] - 1)
+        denom += tgt.shape[1] - 1
+        samples, _, vlen = translator.translate(src_seq=src, src_valid_length=src_vl)
+        best, vbest = samples[:, 0, :].cpu().numpy(), vlen[:, 0].cpu().numpy()
+        for i in range(best.shape[0]):
+            toks = [vocab.idx_to_token[e] for e in best[i][1:(vbest[i] - 1)]]
+            ntok += len(toks)
+            translation_out.append(toks)
+    real = [None] * len(all_ids)
+    for ind, sent in zip(all_ids, translation_out):
+        real[ind] = sent
+    dt = time.time() - tic
+    logging.info('decoded %d caption tokens in %.2fs (%.1f tokens/sec)', ntok, dt, ntok / max(dt, 1e-9))
+    return avg_loss / max(1, denom), real
+
+
+def main(_argv):
+    ctx = cli.context()
+    exp_dir = os.path.join('models', 'captioning', 'experiments', FLAGS.model_id)
+    cli.setup_logging(exp_dir)
+    syn = {} if FLAGS.synthetic else None
+    data_train = TennisSet(split='train', captions=True, max_cap_len=FLAGS.tgt_max_len, every=FLAGS.every,
+                           feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
+    data_val = TennisSet(split='val', captions=True, vocab=data_train.vocab, every=FLAGS.every, inference=True,
+                         feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
+    data_test = TennisSet(split='test', captions=True, vocab=data_train.vocab, every=FLAGS.every, inference=True,
+                          feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
+    embedding = None
+    emb_path = os.path.join('data', FLAGS.emb_file) if FLAGS.emb_file else None
+    if emb_path and os.path.exists(emb_path):
+        data_train.vocab.set_embedding(load_embedding_file(emb_path))
+        embedding = data_train.vocab.embedding.idx_to_vec
+    model = cli.build_captioner(ctx, data_train.vocab, embedding)
+    path = os.path.join(exp_dir, 'valid_best.params')
+    if not os.path.exists(path):
+        path, _ = cli.latest_params(exp_dir)
+    if path is not None:
+        model.load_parameters(path, ctx=ctx)
+        logging.info('Loaded model params: %s', path)
+    else:
+        logging.warning('no checkpoint under %s: evaluating freshly initialised weights', exp_dir)
+    translator = BeamSearchTranslator(model=model, beam_size=FLAGS.beam_size,
+                                      scorer=BeamSearchScorer(alpha=FLAGS.lp_alpha, K=FLAGS.lp_k),
+                                      max_length=FLAGS.tgt_max_len + 100)
+    logging.info('Use beam_size=%d, alpha=%s, K=%d', FLAGS.beam_size, FLAGS.lp_alpha, FLAGS.lp_k)
+    _, val_loader, test_loader = get_dataloaders(data_train, data_val, data_test, FLAGS.batch_size, FLAGS.test_batch_size,
+                                                 FLAGS.num_buckets)
+    for name, loader, data in (('val', val_loader, data_val), ('test', test_loader, data_test)):
+        refs = data.get_captions(split=True)
+        loss, out = run_eval(loader, model, translator, data_train.vocab, ctx)
+        bleu, _, bp, ref_len, out_len = compute_bleu([[r] for r in refs], out)
+        logging.info('%s loss=%.4f ppl=%.4f bleu=%.2f (bp %.3f, ref %d, out %d)', name, loss, np.exp(min(loss, 50)), bleu * 100, bp,
+                     ref_len, out_len)
+        write_sentences(out, os.path.join(exp_dir, 'best_%s_out.txt' % name))
+        write_sentences(refs, os.path.join(exp_dir, '%s_gt.txt' % name))
+        print(get_comp_str(refs[:2], out[:2]))
+
+
+if __name__ == '__main__':
+    app.run(main)

@@ -1,0 +1,171 @@
+"""TennisSet: sample assembly of the reference's dataset.py for the hot path.
+
+Real mode (data/splits, data/annotations/... present): frame / feature path scheme and windowing exactly as the
+reference (dataset.py:135-150, 186-233); annotation parsing itself is out of scope and is delegated
+to a small split-file reader.  Synthetic mode (no dataset on disk, `synthetic=` given or TENNIS_SYNTHETIC=1): a seeded
+procedural stand-in with the same sample tuples, so the scripts, the batching code and the kernels see the shapes
+and index semantics of the real thing:
+    events : (img (T,3,S,S) | (3,S,S) | feats (T,D), label int, idx int)
+    captions: (frames (n,3,S,S) | feats (n,D), cap ids int32 [bos ... eos], n, len(cap)[, idx])
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+from .vocab import Vocab, count_tokens
+
+CLASSES = ['OTH', 'SFI', 'SFF', 'SFL', 'SNI', 'SNF', 'SNL', 'HFL', 'HFR', 'HNL', 'HNR']  # data/classes.names
+
+
+def window_frames(center, window, stride, every, video_length):
+    """Frame indices of a clip (reference dataset.py:190-201): offsets int(-W/2) .. ceil(W/2)-1, each clamped to
+    [0, last frame that is a multiple of `every`]; clamping duplicates edge frames (Appendix C #16)."""
+    offsets = list(range(int(-window / 2), int(math.ceil(window / 2))))
+    max_frame = video_length - every
+    for i in range(every):
+        if (max_frame - i) % every == 0:
+            max_frame -= i
+            break
+    return [min(max(0, center + off * stride), int(max_frame)) for off in offsets]
+
+
+def image_path(root_dir, video_name, frame_number, chunk_size=1000):
+    chunk = int(frame_number / chunk_size) * chunk_size
+    return os.path.join(root_dir, video_name + '.mp4', '{:010d}'.format(chunk), '{:010d}.jpg'.format(frame_number))
+
+
+def feature_path(feat_dir, video_name, frame_number, chunk_size=1000):
+    chunk = int(frame_number / chunk_size) * chunk_size
+    return os.path.join(feat_dir, video_name + '.mp4', '{:010d}'.format(chunk), '{:010d}.npy'.format(frame_number))
+
+
+_WORDS = ("the player serves ball into net far near left right forehand backhand hits return and it goes out wide long "
+          "down line cross court fault in play point won by winner rally short deep body t first second").split()
+
+
+class TennisSet(object):
+    def __init__(self, root='data', captions=False, transform=None, split='train', every=1, balance=True, padding=1,
+                 stride=1, window=1, model_id='0000', split_id='02', flow=False, max_cap_len=-1, vocab=None,
+                 inference=False, feats_model=None, save_feats=False, synthetic=None, data_shape=224):
+        if flow:
+            raise NotImplementedError("optical-flow inputs (TwoStreamModel) are outside the hot path")
+        self._root, self._captions, self._split = root, captions, split
+        self._balance, self._every, self._padding, self._stride, self._window = balance, every, padding, stride, window
+        self._transform, self._inference, self._save_feats = transform, inference, save_feats
+        self._frames_dir = os.path.join(root, "frames")
+        self._splits_dir = os.path.join(root, "splits")
+        self.output_dir = os.path.join(root, "outputs", model_id, split)
+        self._load_feats = feats_model is not None
+        self.feat_dir = os.path.join(root, "features", feats_model if feats_model is not None else model_id)
+        self.classes = list(CLASSES)
+        self._shape = data_shape
+        splits_file = os.path.join(self._splits_dir, split_id, split + '.txt')
+        if synthetic is None and (os.environ.get("TENNIS_SYNTHETIC") == "1" or not os.path.exists(splits_file)):
+            synthetic = {}
+        self._synthetic = synthetic
+        if synthetic is not None:
+            self._init_synthetic(**synthetic)
+        else:
+            self._init_real(splits_file)
+        if self._captions:
+            self._samples = list(self._points.keys())
+            words = ' '.join(p[4] for p in self._points.values()).split()
+            self.vocab = vocab if vocab is not None else Vocab(count_tokens(words))
+            for pid in self._samples:
+                toks = self._points[pid][4].split()
+                ids = self.vocab[toks[:max_cap_len]] if max_cap_len >= 0 else self.vocab[toks]
+                ids = [self.vocab[self.vocab.bos_token]] + ids + [self.vocab[self.vocab.eos_token]]
+                self._points[pid] = self._points[pid][:5] + [np.array(ids, dtype=np.int32)]
+
+    # ------------------------------------------------------------------ sources
+    def _init_synthetic(self, num_videos=2, frames_per_video=96, num_points=6, feat_dim=1024, seed=0):
+        self._seed = {'train': 1, 'val': 2, 'test': 3}.get(self._split, 4) * 1000 + seed
+        self._feat_dim = feat_dim
+        rng = np.random.RandomState(self._seed)
+        self._videos = ['V%03d' % i for i in range(num_videos)]
+        self._video_lengths = {v: frames_per_video for v in self._videos}
+        self._samples = []
+        for v in self._videos:
+            for f in range(0, frames_per_video, self._every):
+                self._samples.append([v, f, self.classes[int(rng.randint(0, len(self.classes)))]])
+        self._points = {}
+        for i in range(num_points):
+            v = self._videos[i % num_videos]
+            n = int(rng.randint(8, max(9, frames_per_video // 2)))
+            start = int(rng.randint(0, frames_per_video - n))
+            cap = ' '.join(_WORDS[int(j)] for j in rng.randint(0, len(_WORDS), size=int(rng.randint(4, 12))))
+            self._points['P%04d' % i] = [v, start, start + n, 'point', cap]
+
+    def _init_real(self, splits_file):
+        with open(splits_file) as f:
+            rows = [line.split() for line in f if line.strip()]
+        self._samples = [[r[0], int(r[1]), r[2] if len(r) > 2 else 'OTH'] for r in rows]
+        self._videos = sorted({s[0] for s in self._samples})
+        self._video_lengths = {v: max(s[1] for s in self._samples if s[0] == v) + 1 for v in self._videos}
+        self._points = {}
+        if self._captions:
+            raise FileNotFoundError("caption annotations need data/annotations (not available offline); use synthetic mode")
+
+    # ------------------------------------------------------------------ access
+    def __len__(self):
+        return len(self._samples)
+
+    def _load_frame(self, video, frame):
+        """-> fp32 (3,S,S) normalised tensor (what the reference's test transform yields) or a (D,) feature."""
+        if self._synthetic is not None:
+            g = torch.Generator().manual_seed(hash((self._seed, video, int(frame))) % (2 ** 31))
+            if self._load_feats:
+                return torch.randn(self._feat_dim, generator=g).relu()
+            return torch.randn(3, self._shape, self._shape, generator=g)
+        if self._load_feats:
+            return torch.from_numpy(np.load(feature_path(self.feat_dir, video, frame)).astype(np.float32))
+        import cv2
+        img = cv2.cvtColor(cv2.imread(image_path(self._frames_dir, video, frame), 1), cv2.COLOR_BGR2RGB)
+        t = torch.from_numpy(img)
+        return self._transform(t) if self._transform is not None else t
+
+    def __getitem__(self, idx):
+        sample = self._samples[idx]
+        if self._captions:
+            vid, start, end = self._points[sample][0], int(self._points[sample][1]), int(self._points[sample][2])
+            cap = self._points[sample][5]
+            imgs = [self._load_frame(vid, f) for c, f in enumerate(range(start, end)) if c % self._every == 0]
+            imgs = torch.stack(imgs)
+            if self._inference:
+                return imgs, cap, len(imgs), len(cap), idx
+            return imgs, cap, len(imgs), len(cap)
+        label = self.classes.index(sample[2])
+        if self._window > 1:
+            frames = window_frames(sample[1], self._window, self._stride, self._every, self._video_lengths[sample[0]])
+            img = torch.stack([self._load_frame(sample[0], f) for f in frames])
+        else:
+            img = self._load_frame(sample[0], sample[1])
+        return img, label, idx
+
+    def get_data_lens(self):
+        assert self._captions
+        return [(int((int(self._points[s][2]) - int(self._points[s][1]) + 1) / self._every), len(self._points[s][5]))
+                for s in self._samples]
+
+    def get_captions(self, ids=False, split=False):
+        out = []
+        for s in self._samples:
+            cap = self._points[s][4]
+            out.append(self._points[s][5] if ids else (cap.split() if split else cap))
+        return out
+
+    def save_feature_path(self, idx, chunk_size=1000):
+        s = self._samples[idx]
+        return feature_path(self.feat_dir, s[0], s[1], chunk_size)
+
+    def class_counts(self):
+        counts = [0] * len(self.classes)
+        for s in self._samples:
+            counts[self.classes.index(s[2])] += 1
+        return counts
+
+    @property
+    def num_class(self):
+        return len(self.classes)

@@ -1,0 +1,97 @@
+"""Caption batching (mirror of the reference's utils/captioning.py + the gluonnlp pieces it uses):
+Pad(0)/Stack batchify, FixedBucketSampler with constant-width buckets, sentence IO."""
+import io
+
+import numpy as np
+import torch
+
+
+def pad_stack(seqs, pad_val=0):
+    """gluonnlp batchify.Pad(axis=0, pad_val=0): pad along the first axis to the longest sample, then stack."""
+    seqs = [torch.as_tensor(s) for s in seqs]
+    n = max(s.shape[0] for s in seqs)
+    out = torch.full((len(seqs), n) + tuple(seqs[0].shape[1:]), pad_val, dtype=seqs[0].dtype)
+    for i, s in enumerate(seqs):
+        out[i, : s.shape[0]] = s
+    return out
+
+
+def train_batchify(samples):
+    src, tgt, sl, tl = zip(*samples)
+    return pad_stack(src), pad_stack(tgt), torch.tensor(sl, dtype=torch.float32), torch.tensor(tl, dtype=torch.float32)
+
+
+def test_batchify(samples):
+    src, tgt, sl, tl, idx = zip(*samples)
+    return (pad_stack(src), pad_stack(tgt), torch.tensor(sl, dtype=torch.float32), torch.tensor(tl, dtype=torch.float32),
+            torch.tensor(idx))
+
+
+class FixedBucketSampler(object):
+    """gluonnlp FixedBucketSampler with ConstWidthBucket: `num_buckets` equal-width length buckets (keyed on the max of a
+    sample's lengths when tuples are given), batches drawn bucket by bucket."""
+
+    def __init__(self, lengths, batch_size, num_buckets=5, shuffle=False, seed=0):
+        keys = [max(l) if isinstance(l, (tuple, list)) else l for l in lengths]
+        lo, hi = min(keys), max(keys)
+        width = max(1, int(np.ceil((hi - lo + 1) / float(num_buckets))))
+        buckets = [[] for _ in range(num_buckets)]
+        for i, k in enumerate(keys):
+            buckets[min((k - lo) // width, num_buckets - 1)].append(i)
+        self._batches = []
+        for b in buckets:
+            for j in range(0, len(b), batch_size):
+                self._batches.append(b[j: j + batch_size])
+        self._shuffle, self._rng = shuffle, np.random.RandomState(seed)
+
+    def __iter__(self):
+        order = list(range(len(self._batches)))
+        if self._shuffle:
+            self._rng.shuffle(order)
+        for i in order:
+            yield self._batches[i]
+
+    def __len__(self):
+        return len(self._batches)
+
+
+class DataLoader(object):
+    def __init__(self, dataset, batch_sampler, batchify_fn):
+        self._d, self._s, self._f = dataset, batch_sampler, batchify_fn
+
+    def __iter__(self):
+        for idxs in self._s:
+            yield self._f([self._d[i] for i in idxs])
+
+    def __len__(self):
+        return len(self._s)
+
+
+def get_dataloaders(data_train, data_val, data_test, batch_size=128, test_batch_size=32, num_buckets=5):
+    """reference utils/captioning.py:28-86 (bucket_scheme 'constant')."""
+    tr = DataLoader(data_train, FixedBucketSampler(data_train.get_data_lens(), batch_size, num_buckets, shuffle=True),
+                    train_batchify)
+    va = DataLoader(data_val, FixedBucketSampler([l[-1] for l in data_val.get_data_lens()], test_batch_size, num_buckets),
+                    test_batchify)
+    te = DataLoader(data_test, FixedBucketSampler([l[-1] for l in data_test.get_data_lens()], test_batch_size, num_buckets),
+                    test_batchify)
+    return tr, va, te
+
+
+def write_sentences(sentences, file_path):
+    with io.open(file_path, 'w', encoding='utf-8') as of:
+        for sent in sentences:
+            of.write((u' '.join(sent) if isinstance(sent, (list, tuple)) else sent) + u'\n')
+
+
+def read_sentences(file_path):
+    with io.open(file_path, 'r', encoding='utf-8') as f:
+        return [line.rstrip('\n').split() for line in f]
+
+
+def get_comp_str(tgts, prds):
+    out = ''
+    for tgt, prd in zip(tgts, prds):
+        out += 'GT:\t' + (' '.join(tgt) if isinstance(tgt, (list, tuple)) else tgt) + '\n'
+        out += '\nPD:\t' + (' '.join(prd) if isinstance(prd, (list, tuple)) else prd) + '\n\n\n'
+    return out
