@@ -287,6 +287,11 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(prof["conv_launches"] + prof["other_launches"]),
             "clocks": clocks,
         }
+        if world == 1:
+            try:
+                line["captioner"] = bench_captioner(device)
+            except Exception as exc:  # the headline metric must still be reported
+                line["captioner"] = {"error": repr(exc)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -307,6 +312,59 @@ def _capture_stdout():
 def emit(line):
     _REAL_STDOUT.write(json.dumps(line) + "\n")
     _REAL_STDOUT.flush()
+
+
+def bench_captioner(device, steps=3):
+    """BASELINE.json configs[3]: GNMT captioner, 1024-d features -> 2-layer LSTM enc/dec + attention, V=254, beam 5.
+    Returns caption tokens/s (best beam, BOS/EOS stripped, train_gnmt.py:289-294) from host features to host token ids,
+    next to the CPU oracle port timed on a bounded sample (4 sentences)."""
+    import torch
+    from oracle import captioning as C
+    from tennis_b200.gluon import Dropout, Embedding, HybridSequential
+    from tennis_b200.models.captioning.gnmt import BeamSearchScorer, NMTModel, get_gnmt_encoder_decoder
+    from tennis_b200.utils.translation import BeamSearchTranslator
+    from tennis_b200.vocab import Vocab, count_tokens
+    B, Tsrc, D, H, E, V, beam, max_len = 32, 224, 1024, 128, 100, 254, 5, 150
+    p = C.synthetic_gnmt_params(seed=10000, scale=0.35, cell="lstm", H=H, D_src=D, E=E, V=V)
+    vocab = Vocab(count_tokens(["w%03d" % i for i in range(V - 4)]))
+    src_embed = HybridSequential()
+    src_embed.add(Dropout(0.0))
+    enc, dec = get_gnmt_encoder_decoder(cell_type="lstm", hidden_size=H, dropout=0.0, num_layers=2, num_bi_layers=1)
+    model = NMTModel(src_vocab=None, tgt_vocab=vocab, encoder=enc, decoder=dec, embed_size=E, prefix="gnmt_",
+                     src_embed=src_embed, tgt_embed=Embedding(V, E))
+    params = model.collect_params()
+    for k, v in p.items():
+        params[k].shape, params[k]._data = tuple(v.shape), v.to(device)
+        params[k]._version += 1
+    x, vl = C.synthetic_sources(B, Tsrc, D, seed=100, min_len=64)
+    xh, vlh = x.pin_memory(), vl.pin_memory()
+    tr = BeamSearchTranslator(model, beam_size=beam, scorer=BeamSearchScorer(alpha=1.0, K=5), max_length=max_len)
+
+    def run():
+        s, _, v = tr.translate(xh.to(device, non_blocking=True), vlh.to(device, non_blocking=True))
+        v = v.cpu()
+        return s.cpu(), v, int((v[:, 0] - 2).clamp(min=0).sum())
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    toks = 0
+    for _ in range(steps):
+        s, v, n = run()
+        toks += n
+    dt = time.perf_counter() - t0
+    # CPU port on a bounded sample, checked for token equality on that sample
+    nb = 4
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        s_ref, _, v_ref = C.translate(p, x[:nb], vl[:nb], cell="lstm", H=H, beam=beam, max_length=max_len)
+    dt_cpu = time.perf_counter() - t1
+    same = C.best_tokens(s_ref, v_ref) == C.best_tokens(s[:nb], v[:nb])
+    return {"metric": "caption tokens/sec (GNMT LSTM, beam 5)", "value": toks / dt, "unit": "tokens/s",
+            "config": {"workload": "configs[3]: B=32 sources x T_src<=224 x 1024-d, H=128, V=254, beam=5, max_length=150",
+                       "decode_steps_per_call": int(s.shape[2]) - 1, "host_to_host": True},
+            "cpu_baseline": {"value": float((v_ref[:, 0] - 2).clamp(min=0).sum()) / dt_cpu, "unit": "tokens/s",
+                             "cores": torch.get_num_threads(), "kind": "port", "sample": "%d of the 32 sources" % nb},
+            "token_ids_equal_to_oracle_on_sample": bool(same)}
 
 
 def main():
