@@ -16,7 +16,8 @@
 //     with warp shuffles + a 1 KB smem exchange between the four epilogue warps), cast to bf16 and written into the
 //     dense block's concat buffer at its channel offset.  Rows 0 and 127 of a tile have no neighbour: tiles advance
 //     by 126 rows.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue.  TMEM accumulators
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue (two per TMEM lane
+// quarter, 16 of the 32 output channels each).  TMEM accumulators
 // are double-buffered (2 x 96 columns) so the epilogue of tile i overlaps the MMAs of tile i+1; the halo tile is
 // double-buffered when it fits.
 #include <cuda.h>
@@ -30,7 +31,7 @@ namespace tn {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;            // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kTileRows = 126;         // valid outputs per tile
 constexpr int kN = 96;                 // 3 dx taps x 32 output channels
 constexpr int kWBlob = kN * 128;       // one (dy, half) weight blob: 96 rows x 64 bf16, swizzled
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   uint64_t* acc_empty = acc_full + 2;                    // [2]
   uint64_t* w_full = acc_empty + 2;                      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* xch = reinterpret_cast<float*>(tail + 128);     // [2 parity][4 warps][2][32]
+  float* xch = reinterpret_cast<float*>(tail + 128);     // [2 parity][2 halves][4 quarters][2][16]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[i], 8);  // one arrive per epilogue warp
     }
     mbar_init(w_full, 1);
     mbar_fence_init();
@@ -146,42 +147,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarter warp&3)
+    // ------------------------------------------------------------ epilogue (warps 2..9: lane quarter warp&3, channel half)
     const int qw = warp & 3;              // lanes 32*qw .. 32*qw+31
+    const int hf = (warp - 2) >> 2;       // output channels [16*hf, 16*hf+16)
     const int r = qw * 32 + lane;         // accumulator row of this thread
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int ab = it & 1;
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t v0[32], v1[32], v2[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * kN;
-      tmem_ld32(taddr, v0);
-      tmem_ld32(taddr + 32, v1);
-      tmem_ld32(taddr + 64, v2);
+      uint32_t v0[16], v1[16], v2[16];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * kN + hf * 16;
+      tmem_ld16(taddr, v0);
+      tmem_ld16(taddr + 32, v1);
+      tmem_ld16(taddr + 64, v2);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ab]);  // accumulator drained: MMA warp may overwrite it
 
-      float* x = xch + (it & 1) * 256;
-      // publish the rows the neighbouring warps need: my last row's dx=-1 part, my first row's dx=+1 part
+      float* x = xch + (it & 1) * 256 + hf * 128;
+      // publish the rows the neighbouring quarters need: my last row's dx=-1 part, my first row's dx=+1 part
       if (lane == 31) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[(qw * 2 + 0) * 32 + j] = __uint_as_float(v0[j]);
+        for (int j = 0; j < 16; ++j) x[(qw * 2 + 0) * 16 + j] = __uint_as_float(v0[j]);
       }
       if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[(qw * 2 + 1) * 32 + j] = __uint_as_float(v2[j]);
+        for (int j = 0; j < 16; ++j) x[(qw * 2 + 1) * 16 + j] = __uint_as_float(v2[j]);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float o[32];
+      if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      float o[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < 16; ++j) {
         float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);      // D[r-1][j]
         float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);    // D[r+1][64+j]
-        if (lane == 0 && qw > 0) up = x[((qw - 1) * 2 + 0) * 32 + j];
-        if (lane == 31 && qw < 3) dn = x[((qw + 1) * 2 + 1) * 32 + j];
+        if (lane == 0 && qw > 0) up = x[((qw - 1) * 2 + 0) * 16 + j];
+        if (lane == 31 && qw < 3) dn = x[((qw + 1) * 2 + 1) * 16 + j];
         o[j] = up + __uint_as_float(v1[j]) + dn;
       }
       const int q = t * kTileRows - 1 + r;
@@ -192,9 +195,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         const int xp = rem - yp * p.Wp;
         if (yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(f * p.H + yp - 1) * p.W + (xp - 1)) * p.out_cstride +
-                                                p.out_coff);
+                                                p.out_coff + hf * 16);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
             dst[c] = make_uint4(pack_bf16x2(o[8 * c], o[8 * c + 1]), pack_bf16x2(o[8 * c + 2], o[8 * c + 3]),
                                 pack_bf16x2(o[8 * c + 4], o[8 * c + 5]), pack_bf16x2(o[8 * c + 6], o[8 * c + 7]));
         }

@@ -97,20 +97,35 @@ class HostPipeline(object):
             self._dev_bufs = (key, [torch.empty(shape, dtype=dtype, device=device) for _ in range(2)])
         return self._dev_bufs[1]
 
+    def _schedule(self, B):
+        if B < 16 or self.chunks <= 1:
+            n = max(1, min(self.chunks, B))
+            per = (B + n - 1) // n
+            return [min(B, i * per) for i in range(n)] + [B]
+        cuts, size, lo = [0], max(1, B // 16), 0
+        while lo < B:
+            lo = lo + size if B - (lo + size) >= size else B  # fold a short tail into the last chunk
+            cuts.append(lo)
+            size *= 2
+        return cuts
+
     def forward(self, clips_host):
         """clips_host: pinned (B,T,3,H,W) fp32 [or (B,T,H,W,3) uint8] host tensor -> (B*world, C) fp32 host tensor."""
         assert not clips_host.is_cuda
         B, T = clips_host.shape[:2]
         dev = torch.device("cuda", torch.cuda.current_device())
-        nch = min(self.chunks, B)
-        per = (B + nch - 1) // nch
+        # chunk schedule: a small first chunk so compute starts after ~1/16 of the copy, then growing chunks so the
+        # kernels keep large grids (H2D of chunk i+1 overlaps the backbone of chunk i)
+        bounds = self._schedule(B)
+        nch = len(bounds) - 1
+        per = max(bounds[i + 1] - bounds[i] for i in range(nch))
         main = torch.cuda.current_stream()
         bufs = self._bufs((per,) + tuple(clips_host.shape[1:]), clips_host.dtype, dev)
         feats_all, twin_all = [], []
         ready = [torch.cuda.Event() for _ in range(nch)]
         consumed = [torch.cuda.Event() for _ in range(nch)]
         for i in range(nch):
-            lo, hi = i * per, min(B, (i + 1) * per)
+            lo, hi = bounds[i], bounds[i + 1]
             with torch.cuda.stream(self.copy_stream):
                 if i >= 2:
                     self.copy_stream.wait_event(consumed[i - 2])
