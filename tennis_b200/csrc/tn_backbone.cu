@@ -10,6 +10,7 @@
 #include "tn_common.h"
 #include "tn_conv3x3.h"
 #include "tn_elementwise.h"
+#include "tn_stem.h"
 
 namespace {
 
@@ -42,6 +43,7 @@ struct tn_backbone {
   tn::DeviceArena arena;
   // stem (both archs)
   tn::ConvDev stem;
+  tn::StemDev stem_s2d;
   tn::BnDev bn0;
   float in_scale[3] = {1, 1, 1}, in_shift[3] = {0, 0, 0};  // ResNet-v2 bn_data folded into the input conversion
   // DenseNet
@@ -114,6 +116,28 @@ bool take_conv(Cursor& cur, DeviceArena& arena, int Cout, int Cin, int R, int S,
   const float* w = cur.take(static_cast<size_t>(Cout) * Cin * R * S);
   if (!w) return false;
   return make_conv(arena, w, Cout, Cin, R, S, mode, cv);
+}
+// 7x7/2 stem as a 4x4/1 conv on the space-to-depth image: weights (64,3,7,7) -> (64, 64 = 4 px x 16 ch, 4 rows, 1)
+bool take_stem_bn(Cursor& cur, DeviceArena& arena, ConvDev* cv, BnDev* bn, StemDev* sd) {
+  const float* w = cur.take(static_cast<size_t>(64) * 3 * 49);
+  if (!w) return false;
+  std::vector<float> hs, hb;
+  if (!take_bn(cur, arena, 64, bn, &hs, &hb)) return false;
+  if (!make_stem(arena, w, hs.data(), sd)) return false;
+  std::vector<float> ws(static_cast<size_t>(64) * 64 * 4, 0.f);  // [n][ci = b*16 + (py*2+px)*3 + c][a][0]
+  for (int n = 0; n < 64; ++n)
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b)
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) {
+            const int r = 2 * a + py - 1, s = 2 * b + px - 1;  // W8[u][v] = W[u-1][v-1]
+            if (r < 0 || s < 0 || r > 6 || s > 6) continue;
+            for (int c = 0; c < 3; ++c) {
+              const int ci = b * 16 + (py * 2 + px) * 3 + c;
+              ws[(static_cast<size_t>(n) * 64 + ci) * 4 + a] = w[((static_cast<size_t>(n) * 3 + c) * 7 + r) * 7 + s];
+            }
+          }
+  return make_conv(arena, ws.data(), 64, 64, 4, 1, kModeConv, cv, hs.data());
 }
 // conv followed (in parameter order) by the BatchNorm whose scale is folded into its weights; the shift stays in `bn`
 bool take_conv_bn(Cursor& cur, DeviceArena& arena, int Cout, int Cin, int R, int S, int mode, ConvDev* cv, BnDev* bn) {
@@ -227,8 +251,8 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
 
   // stem: conv7x7/2 -> BN -> ReLU (epilogue) ; max-pool 3/2/1 into channels [0,64) of block 1
   {
-    ConvGemmParams p = conv_params(bb->stem, in4, 4, n, d.H0, d.W0, d.Hs, d.Ws, 2, 3, nullptr, stem, 64, 0, &bb->bn0, true);
-    TN_CUDA(launch_conv_gemm(p, st));
+    // 7x7/2 stem == 4x4/1 conv on the zero-padded space-to-depth image (tn_stem.cu), BN folded, ReLU
+    TN_CUDA(launch_stem_s2d(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, bb->bn0.shift, stem, bb->num_sms, st));
     TN_CUDA(launch_maxpool3s2(stem, blk[0], n, d.Hs, d.Ws, 64, d.Hp, d.Wp, pl.ctot[0], 0, st));
   }
   for (int b = 0; b < 4; ++b) {
@@ -273,8 +297,8 @@ int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int 
   __nv_bfloat16* rb = ws.get<__nv_bfloat16>(act);
   if (dry) return TN_OK;
   {
-    ConvGemmParams p = conv_params(bb->stem, in4, 4, n, d.H0, d.W0, d.Hs, d.Ws, 2, 3, nullptr, stem, 64, 0, &bb->bn0, true);
-    TN_CUDA(launch_conv_gemm(p, st));
+    // 7x7/2 stem == 4x4/1 conv on the zero-padded space-to-depth image (tn_stem.cu), BN folded, ReLU
+    TN_CUDA(launch_stem_s2d(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, bb->bn0.shift, stem, bb->num_sms, st));
     TN_CUDA(launch_maxpool3s2(stem, xa, n, d.Hs, d.Ws, 64, d.Hp, d.Wp, 64, 0, st));
   }
   int H = d.Hp, W = d.Wp;
@@ -311,10 +335,12 @@ int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int 
 int backbone_run(tn_backbone* bb, const void* frames, int dtype, int n, int h, int w, float* feats, void* feats_bf16,
                  void* workspace, bool dry, size_t* need, cudaStream_t st) {
   Bump ws{static_cast<uint8_t*>(workspace)};
-  __nv_bfloat16* in4 = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * h * w * 4);
+  const Dims sd = stem_dims(h, w);
+  const int Hz = sd.Hs + 3, Wz = sd.Ws + 3;  // zero-padded space-to-depth image, 16 ch per pixel
+  __nv_bfloat16* in4 = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * Hz * Wz * 16);
   if (!dry) {
     if (dtype == TN_FRAMES_F32_NCHW) {
-      TN_CUDA(launch_convert_nchw_f32(static_cast<const float*>(frames), in4, n, h, w, bb->in_scale, bb->in_shift, st));
+      TN_CUDA(launch_s2d_convert(frames, 0, in4, n, h, w, Hz, Wz, bb->in_scale, bb->in_shift, st));
     } else if (dtype == TN_FRAMES_U8_NHWC) {
       // ToTensor (/255) + Normalize(mean,std) (train.py:142-147), then the arch's input affine
       const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
@@ -324,7 +350,7 @@ int backbone_run(tn_backbone* bb, const void* frames, int dtype, int n, int h, i
         s[c] = s1 * bb->in_scale[c];
         b[c] = b1 * bb->in_scale[c] + bb->in_shift[c];
       }
-      TN_CUDA(launch_convert_nhwc_u8(static_cast<const uint8_t*>(frames), in4, n, h, w, s, b, st));
+      TN_CUDA(launch_s2d_convert(frames, 1, in4, n, h, w, Hz, Wz, s, b, st));
     } else {
       return set_error(TN_ERR_INVALID, "unknown frames dtype %d", dtype);
     }
@@ -372,7 +398,7 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
   Cursor cur{params, n_params};
   bool ok = true;
   if (arch == TN_ARCH_DENSENET121) {
-    ok = ok && take_conv_bn(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem, &bb->bn0);
+    ok = ok && take_stem_bn(cur, bb->arena, &bb->stem, &bb->bn0, &bb->stem_s2d);
     int c = 64;
     for (int b = 0; b < 4 && ok; ++b) {
       for (int l = 0; l < kDenseCfg[b] && ok; ++l) {
@@ -404,7 +430,7 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
         bb->in_shift[i] = hb[i];
       }
     }
-    ok = ok && take_conv_bn(cur, bb->arena, 64, 3, 7, 7, tn::kModeStem, &bb->stem, &bb->bn0);
+    ok = ok && take_stem_bn(cur, bb->arena, &bb->stem, &bb->bn0, &bb->stem_s2d);
     int cin = 64;
     const int ch[4] = {64, 128, 256, 512};
     for (int s = 0; s < 4 && ok; ++s) {

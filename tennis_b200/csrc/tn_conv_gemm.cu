@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
-          const int ch = c * 64 + g * 8;
+          const int ch = (c % p.chunks_per_tap) * 64 + g * 8;
           ScaleShift8 ss;
           const bool ch_ok = ch < p.Cin;
           if (ch_ok) load_ss8(p.pro_scale, p.pro_shift, ch, ss);
@@ -265,7 +265,8 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
           mbar_arrive_expect_tx(&tma_full[stage], static_cast<uint32_t>(kABytes + (RESIDENT ? 0 : C::kBBytes)));
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-              ::"r"(smem_u32(st_base)), "l"(&tmap), "r"(c * 64), "r"(tile * kBM), "r"(smem_u32(&tma_full[stage]))
+              ::"r"(smem_u32(st_base)), "l"(&tmap), "r"((c % p.chunks_per_tap) * 64),
+                "r"(tile * kBM + (c / p.chunks_per_tap) * p.tma_tap_rows), "r"(smem_u32(&tma_full[stage]))
               : "memory");
           if (!RESIDENT) bulk_g2s(st_base + kABytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &tma_full[stage]);
           if (++stage == NS) {
@@ -531,7 +532,14 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
       int orow = -1;
       if (m < p.M) {
         orow = m;
-        if (p.out_pad) {
+        if (p.out_pad == 2) {  // rows enumerate the input grid; keep y < Ho, x < Wo
+          const int ghw = p.H * p.W;
+          const int f = m / ghw;
+          const int rem = m - f * ghw;
+          const int y = rem / p.W;
+          const int x = rem - y * p.W;
+          orow = (y < p.Ho && x < p.Wo) ? (f * p.Ho + y) * p.Wo + x : -1;
+        } else if (p.out_pad) {
           const int f = m / hw;
           const int rem = m - f * hw;
           const int oy = rem / p.Wo;
@@ -632,6 +640,11 @@ cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
     if (!encode) return cudaErrorNotSupported;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.in_cstride), static_cast<cuuint64_t>(p.M)};
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.in_cstride) * sizeof(__nv_bfloat16)};
+    if (p.tma_taps > 0) {
+      gdim[0] = static_cast<cuuint64_t>(p.chunks_per_tap) * 64;
+      gdim[1] = static_cast<cuuint64_t>(p.tma_rows);
+      gstride[0] = static_cast<cuuint64_t>(p.tma_row_bytes);
+    }
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kBM)};
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p.in), gdim, gstride, box, estr,
@@ -659,9 +672,10 @@ template <int BN>
 cudaError_t launch_bn(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   // 1x1 / stride-1 convs (every DenseNet bottleneck conv, the RNN input projection): A tiles are plain 2-D boxes of the
   // activation matrix -> TMA fetches them, the producer warps only apply BN+ReLU in place
-  const bool tma_ok = p.mode == kModeConv && p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.H == p.Ho &&
-                      p.W == p.Wo && (p.in_cstride % 64) == 0 && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
-                      p.num_chunks * 64 <= p.in_cstride;
+  const bool tma_ok = (p.tma_taps > 0) ||
+                      (p.mode == kModeConv && p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.H == p.Ho &&
+                       p.W == p.Wo && (p.in_cstride % 64) == 0 && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
+                       p.num_chunks * 64 <= p.in_cstride);
   if constexpr (BN <= 128) {
     if (p.num_chunks <= kMaxResidentChunks) {  // weights stay resident in shared memory
       if (tma_ok) return launch_t<BN, kModeTma, true>(p, num_sms, stream);

@@ -35,6 +35,13 @@ struct ConvGemmParams {
   int out_coff;
   int out_fp32;  // 0 -> bf16, 1 -> fp32
   int out_pad;   // 1 -> output rows address a zero-padded (F, Ho+2, Wo+2, C) buffer (interior pixels only)
+                 // 2 -> GEMM rows enumerate the (H, W) INPUT grid; only rows with y < Ho and x < Wo are written, compacted
+  // "row-tap" TMA mode (space-to-depth stem): the A tile of K-chunk c is the 2-D box at row (tile*128 + (c / chunks_per_tap)
+  // * tma_tap_rows) of a tensor map with `tma_rows` rows of `tma_row_bytes` stride (rows may overlap: Toeplitz view).
+  int tma_taps;        // 0 = not used (1x1 convs are auto-detected), >0 = number of row taps
+  int tma_tap_rows;
+  long long tma_rows;
+  int tma_row_bytes;
   int Cout;      // multiple of 32
   // epilogue: y = relu?(acc + shift[n] + residual); a per-channel scale must be folded into the packed weights
   const float* epi_scale;  // must be null

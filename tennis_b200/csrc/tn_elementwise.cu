@@ -244,6 +244,60 @@ cudaError_t launch_cast_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStr
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- space-to-depth input for the 7x7/2 stem
+// A 7x7 / stride 2 / pad 3 conv equals a 4x4 / stride 1 conv on the 2x2 space-to-depth image (filter padded to 8x8):
+//   out(oy,ox) = sum_{a,b<4} sum_{py,px<2,c<3} W8[2a+py][2b+px][c] * Z[oy-2+a][ox-2+b][(py,px,c)],  W8[u][v] = W[u-1][v-1].
+// Z is stored zero-padded (2 px top/left, 1 px bottom/right) with 16 channels per pixel (12 used), so that one filter row
+// (4 px x 16 ch) is 128 contiguous bytes == one K-chunk of the implicit GEMM, fetched with plain 16-byte loads.
+template <typename SrcT, bool NHWC>
+__global__ void s2d_convert_kernel(const SrcT* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int H, int W, int Hz,
+                                   int Wz, float s0, float s1, float s2, float b0, float b1, float b2) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n) * Hz * Wz;
+  if (i >= total) return;
+  const int Xp = static_cast<int>(i % Wz);
+  const size_t t = i / Wz;
+  const int Yp = static_cast<int>(t % Hz);
+  const size_t f = t / Hz;
+  const float sc[3] = {s0, s1, s2}, sh[3] = {b0, b1, b2};
+  float v[12];
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const int y = 2 * (Yp - 2) + py, x = 2 * (Xp - 2) + px;
+      const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float val = 0.f;
+        if (ok) {
+          const size_t src = NHWC ? ((f * H + y) * W + x) * 3 + c : ((f * 3 + c) * H + y) * W + x;
+          val = static_cast<float>(in[src]) * sc[c] + sh[c];
+        }
+        v[(py * 2 + px) * 3 + c] = val;
+      }
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+  dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), 0u, 0u);
+}
+
+cudaError_t launch_s2d_convert(const void* in, int is_u8_nhwc, __nv_bfloat16* out, int n, int h, int w, int Hz, int Wz,
+                               const float* scale3, const float* shift3, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(n) * Hz * Wz;
+  if (total == 0) return cudaSuccess;
+  ProfScope prof_scope(kProfOther, st);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (is_u8_nhwc)
+    s2d_convert_kernel<uint8_t, true><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(in), out, n, h, w, Hz, Wz, scale3[0],
+                                                            scale3[1], scale3[2], shift3[0], shift3[1], shift3[2]);
+  else
+    s2d_convert_kernel<float, false><<<grid, 256, 0, st>>>(static_cast<const float*>(in), out, n, h, w, Hz, Wz, scale3[0],
+                                                           scale3[1], scale3[2], shift3[0], shift3[1], shift3[2]);
+  return cudaGetLastError();
+}
+
 // split-bf16 operand for the "precise" input projection: row m -> [hi(x) | lo(x) | hi(x)]
 __global__ void split3_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t M, int D) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -10,6 +10,9 @@ cudaError_t launch_convert_nchw_f32(const float* in, __nv_bfloat16* out, int n, 
                                     const float* shift3, cudaStream_t st);
 cudaError_t launch_convert_nhwc_u8(const uint8_t* in, __nv_bfloat16* out, int n, int h, int w, const float* scale3,
                                    const float* shift3, cudaStream_t st);
+// frames (fp32 NCHW or uint8 NHWC) -> zero-padded 2x2 space-to-depth image (n, Hz, Wz, 16) bf16 for the stem (see .cu)
+cudaError_t launch_s2d_convert(const void* in, int is_u8_nhwc, __nv_bfloat16* out, int n, int h, int w, int Hz, int Wz,
+                               const float* scale3, const float* shift3, cudaStream_t st);
 cudaError_t launch_maxpool3s2(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int H, int W, int C, int Ho, int Wo,
                               int out_cstride, int out_coff, cudaStream_t st);
 cudaError_t launch_tail_pool(const __nv_bfloat16* in, int n, int H, int W, int C, int cstride, int kh, int kw, int ph,

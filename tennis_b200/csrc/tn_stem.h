@@ -1,0 +1,20 @@
+// Persistent TMA + tcgen05 stem kernel (7x7/2 conv as a 4x4/1 conv on the space-to-depth image).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tn_common.h"
+
+namespace tn {
+
+struct StemDev {
+  const uint8_t* wpack = nullptr;  // 16 taps x (64 rows x 16 bf16), SWIZZLE_32B image, BN scale folded in
+};
+
+bool make_stem(DeviceArena& arena, const float* w_64x3x7x7, const float* fold_scale, StemDev* out);
+// z: zero-padded space-to-depth image (n, Hz, Wz, 16) bf16; out: (n, Ho, Wo, 64) bf16 = relu(conv + shift)
+cudaError_t launch_stem_s2d(const StemDev& sd, const __nv_bfloat16* z, int n, int Hz, int Wz, int Ho, int Wo, const float* shift,
+                            __nv_bfloat16* out, int num_sms, cudaStream_t st);
+
+}  // namespace tn
