@@ -121,6 +121,27 @@ int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t*
                      float* ymax, float* h_final, float* c_final, void* workspace, size_t workspace_bytes,
                      tn_stream_t stream);
 
+/* ------------------------------------------------------------------ training of the temporal head (V7, head-only)
+ * The published CNN-RNN (models/README.md id 0042) trains BiGRU(128)+max+Dense on frozen / pre-extracted features
+ * (train.py:197-217,231-236).  These entry points implement that step: forward with saved activations, softmax
+ * cross-entropy (gluon SoftmaxCrossEntropyLoss, train.py:324,419), backward (ag.backward, train.py:421) and the
+ * optimiser updates of gluon.Trainer.step (train.py:298-299,424; train_gnmt.py:310,337).  The CNN backward is not built. */
+int tn_birnn_forward_train(tn_birnn_t* r, const void* x, int x_is_bf16, int B, int T, float* y, float* ymax, float* gx,
+                           float* cseq, void* workspace, size_t workspace_bytes, tn_stream_t stream);
+size_t tn_birnn_backward_workspace_bytes(const tn_birnn_t* r, int B, int T);
+int tn_birnn_backward(tn_birnn_t* r, const void* x, int x_is_bf16, int B, int T, const float* gx, const float* y,
+                      const float* cseq, const float* ymax, const float* d_ymax, const float* dy, float* dW_ih, float* dW_hh,
+                      float* db_ih, float* db_hh, void* workspace, size_t workspace_bytes, tn_stream_t stream);
+/* loss (B) = -log_softmax(logits)[label]; dlogits (B,C) = softmax - onehot (head gradient 1 per sample); either may be NULL */
+int tn_softmax_ce(const float* logits, const int32_t* labels, float* loss, float* dlogits, int B, int C, tn_stream_t stream);
+int tn_dense_backward(const float* x, const float* weight, const float* dy, float* dx, float* dweight, float* dbias, int rows,
+                      int in_dim, int out_dim, tn_stream_t stream);
+/* sgd: g' = rescale*g + wd*w; m = momentum*m - lr*g'; w += m.   adam (step t >= 1): bias-corrected, eps outside sqrt. */
+int tn_sgd_mom_update(float* weight, const float* grad, float* mom, size_t n, float lr, float momentum, float wd,
+                      float rescale_grad, tn_stream_t stream);
+int tn_adam_update(float* weight, const float* grad, float* mean, float* var, size_t n, float lr, float beta1, float beta2,
+                   float eps, float wd, float rescale_grad, int t, tn_stream_t stream);
+
 /* ------------------------------------------------------------------ GNMT decoder + beam search
  * Replaces GNMTDecoder (models/captioning/gnmt.py:163-404) + gluonnlp NMTModel.decode_step/decode_seq glue
  * (tgt_embed, tgt_proj) and gluonnlp BeamSearchSampler/BeamSearchScorer as driven by

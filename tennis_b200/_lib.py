@@ -120,3 +120,17 @@ SIGNATURES.update({
                                     c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int),
                                     c_void_p, c_size_t, c_void_p]),
 })
+
+
+SIGNATURES.update({
+    "tn_birnn_forward_train": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
+    "tn_birnn_backward_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "tn_birnn_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tn_softmax_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tn_dense_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tn_sgd_mom_update": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_void_p]),
+    "tn_adam_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float,
+                               c_float, c_int, c_void_p]),
+})

@@ -18,6 +18,21 @@ struct tn_birnn {
   const float* bhh = nullptr;   // [ndir*G*H]
 };
 
+namespace tn {
+void birnn_dims(const tn_birnn* r, int* G, int* D, int* H, int* ndir) {
+  *G = r->gates;
+  *D = r->D;
+  *H = r->H;
+  *ndir = r->ndir;
+}
+const float* birnn_whhT(const tn_birnn* r) { return r->WhhT; }
+const float* birnn_bhh(const tn_birnn* r) { return r->bhh; }
+}  // namespace tn
+
+static int birnn_forward_impl(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t* valid_len, int B, int T, float* y,
+                              float* ymax, float* h_final, float* c_final, float* gx_out, float* cseq, void* workspace,
+                              size_t workspace_bytes, tn_stream_t stream);
+
 extern "C" {
 
 int tn_dense_forward(const float* x, const float* weight, const float* bias, float* y, int rows, int in_dim,
@@ -107,6 +122,23 @@ size_t tn_birnn_workspace_bytes(const tn_birnn_t* r, int B, int T) {
 int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t* valid_len, int B, int T, float* y,
                      float* ymax, float* h_final, float* c_final, void* workspace, size_t workspace_bytes,
                      tn_stream_t stream) {
+  return birnn_forward_impl(r, x, x_is_bf16, valid_len, B, T, y, ymax, h_final, c_final, nullptr, nullptr, workspace,
+                            workspace_bytes, stream);
+}
+
+// Forward that also keeps what the backward pass needs: gx (B*T, ndir*G*H) input-projection pre-activations and, for
+// LSTM, the cell state per step cseq (B,T,ndir*H).  y must be given.
+int tn_birnn_forward_train(tn_birnn_t* r, const void* x, int x_is_bf16, int B, int T, float* y, float* ymax, float* gx,
+                           float* cseq, void* workspace, size_t workspace_bytes, tn_stream_t stream) {
+  if (!y || !gx) return tn::set_error(TN_ERR_INVALID, "y and gx are required for training");
+  return birnn_forward_impl(r, x, x_is_bf16, nullptr, B, T, y, ymax, nullptr, nullptr, gx, cseq, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+static int birnn_forward_impl(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t* valid_len, int B, int T, float* y,
+                              float* ymax, float* h_final, float* c_final, float* gx_out, float* cseq, void* workspace,
+                              size_t workspace_bytes, tn_stream_t stream) {
   if (!r || B < 0 || T < 0) return tn::set_error(TN_ERR_INVALID, "bad rnn handle / shape");
   if (B == 0 || T == 0) return TN_OK;
   if (!x || !workspace) return tn::set_error(TN_ERR_INVALID, "null device pointer");
@@ -118,7 +150,7 @@ int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t*
   const int N = r->ndir * r->gates * r->H;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(ws);
-  float* gx = reinterpret_cast<float*>(ws + tn::align_up(M * 3 * r->D * sizeof(__nv_bfloat16), 1024));
+  float* gx = gx_out ? gx_out : reinterpret_cast<float*>(ws + tn::align_up(M * 3 * r->D * sizeof(__nv_bfloat16), 1024));
   const __nv_bfloat16* xin = static_cast<const __nv_bfloat16*>(x);
   const bool precise = r->precise && !x_is_bf16;
   const int Dk = precise ? 3 * r->D : r->D;
@@ -171,11 +203,10 @@ int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t*
   s.bhh = r->bhh;
   s.valid_len = valid_len;
   s.y = y;
+  s.cseq = cseq;
   s.ymax = ymax;
   s.h_final = h_final;
   s.c_final = c_final;
   TN_CUDA(tn::launch_rnn_scan(s, st));
   return TN_OK;
 }
-
-}  // extern "C"

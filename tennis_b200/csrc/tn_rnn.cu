@@ -159,6 +159,10 @@ __global__ void rnn_scan_kernel(const RnnScanParams p) {
           const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : it_len[n] - 1 - s;
           p.y[(static_cast<size_t>(b0 + b) * p.T + pos) * (p.ndir * H) + dir * H + q * HS + u] = hnew;
         }
+        if (G == 4 && p.cseq) {
+          const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : it_len[n] - 1 - s;
+          p.cseq[(static_cast<size_t>(b0 + b) * p.T + pos) * (p.ndir * H) + dir * H + q * HS + u] = it_c[n];
+        }
       }
       // publish (frozen rows re-publish their last state so both buffers stay coherent)
       const int hidx = (q * HS + u) * kRB + b;

@@ -18,6 +18,7 @@ struct RnnScanParams {
   const float* h0;       // nullable, [ndir][B][H]
   const float* c0;       // nullable, [ndir][B][H]
   float* y;              // nullable, [B][T][ndir*H]  (pre-zeroed by the caller when valid_len is given)
+  float* cseq;           // nullable, LSTM cell state per step [B][T][ndir*H] (saved for the backward pass)
   float* ymax;           // nullable, [B][ndir*H]   max over time
   float* h_final;        // nullable, [ndir][B][H]
   float* c_final;        // nullable, [ndir][B][H]

@@ -30,6 +30,7 @@ class Parameter(object):
         self.lr_mult = 1.0
         self.wd_mult = 1.0
         self._data = None
+        self._grad = None
         self._version = 0
 
     # -- Gluon-like accessors
@@ -37,6 +38,22 @@ class Parameter(object):
         if self._data is None:
             raise RuntimeError("Parameter '%s' has not been initialized" % self.name)
         return self._data
+
+    def grad(self, ctx=None):
+        if self._grad is None:
+            raise RuntimeError("Parameter '%s' has no gradient (grad_req=%s, backward not run?)" % (self.name, self.grad_req))
+        return self._grad
+
+    def zero_grad(self):
+        self._grad = None
+
+    def _accumulate_grad(self, g):
+        if self.grad_req == 'null':
+            return
+        self._grad = g.clone() if self._grad is None else self._grad + g
+
+    def _bump(self):
+        self._version += 1
 
     def list_ctx(self):
         return [] if self._data is None else [self._data.device]
@@ -298,6 +315,7 @@ class Dense(Block):
 
     def forward(self, x):
         from . import ops
+        x_orig = x  # the tape links tensors by object identity; reshape() below makes a new object
         lead = None
         if not self._flatten and x.dim() > 2:
             lead = x.shape[:-1]
@@ -308,6 +326,17 @@ class Dense(Block):
             self.weight._finish_deferred((self._units, x.shape[1]))
             self.weight.reset_ctx(x.device)
         y = ops.dense(x, self.weight.data(), None if self.bias is None else self.bias.data())
+        from . import autograd
+        if autograd.is_recording() and lead is None:
+            xin = x.contiguous().float()
+
+            def bwd(dy, xin=xin, self=self):
+                dx, dw, db = ops.dense_backward(xin, self.weight.data(), dy)
+                self.weight._accumulate_grad(dw)
+                if self.bias is not None:
+                    self.bias._accumulate_grad(db)
+                return dx.reshape(x_orig.shape)
+            autograd.tag(y, bwd, x_orig)
         return y if lead is None else y.reshape(tuple(lead) + (self._units,))
 
 
@@ -319,3 +348,63 @@ class Embedding(Block):
     def forward(self, ids):
         # pure gather (indexing, no arithmetic): rows of the table selected by (float or int) token ids
         return self.weight.data()[ids.long()]
+
+
+class SoftmaxCrossEntropyLoss(object):
+    """gluon.loss.SoftmaxCrossEntropyLoss(): -log_softmax(pred)[label] per sample -> (B,)  (train.py:324, A.8)."""
+
+    def __call__(self, pred, label):
+        from . import autograd, ops
+        loss, dlogits = ops.softmax_ce(pred, label, want_grad=autograd.is_recording())
+        if autograd.is_recording():
+            autograd.tag(loss, lambda g, d=dlogits: d * g.reshape(-1, 1), pred)
+        return loss
+
+
+class Trainer(object):
+    """gluon.Trainer(params, 'sgd'|'adam', {...}) as the scripts use it (train.py:298-299,424; train_gnmt.py:310,337):
+    step(n) rescales the summed gradients by 1/n, applies wd to EVERY parameter (Gluon wd_mult = 1) and updates in place.
+    With torch.distributed initialised, gradients are summed across ranks first (the reference's KVStore('device') sum)."""
+
+    def __init__(self, params, optimizer, optimizer_params=None):
+        self._params = [p for p in (params.values() if hasattr(params, "values") else params)]
+        self._opt = optimizer.lower()
+        if self._opt not in ("sgd", "adam"):
+            raise ValueError("optimizer must be 'sgd' or 'adam'")
+        op = dict(optimizer_params or {})
+        self._lr = float(op.get("learning_rate", 0.01))
+        self._momentum = float(op.get("momentum", 0.0))
+        self._wd = float(op.get("wd", 0.0))
+        self._b1, self._b2, self._eps = float(op.get("beta1", 0.9)), float(op.get("beta2", 0.999)), float(op.get("epsilon", 1e-8))
+        self._state = {}
+        self._t = 0
+
+    @property
+    def learning_rate(self):
+        return self._lr
+
+    def set_learning_rate(self, lr):
+        self._lr = float(lr)
+
+    def step(self, batch_size, ignore_stale_grad=False):
+        import torch.distributed as dist
+        from . import ops
+        self._t += 1
+        for p in self._params:
+            if p.grad_req == 'null' or p._grad is None:
+                continue
+            g = p._grad.contiguous()
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(g)
+            w = p.data()
+            st = self._state.get(id(p))
+            if self._opt == "sgd":
+                if st is None:
+                    st = self._state[id(p)] = (torch.zeros_like(w),)
+                ops.sgd_mom_update(w, g, st[0], self._lr, self._momentum, self._wd, 1.0 / batch_size)
+            else:
+                if st is None:
+                    st = self._state[id(p)] = (torch.zeros_like(w), torch.zeros_like(w))
+                ops.adam_update(w, g, st[0], st[1], self._lr, self._b1, self._b2, self._eps, self._wd, 1.0 / batch_size, self._t)
+            p._bump()
+            p._grad = None

@@ -91,6 +91,11 @@ class Features(Block):
 
     def forward(self, x):
         ops._require_cuda(x)
+        from . import autograd
+        if autograd.is_recording() and any(p.grad_req != 'null' for n, p in self._reg_params.items()
+                                           if not n.endswith(("running_mean", "running_var"))):
+            raise NotImplementedError("the CNN backward pass is not built: train with --freeze_backbone or --feats_model "
+                                      "(the published CNN-RNN setting), see DESIGN.md section 8")
         eng = self._get_engine(x.device)
         feats, fb = eng(x, want_bf16=True)
         feats._tn_bf16 = fb  # bf16 twin written by the same kernel; lets the RNN skip a cast pass

@@ -213,6 +213,52 @@ class BiRNN:
                                          stream_ptr()))
         return {"y": y, "ymax": ymax, "h": h, "c": c}
 
+    def forward_train(self, x):
+        """Forward keeping the activations the backward needs.  -> dict(y, ymax, gx, cseq, x)."""
+        _require_cuda(x)
+        B, T, D = x.shape
+        x = x.contiguous()
+        dev = x.device
+        G = 3 if self.cell == "gru" else 4
+        y = torch.empty((B, T, self.ndir * self.H), dtype=torch.float32, device=dev)
+        ymax = torch.empty((B, self.ndir * self.H), dtype=torch.float32, device=dev)
+        gx = torch.empty((B * T, self.ndir * G * self.H), dtype=torch.float32, device=dev)
+        cseq = torch.empty_like(y) if self.cell == "lstm" else None
+        need = lib().tn_birnn_workspace_bytes(self._h, B, T)
+        if self._ws is None or self._ws_bytes < need:
+            self._ws = None
+            self._ws = _workspace(need, dev)
+            self._ws_bytes = need
+        check(lib().tn_birnn_forward_train(self._h, dptr(x), int(x.dtype == torch.bfloat16), B, T, dptr(y), dptr(ymax), dptr(gx),
+                                           dptr(cseq), c_void_p(self._ws[1]), self._ws_bytes, stream_ptr()))
+        return {"y": y, "ymax": ymax, "gx": gx, "cseq": cseq, "x": x}
+
+    def backward(self, saved, d_ymax=None, dy=None):
+        """-> dict of gradients keyed like the Gluon parameters (l0_i2h_weight, ..., r0_h2h_bias)."""
+        x = saved["x"]
+        B, T, D = x.shape
+        G = 3 if self.cell == "gru" else 4
+        GH = G * self.H
+        dev = x.device
+        dWih = torch.empty((self.ndir * GH, D), dtype=torch.float32, device=dev)
+        dWhh = torch.empty((self.ndir * GH, self.H), dtype=torch.float32, device=dev)
+        dbih = torch.empty((self.ndir * GH,), dtype=torch.float32, device=dev)
+        dbhh = torch.empty((self.ndir * GH,), dtype=torch.float32, device=dev)
+        need = lib().tn_birnn_backward_workspace_bytes(self._h, B, T)
+        buf, ptr = _workspace(need, dev)
+        check(lib().tn_birnn_backward(self._h, dptr(x), int(x.dtype == torch.bfloat16), B, T, dptr(saved["gx"]), dptr(saved["y"]),
+                                      dptr(saved["cseq"]), dptr(saved["ymax"]),
+                                      dptr(None if d_ymax is None else d_ymax.contiguous().float()),
+                                      dptr(None if dy is None else dy.contiguous().float()), dptr(dWih), dptr(dWhh), dptr(dbih),
+                                      dptr(dbhh), c_void_p(ptr), need, stream_ptr()))
+        out = {}
+        for i, d in enumerate(["l0", "r0"][: self.ndir]):
+            out[d + "_i2h_weight"] = dWih[i * GH:(i + 1) * GH]
+            out[d + "_h2h_weight"] = dWhh[i * GH:(i + 1) * GH]
+            out[d + "_i2h_bias"] = dbih[i * GH:(i + 1) * GH]
+            out[d + "_h2h_bias"] = dbhh[i * GH:(i + 1) * GH]
+        return out
+
 
 class GNMTDecoderEngine:
     """GNMT decoder + target embedding/projection + beam search on the device (tn_gnmt_*)."""
@@ -303,3 +349,42 @@ class GNMTDecoderEngine:
                                         float(K), bos, eos, dptr(samples), dptr(scores), dptr(vlen), ctypes.byref(out_len), ws,
                                         wsb, stream_ptr()))
         return samples[:, :, : out_len.value].contiguous(), scores, vlen
+
+
+def softmax_ce(logits, labels, want_grad=False):
+    """-> (loss (B,), dlogits (B,C) or None)."""
+    _require_cuda(logits, labels)
+    B, C = logits.shape
+    logits = logits.contiguous().float()
+    lab = labels.to(torch.int32).contiguous()
+    loss = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    check(lib().tn_softmax_ce(dptr(logits), dptr(lab), dptr(loss), dptr(dl), B, C, stream_ptr()))
+    return loss, dl
+
+
+def dense_backward(x, weight, dy):
+    """-> (dx (R,in), dW (out,in), db (out))."""
+    _require_cuda(x, weight, dy)
+    R, in_dim = x.shape
+    out_dim = weight.shape[0]
+    dy = dy.contiguous().float()
+    dx = torch.empty((R, in_dim), dtype=torch.float32, device=x.device)
+    dw = torch.empty((out_dim, in_dim), dtype=torch.float32, device=x.device)
+    db = torch.empty((out_dim,), dtype=torch.float32, device=x.device)
+    check(lib().tn_dense_backward(dptr(x), dptr(weight.contiguous()), dptr(dy), dptr(dx), dptr(dw), dptr(db), R, in_dim, out_dim,
+                                  stream_ptr()))
+    return dx, dw, db
+
+
+def sgd_mom_update(w, g, mom, lr, momentum, wd, rescale):
+    _require_cuda(w, g, mom)
+    assert w.is_contiguous() and mom.is_contiguous()
+    check(lib().tn_sgd_mom_update(dptr(w), dptr(g.contiguous()), dptr(mom), w.numel(), lr, momentum, wd, rescale, stream_ptr()))
+
+
+def adam_update(w, g, mean, var, lr, b1, b2, eps, wd, rescale, t):
+    _require_cuda(w, g, mean, var)
+    assert w.is_contiguous()
+    check(lib().tn_adam_update(dptr(w), dptr(g.contiguous()), dptr(mean), dptr(var), w.numel(), lr, b1, b2, eps, wd, rescale, t,
+                               stream_ptr()))

@@ -21,16 +21,17 @@ class _RNNLayer(Block):
         self._engine = None
         self._engine_key = None
 
-    def _get_engine(self, x):
+    def _get_engine(self, x, precise=False):
         D = x.shape[2]
         for n, p in self._reg_params.items():
             if p._data is None and n.endswith('_i2h_weight'):
                 p._finish_deferred((self._gates * self._hidden_size, D))
                 p.reset_ctx(x.device)
-        key = (x.device.index or 0,) + tuple(p._version for p in self._reg_params.values())
+        key = (x.device.index or 0, precise) + tuple(p._version for p in self._reg_params.values())
         if self._engine is None or self._engine_key != key:
             params = {n: p.data() for n, p in self._reg_params.items()}
-            self._engine = ops.BiRNN(self._cell, D, self._hidden_size, params, self._bidirectional, device=x.device.index or 0)
+            self._engine = ops.BiRNN(self._cell, D, self._hidden_size, params, self._bidirectional, device=x.device.index or 0,
+                                     precise=precise)
             self._engine_key = key
         return self._engine
 
@@ -39,14 +40,35 @@ class _RNNLayer(Block):
         twin = getattr(x, "_tn_bf16", None)
         return twin if twin is not None else x
 
+    def _train_forward(self, x, pooled):
+        from . import autograd
+        # training runs the input projection in split-bf16 on the fp32 features: the max-over-time arg-max (which routes
+        # the gradient) must not flip on bf16 rounding noise
+        eng = self._get_engine(x, precise=True)
+        saved = eng.forward_train(x.float())
+        out = saved["ymax"] if pooled else saved["y"]
+
+        def bwd(g, eng=eng, saved=saved, self=self):
+            grads = eng.backward(saved, d_ymax=g if pooled else None, dy=None if pooled else g)
+            for name, gr in grads.items():
+                self._reg_params[name]._accumulate_grad(gr)
+            return None  # the per-frame features are leaves (frozen / pre-extracted backbone)
+        return autograd.tag(out, bwd, None)
+
     def forward(self, x):
         """(B,T,D) -> (B,T,ndir*H)."""
+        from . import autograd
         ops._require_cuda(x)
+        if autograd.is_recording():
+            return self._train_forward(x, pooled=False)
         return self._get_engine(x)(self._pick_input(x), want_y=True)["y"]
 
     def forward_max(self, x):
         """max over time of the layer output, fused into the scan: (B,T,D) -> (B,ndir*H) (definitions.py:106-107)."""
+        from . import autograd
         ops._require_cuda(x)
+        if autograd.is_recording():
+            return self._train_forward(x, pooled=True)
         return self._get_engine(x)(self._pick_input(x), want_y=False, want_max=True)["ymax"]
 
 
