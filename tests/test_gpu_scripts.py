@@ -40,3 +40,23 @@ def test_evaluate_gnmt_synthetic(tmp_path):
                 "--test_batch_size", "4", "--tgt_max_len", "10", "--synthetic", "--model_id", "t101"], str(tmp_path))
     assert "tokens/sec" in out and "bleu=" in out
     assert os.path.exists(os.path.join(str(tmp_path), "models", "captioning", "experiments", "t101", "best_test_out.txt"))
+
+
+def test_train_head_on_features_synthetic_and_resume(tmp_path):
+    """The published CNN-RNN setting (features -> BiGRU -> max -> Dense): two epochs, checkpoints, scores.txt, resume."""
+    args = [os.path.join(ROOT, "train.py"), "--feats_model", "0006", "--temp_pool", "gru", "--window", "8", "--batch_size", "16",
+            "--every", "4,8,8", "--epochs", "2", "--log_interval", "2", "--lr", "0.05", "--synthetic", "--model_id", "t042"]
+    out = _run(args, str(tmp_path))
+    exp = os.path.join(str(tmp_path), "models", "vision", "experiments", "t042")
+    assert os.path.exists(os.path.join(exp, "0000.params")) and os.path.exists(os.path.join(exp, "0001.params"))
+    assert len(open(os.path.join(exp, "scores.txt")).read().split()) == 4
+    assert "test AVG_NB_f1" in out
+    out2 = _run(args[:args.index("--epochs")] + ["--epochs", "3"] + args[args.index("--epochs") + 2:], str(tmp_path))
+    assert "Loaded model params" in out2 and os.path.exists(os.path.join(exp, "0002.params"))
+
+
+def test_train_frozen_backbone_cnn_gru(tmp_path):
+    out = _run([os.path.join(ROOT, "train.py"), "--backbone", "resnet18_v2", "--freeze_backbone", "--temp_pool", "gru", "--window", "4",
+                "--data_shape", "224", "--batch_size", "4", "--every", "24,48,48", "--epochs", "1", "--synthetic", "--model_id",
+                "t043"], str(tmp_path))
+    assert "validation" in out

@@ -1,0 +1,130 @@
+"""Event-detector training (same CLI surface as the reference's train.py).
+
+The backward pass covers the temporal head (Dense, BiGRU/LSTM + max-over-time): use `--feats_model <id>` (the published
+CNN-RNN 0042 setting) or `--freeze_backbone`; a trainable CNN raises (its backward is not built).
+
+    python train.py --feats_model 0006 --temp_pool gru --window 30 --synthetic --epochs 2
+    python train.py --backbone DenseNet121 --freeze_backbone --temp_pool gru --window 8 --data_shape 224 --synthetic
+"""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+from absl import app, flags
+
+from tennis_b200 import autograd as ag
+from tennis_b200 import cli
+from tennis_b200.dataset import TennisSet
+from tennis_b200.gluon import SoftmaxCrossEntropyLoss, Trainer
+from tennis_b200.metrics.vision import PRF1, Accuracy
+from tennis_b200.models.vision.definitions import TemporalPooling
+
+cli.define_detector_flags(training=True)
+FLAGS = flags.FLAGS
+
+
+def batches(dataset, batch_size, shuffle, seed):
+    order = list(range(len(dataset)))
+    if shuffle:
+        np.random.RandomState(seed).shuffle(order)
+    for lo in range(0, len(order), batch_size):
+        items = [dataset[i] for i in order[lo:lo + batch_size]]
+        yield (torch.stack([it[0] for it in items]), torch.tensor([it[1] for it in items]),
+               torch.tensor([it[2] for it in items]))
+
+
+def test_model(net, dataset, ctx, metrics, batch_size):
+    """reference train.py:503-527."""
+    for m in metrics:
+        m.reset()
+    for data, labels, _ in batches(dataset, batch_size, False, 0):
+        out = net(data.to(ctx, non_blocking=True)).cpu()
+        for m in metrics:
+            m.update([labels], [out])
+    return metrics
+
+
+def train_model(model, train_set, val_set, trainer, loss_fn, ctx, exp_dir, start_epoch):
+    """reference train.py:388-500: epoch loop, LR steps, per-epoch validation, scores.txt, NNNN.params."""
+    train_metrics = [Accuracy(), PRF1(label_names=train_set.classes)]
+    val_metrics = [Accuracy(), Accuracy('top5', top_k=5), PRF1(label_names=val_set.classes)]
+    lr_steps = sorted(FLAGS.lr_steps)
+    lr_counter = sum(1 for s in lr_steps if s <= start_epoch)  # derived from the resume point (Appendix C #9)
+    trainer.set_learning_rate(FLAGS.lr * (FLAGS.lr_factor ** lr_counter))
+    for epoch in range(start_epoch, FLAGS.epochs):
+        if lr_counter < len(lr_steps) and epoch == lr_steps[lr_counter]:
+            trainer.set_learning_rate(trainer.learning_rate * FLAGS.lr_factor)
+            lr_counter += 1
+        for m in train_metrics:
+            m.reset()
+        tic, btic, train_loss = time.time(), time.time(), 0.0
+        for i, (data, labels, _) in enumerate(batches(train_set, FLAGS.batch_size, True, epoch)):
+            if FLAGS.max_batches > 0 and i >= FLAGS.max_batches:
+                break
+            data, dl = data.to(ctx, non_blocking=True), labels.to(ctx)
+            with ag.record():
+                out = model(data)
+                loss = loss_fn(out, dl)
+            ag.backward([loss])
+            trainer.step(FLAGS.batch_size)
+            train_loss += loss.mean().item()  # device -> host sync point, as in the reference (train.py:427)
+            for m in train_metrics:
+                m.update([labels], [out.cpu()])
+            if FLAGS.log_interval and (i + 1) % FLAGS.log_interval == 0:
+                name, acc = train_metrics[0].get()
+                logging.info('[Epoch %d] [Batch %d] Speed: %.3f samples/sec, %s=%.4f, lr=%.6f', epoch, i + 1,
+                             FLAGS.batch_size * FLAGS.log_interval / max(1e-9, time.time() - btic), name, acc, trainer.learning_rate)
+                btic = time.time()
+        nb = max(1, i + 1)
+        logging.info('[Epoch %d] training: loss=%.4f %s=%.4f time: %.1fs', epoch, train_loss / nb, *train_metrics[0].get(),
+                     time.time() - tic)
+        tic = time.time()
+        test_model(model, val_set, ctx, val_metrics, FLAGS.batch_size)
+        scores = dict(val_metrics[2].get())
+        logging.info('[Epoch %d] validation: acc=%.4f AVG_NB_f1=%.4f time: %.1fs', epoch, val_metrics[0].get()[1], scores['AVG_NB_f1'],
+                     time.time() - tic)
+        with open(os.path.join(exp_dir, 'scores.txt'), 'a') as f:
+            f.write('%04d %.4f\n' % (epoch, scores['AVG_NB_f1']))
+        model.save_parameters(os.path.join(exp_dir, '%04d.params' % epoch))
+
+
+def main(_argv):
+    cli.parse_list_flags()
+    ctx = cli.context()
+    exp_dir = os.path.join('models', 'vision', 'experiments', FLAGS.model_id)
+    cli.setup_logging(exp_dir)
+    syn = {} if FLAGS.synthetic else None
+    common = dict(padding=FLAGS.padding, stride=FLAGS.stride, window=FLAGS.window, model_id=FLAGS.model_id, split_id=FLAGS.split_id,
+                  feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
+    train_set = TennisSet(split='train', balance=FLAGS.balance[0], every=FLAGS.every[0], **common)
+    val_set = TennisSet(split='val', balance=FLAGS.balance[1], every=FLAGS.every[1], **common)
+    test_set = TennisSet(split='test', balance=FLAGS.balance[2], every=FLAGS.every[2], **common)
+    logging.info('train/val/test: %d / %d / %d samples', len(train_set), len(val_set), len(test_set))
+    model = cli.build_detector(ctx, len(train_set.classes))
+    path, start_epoch = cli.latest_params(exp_dir)
+    if path is not None:
+        x0 = train_set[0][0].unsqueeze(0).to(ctx)
+        model(x0)  # resolve deferred shapes before loading
+        model.load_parameters(path, ctx=ctx)
+        logging.info('Loaded model params: %s', path)
+    trainer = Trainer(model.collect_params(), 'sgd', {'learning_rate': FLAGS.lr, 'momentum': FLAGS.momentum, 'wd': FLAGS.wd})
+    train_model(model, train_set, val_set, trainer, SoftmaxCrossEntropyLoss(), ctx, exp_dir, start_epoch)
+    best = cli.best_epoch(exp_dir)
+    if best is not None:
+        model.load_parameters(os.path.join(exp_dir, '%04d.params' % best), ctx=ctx)
+        logging.info('Testing best epoch %d', best)
+    net = model
+    if FLAGS.temp_pool in ('max', 'mean') and FLAGS.window > 1 and FLAGS.feats_model is None:
+        net = TemporalPooling(model, pool=FLAGS.temp_pool, num_classes=0, feats=False)  # train.py:349-351
+    metrics = test_model(net, test_set, ctx, [Accuracy(), Accuracy('top5', top_k=5), PRF1(label_names=test_set.classes)],
+                         FLAGS.batch_size)
+    print(metrics[2].mat.astype(int))
+    print('test %s: %.4f' % metrics[0].get())
+    for k, v in metrics[2].get()[-6:]:
+        print('test %s: %.4f' % (k, v))
+
+
+if __name__ == '__main__':
+    app.run(main)
