@@ -13,6 +13,7 @@ from absl import app, flags
 
 from tennis_b200 import cli
 from tennis_b200.dataset import TennisSet
+from tennis_b200.gluon import MaskedSoftmaxCELoss
 from tennis_b200.metrics.vision import compute_bleu
 from tennis_b200.models.captioning.gnmt import BeamSearchScorer
 from tennis_b200.utils.captioning import get_comp_str, get_dataloaders, write_sentences
@@ -21,15 +22,7 @@ from tennis_b200.vocab import load_embedding_file
 
 cli.define_captioner_flags(training=False)
 FLAGS = flags.FLAGS
-
-
-def masked_ce_host(logits, labels, vl):
-    """MaskedSoftmaxCELoss (A.8) on the logits copied back to the host -- evaluation-only bookkeeping, not the hot path."""
-    logp = torch.log_softmax(logits.float().cpu(), dim=-1)
-    ce = -logp.gather(-1, labels.long().cpu().unsqueeze(-1)).squeeze(-1)
-    T = logits.shape[1]
-    w = (torch.arange(T).reshape(1, T) < vl.cpu().reshape(-1, 1)).float()
-    return (ce * w).mean(dim=1)
+loss_function = MaskedSoftmaxCELoss()
 
 
 def run_eval(data_loader, model, translator, vocab, ctx):
@@ -40,7 +33,7 @@ def run_eval(data_loader, model, translator, vocab, ctx):
         src, tgt = src.to(ctx).float(), tgt.to(ctx).float()
         src_vl, tgt_vl = src_vl.to(ctx), tgt_vl.to(ctx)
         out, _ = model(src, tgt[:, :-1], src_vl, tgt_vl - 1)
-        loss = masked_ce_host(out, tgt[:, 1:], tgt_vl - 1).mean().item()
+        loss = loss_function(out, tgt[:, 1:], tgt_vl - 1).mean().item()
         all_ids.extend(inst_ids.tolist())
         avg_loss += loss * (tgt.shape[1] - 1)
         denom += tgt.shape[1] - 1

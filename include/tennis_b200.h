@@ -134,6 +134,10 @@ int tn_birnn_backward(tn_birnn_t* r, const void* x, int x_is_bf16, int B, int T,
                       float* db_ih, float* db_hh, void* workspace, size_t workspace_bytes, tn_stream_t stream);
 /* loss (B) = -log_softmax(logits)[label]; dlogits (B,C) = softmax - onehot (head gradient 1 per sample); either may be NULL */
 int tn_softmax_ce(const float* logits, const int32_t* labels, float* loss, float* dlogits, int B, int C, tn_stream_t stream);
+/* gluonnlp MaskedSoftmaxCELoss forward (train_gnmt.py:256,282,332): pred (B,T,V), label (B,T) float ids, valid_len (B) float
+ * -> loss (B) = sum_{t < valid_len} CE_t / T. */
+int tn_masked_softmax_ce(const float* pred, const float* label, const float* valid_len, float* loss, int B, int T, int V,
+                         tn_stream_t stream);
 int tn_dense_backward(const float* x, const float* weight, const float* dy, float* dx, float* dweight, float* dbias, int rows,
                       int in_dim, int out_dim, tn_stream_t stream);
 /* sgd: g' = rescale*g + wd*w; m = momentum*m - lr*g'; w += m.   adam (step t >= 1): bias-corrected, eps outside sqrt. */

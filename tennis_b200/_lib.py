@@ -134,3 +134,5 @@ SIGNATURES.update({
     "tn_adam_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float,
                                c_float, c_int, c_void_p]),
 })
+
+SIGNATURES["tn_masked_softmax_ce"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])

@@ -3,12 +3,14 @@
 // helpers.  Activations live in HBM as NHWC bf16; a dense block is ONE buffer of its final channel count
 // and every dense layer writes its 32 new channels in place (concat == channel offset).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
 
 #include "tn_common.h"
 #include "tn_conv3x3.h"
+#include "tn_dense_fused.h"
 #include "tn_elementwise.h"
 #include "tn_stem.h"
 
@@ -259,7 +261,18 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
     const int H = pl.Hb[b], W = pl.Wb[b], ct = pl.ctot[b];
     const bool halo = conv3x3_halo_supported(H, W) && static_cast<long long>(n) * (H + 2) * (W + 2) < (1ll << 31) - 4096;
     if (halo) TN_CUDA(launch_zero_border(bott, n, H + 2, W + 2, kBott, st));
+    // EXPERIMENTAL (off by default): one fused kernel per dense layer, bottleneck kept in shared memory (tn_dense_fused.cu).
+    // Numerically identical to the two-kernel path, but with one tile in flight per SM its phases serialise and it measures
+    // slower (31.8 vs 25.8 ms/2048 frames); enable with TN_DENSE_FUSED_MIN_W=<min map width>, e.g. 28 for blocks 1-2.
+    const char* fused_env = getenv("TN_DENSE_FUSED_MIN_W");
+    const int fused_min_w = fused_env ? atoi(fused_env) : (1 << 30);
+    const bool fused = dense_fused_supported(H, W) && W >= fused_min_w;
     for (const DenseLayer& L : bb->layers[b]) {
+      if (fused) {
+        TN_CUDA(launch_dense_layer_fused(blk[b], ct, n, H, W, L.cin, L.bn1.scale, L.bn1.shift, L.conv1.wpack, L.conv1.num_chunks,
+                                         L.bn2.shift, L.conv2h.wpack, bb->num_sms, st));
+        continue;
+      }
       // BN1+ReLU (prologue) -> 1x1 conv -> BN2+ReLU (epilogue) -> bottleneck
       ConvGemmParams p1 = conv_params(L.conv1, blk[b], ct, n, H, W, H, W, 1, 0, &L.bn1, bott, kBott, 0, &L.bn2, true);
       p1.out_pad = halo ? 1 : 0;

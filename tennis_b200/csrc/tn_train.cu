@@ -226,6 +226,31 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int* _
     for (int c = 0; c < C; ++c) dlogits[static_cast<size_t>(b) * C + c] = expf(x[c] - lse) - (c == y ? 1.f : 0.f);
 }
 
+// gluonnlp MaskedSoftmaxCELoss (A.8): per-token CE x SequenceMask(valid_len) weights, MEAN over the padded length T -> (B,)
+__global__ void __launch_bounds__(128) masked_ce_kernel(const float* __restrict__ pred, const float* __restrict__ label,
+                                                        const float* __restrict__ vlen, float* __restrict__ loss, int T, int V) {
+  __shared__ float red[4];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = min(max(static_cast<int>(vlen[b]), 0), T);
+  float total = 0.f;
+  for (int t = warp; t < len; t += 4) {  // one warp per valid token
+    const float* x = pred + (static_cast<size_t>(b) * T + t) * V;
+    float m = -INFINITY;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, x[v]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(x[v] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int y = min(max(static_cast<int>(lrintf(label[static_cast<size_t>(b) * T + t])), 0), V - 1);
+    total += (m + logf(s)) - x[y];
+  }
+  if (lane == 0) red[warp] = total;
+  __syncthreads();
+  if (tid == 0) loss[b] = (red[0] + red[1] + red[2] + red[3]) / static_cast<float>(T);
+}
+
 // Dense backward: dW[j][k] = sum_r dy[r][j] x[r][k]; db[j] = sum_r dy[r][j]; dx[r][k] = sum_j dy[r][j] W[j][k]
 __global__ void dense_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dW,
                                    float* __restrict__ db, int R, int in_dim, int out_dim) {
@@ -294,6 +319,18 @@ int tn_softmax_ce(const float* logits, const int32_t* labels, float* loss, float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope ps(kProfOther, st);
   softmax_ce_kernel<<<(B + 127) / 128, 128, 0, st>>>(logits, labels, loss, dlogits, B, C);
+  TN_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
+int tn_masked_softmax_ce(const float* pred, const float* label, const float* valid_len, float* loss, int B, int T, int V,
+                         tn_stream_t stream) {
+  if (B < 0 || T <= 0 || V <= 0) return set_error(TN_ERR_INVALID, "bad shape");
+  if (B == 0) return TN_OK;
+  if (!pred || !label || !valid_len || !loss) return set_error(TN_ERR_INVALID, "null device pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps(kProfOther, st);
+  masked_ce_kernel<<<B, 128, 0, st>>>(pred, label, valid_len, loss, T, V);
   TN_CUDA(cudaGetLastError());
   return TN_OK;
 }

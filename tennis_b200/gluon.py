@@ -361,6 +361,14 @@ class SoftmaxCrossEntropyLoss(object):
         return loss
 
 
+class MaskedSoftmaxCELoss(object):
+    """gluonnlp.loss.MaskedSoftmaxCELoss forward (train_gnmt.py:256): (B,T,V) logits, (B,T) labels, (B,) valid lengths -> (B,)."""
+
+    def __call__(self, pred, label, valid_length):
+        from . import ops
+        return ops.masked_softmax_ce(pred, label, valid_length)
+
+
 class Trainer(object):
     """gluon.Trainer(params, 'sgd'|'adam', {...}) as the scripts use it (train.py:298-299,424; train_gnmt.py:310,337):
     step(n) rescales the summed gradients by 1/n, applies wd to EVERY parameter (Gluon wd_mult = 1) and updates in place.

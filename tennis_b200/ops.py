@@ -388,3 +388,13 @@ def adam_update(w, g, mean, var, lr, b1, b2, eps, wd, rescale, t):
     assert w.is_contiguous()
     check(lib().tn_adam_update(dptr(w), dptr(g.contiguous()), dptr(mean), dptr(var), w.numel(), lr, b1, b2, eps, wd, rescale, t,
                                stream_ptr()))
+
+
+def masked_softmax_ce(pred, label, valid_len):
+    """gluonnlp MaskedSoftmaxCELoss forward: pred (B,T,V), label (B,T), valid_len (B) -> loss (B)."""
+    _require_cuda(pred, label, valid_len)
+    B, T, V = pred.shape
+    loss = torch.empty((B,), dtype=torch.float32, device=pred.device)
+    check(lib().tn_masked_softmax_ce(dptr(pred.contiguous().float()), dptr(label.contiguous().float()),
+                                     dptr(valid_len.contiguous().float()), dptr(loss), B, T, V, stream_ptr()))
+    return loss

@@ -82,3 +82,26 @@ def test_dense_and_pool():
     z = torch.randn(4, 6, 50, generator=g)
     assert torch.equal(ops.temporal_pool(z.cuda(), "max").cpu(), z.max(dim=1).values)
     assert (ops.temporal_pool(z.cuda(), "mean").cpu() - z.mean(dim=1)).abs().max().item() < 1e-6
+
+
+def test_fused_dense_layer_kernel_matches_two_kernel_path():
+    """The experimental fused dense-layer kernel (TN_DENSE_FUSED_MIN_W) must reproduce the default path bit for bit:
+    same bf16 roundings at the same points, only the bottleneck stays on-chip."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, torch; sys.path.insert(0, %r); from oracle import vision as O; from tennis_b200 import ops;"
+            "p = O.synthetic_params('densenet121', seed=1234); _, x = O.synthetic_frames(3, 224, seed=100);"
+            "bb = ops.Backbone('densenet121', O.flatten_params('densenet121', p)); f = bb(x.cuda()).cpu();"
+            "torch.save(f, sys.argv[1])" % root)
+    outs = []
+    for i, env_val in enumerate([None, "28"]):
+        env = dict(os.environ)
+        env.pop("TN_DENSE_FUSED_MIN_W", None)
+        if env_val:
+            env["TN_DENSE_FUSED_MIN_W"] = env_val
+        path = "/tmp/_tn_fused_%d.pt" % i
+        subprocess.run([sys.executable, "-c", code, path], env=env, check=True, timeout=300)
+        outs.append(torch.load(path))
+    assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max()

@@ -126,3 +126,15 @@ def test_beam_search_early_exit_and_max_length():
         s_ref, _, v_ref = C.translate(p3, x, vl, cell=cell, H=H, beam=3, max_length=10)
     s, _, v = BeamSearchTranslator(model, 3, BeamSearchScorer(1.0, 5), 10).translate(x.cuda(), vl.cuda())
     assert s.shape == s_ref.shape == (3, 3, 12) and torch.equal(s.cpu(), s_ref) and torch.equal(v.cpu(), v_ref)
+
+
+def test_masked_softmax_ce_matches_oracle():
+    from oracle import captioning as C
+    from tennis_b200.gluon import MaskedSoftmaxCELoss
+    g = torch.Generator().manual_seed(4)
+    pred = torch.randn(5, 9, 254, generator=g)
+    label = torch.randint(0, 254, (5, 9), generator=g).float()
+    vl = torch.tensor([9., 1., 4., 0., 7.])
+    ref = C.masked_softmax_ce(pred, label, vl)
+    out = MaskedSoftmaxCELoss()(pred.cuda(), label.cuda(), vl.cuda())
+    assert (out.cpu() - ref).abs().max().item() < 1e-5
