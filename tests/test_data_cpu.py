@@ -1,0 +1,121 @@
+"""CPU-only: dataset sample assembly (D1), caption batching (8f-3), vocabulary, metrics (8f-4), host pipeline schedule."""
+import math
+
+import numpy as np
+import torch
+
+from tennis_b200.dataset import TennisSet, feature_path, image_path, window_frames
+from tennis_b200.metrics.vision import PRF1, Accuracy, compute_bleu
+from tennis_b200.utils.captioning import FixedBucketSampler, get_dataloaders, pad_stack
+from tennis_b200.vocab import Vocab, count_tokens
+
+
+def _reference_window(center, window, stride, every, video_length):
+    """Independent restatement of dataset.py:190-201 written as nested conditionals."""
+    out = []
+    last = video_length - every
+    while last % every != 0:
+        last -= 1
+    for off in range(int(-window / 2), int(math.ceil(window / 2))):
+        f = center + off * stride
+        if f < 0:
+            f = 0
+        if f > last:
+            f = last
+        out.append(f)
+    return out
+
+
+def test_window_offsets_and_clamping():
+    for (c, w, s, e, L) in [(3, 32, 1, 1, 96), (90, 32, 1, 1, 96), (50, 30, 1, 1, 96), (10, 8, 2, 2, 21), (0, 15, 3, 1, 40),
+                            (39, 15, 3, 1, 40), (7, 1, 1, 1, 9)]:
+        got = window_frames(c, w, s, e, L)
+        assert got == _reference_window(c, w, s, e, L)
+        assert len(got) == w
+    assert window_frames(50, 32, 1, 1, 96) == list(range(34, 66))          # -16 .. +15 (dataset.py:192)
+    assert window_frames(2, 4, 1, 1, 96) == [0, 1, 2, 3]                   # clamped at 0 duplicates edge frames
+
+
+def test_path_scheme_matches_reference_layout():
+    assert image_path("data/frames", "V010", 12345) == "data/frames/V010.mp4/0000012000/0000012345.jpg"
+    assert feature_path("data/features/0006", "V010", 999) == "data/features/0006/V010.mp4/0000000000/0000000999.npy"
+
+
+def test_event_samples_shapes_and_determinism():
+    ds = TennisSet(split='val', window=8, stride=1, every=4, synthetic={}, data_shape=32)
+    x, y, i = ds[5]
+    assert x.shape == (8, 3, 32, 32) and x.dtype == torch.float32 and 0 <= y < 11 and i == 5
+    x2, _, _ = TennisSet(split='val', window=8, stride=1, every=4, synthetic={}, data_shape=32)[5]
+    assert torch.equal(x, x2)
+    feats = TennisSet(split='train', window=30, feats_model='0006', synthetic={})[0][0]
+    assert feats.shape == (30, 1024)
+    single = TennisSet(split='test', window=1, synthetic={}, data_shape=16)[0][0]
+    assert single.shape == (3, 16, 16)
+    assert ds.classes[0] == 'OTH' and len(ds.classes) == 11
+
+
+def test_caption_samples_and_vocab_convention():
+    dc = TennisSet(split='train', captions=True, synthetic={}, feats_model='0006', max_cap_len=5)
+    v = dc.vocab
+    assert [v.token_to_idx[t] for t in ('<unk>', '<pad>', '<bos>', '<eos>')] == [0, 1, 2, 3]
+    frames, cap, n, ncap = dc[0]
+    assert cap.dtype == np.int32 and cap[0] == 2 and cap[-1] == 3 and ncap == len(cap) <= 7
+    assert frames.shape[0] == n and frames.shape[1] == 1024
+    dv = TennisSet(split='val', captions=True, synthetic={}, feats_model='0006', vocab=v, inference=True)
+    assert len(dv[0]) == 5 and dv[0][4] == 0
+    lens = dc.get_data_lens()
+    assert all(isinstance(a, int) and b >= 2 for a, b in lens)
+    vv = Vocab(count_tokens("b a a c c c".split()))
+    assert vv.idx_to_token[4:] == ['c', 'a', 'b']  # descending frequency
+    vv.set_embedding({'a': np.ones(3, np.float32)})
+    assert vv.embedding.idx_to_vec.shape == (7, 3) and vv.embedding.idx_to_vec[0].sum() == 0  # specials -> zero vectors
+
+
+def test_bucketed_batches_cover_dataset_and_pad_with_zero():
+    dc = TennisSet(split='train', captions=True, synthetic={'num_points': 11}, feats_model='0006')
+    dv = TennisSet(split='val', captions=True, synthetic={'num_points': 7}, feats_model='0006', vocab=dc.vocab, inference=True)
+    tr, va, te = get_dataloaders(dc, dv, dv, batch_size=4, test_batch_size=3, num_buckets=5)
+    seen = []
+    for src, tgt, sl, tl, idx in va:
+        assert src.shape[0] == tgt.shape[0] == sl.shape[0] == idx.shape[0] <= 3
+        assert sl.dtype == torch.float32 and int(sl.max()) == src.shape[1] and int(tl.max()) == tgt.shape[1]
+        for b in range(src.shape[0]):
+            assert (src[b, int(sl[b]):] == 0).all() and (tgt[b, int(tl[b]):] == 0).all()
+        seen += idx.tolist()
+    assert sorted(seen) == list(range(len(dv)))
+    assert sum(b[0].shape[0] for b in tr) == len(dc)
+    assert pad_stack([torch.ones(2, 3), torch.ones(4, 3)]).shape == (2, 4, 3)
+    s = FixedBucketSampler([(5, 3), (50, 9), (7, 2), (48, 8)], batch_size=2, num_buckets=2)
+    assert sorted(map(sorted, s)) == [[0, 2], [1, 3]]
+
+
+def test_prf1_counts_and_swapped_names():
+    m = PRF1(label_names=['OTH', 'A', 'B'])
+    labels = torch.tensor([0, 1, 2, 2, 1, 0])
+    preds = torch.tensor([0, 1, 1, 2, 1, 1])
+    m.update([labels], [preds])
+    assert m.mat.astype(int).tolist() == [[1, 1, 0], [0, 2, 0], [0, 1, 1]]
+    d = dict(m.get())
+    # reference quirk (metrics/vision.py:73-74): "prec" = matches / positives(labels), "rec" = matches / predictions
+    assert abs(d['A_prec'] - 2 / 2) < 1e-9 and abs(d['A_rec'] - 2 / 4) < 1e-9
+    assert abs(d['AVG_NB_f1'] - np.mean([d['A_f1'], d['B_f1']])) < 1e-12
+    a = Accuracy(top_k=2)
+    a.update([torch.tensor([2, 0])], [torch.tensor([[0.1, 0.5, 0.4], [0.2, 0.7, 0.1]])])
+    assert a.get()[1] == 1.0
+
+
+def test_bleu_known_values():
+    ref = [[["the", "cat", "sat", "on", "the", "mat"]]]
+    assert abs(compute_bleu(ref, [["the", "cat", "sat", "on", "the", "mat"]])[0] - 1.0) < 1e-12
+    b, prec, bp, rl, tl = compute_bleu(ref, [["the", "cat", "sat", "on", "mat"]])
+    assert prec[0] == 1.0 and abs(bp - math.exp(1 - 6 / 5)) < 1e-12 and 0 < b < 1
+
+
+def test_host_pipeline_chunk_schedule():
+    from tennis_b200.parallel import HostPipeline
+    h = HostPipeline.__new__(HostPipeline)
+    h.chunks = 4
+    for B in (1, 3, 16, 17, 64, 100, 256):
+        cuts = h._schedule(B)
+        assert cuts[0] == 0 and cuts[-1] == B and all(b > a for a, b in zip(cuts, cuts[1:]))
+    assert h._schedule(64) == [0, 4, 12, 28, 64]
