@@ -254,8 +254,14 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
   // stem: conv7x7/2 -> BN -> ReLU (epilogue) ; max-pool 3/2/1 into channels [0,64) of block 1
   {
     // 7x7/2 stem == 4x4/1 conv on the zero-padded space-to-depth image (tn_stem.cu), BN folded, ReLU
-    TN_CUDA(launch_stem_s2d(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, bb->bn0.shift, stem, bb->num_sms, st));
-    TN_CUDA(launch_maxpool3s2(stem, blk[0], n, d.Hs, d.Ws, 64, d.Hp, d.Wp, pl.ctot[0], 0, st));
+    if (d.Ws <= 128 && !getenv("TN_NO_STEM_POOL_FUSION")) {
+      // stem conv + BN + ReLU + max-pool in one kernel, written straight into channels [0,64) of block 1
+      TN_CUDA(launch_stem_pool(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, d.Hp, d.Wp, bb->bn0.shift, blk[0], pl.ctot[0],
+                               bb->num_sms, st));
+    } else {
+      TN_CUDA(launch_stem_s2d(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, bb->bn0.shift, stem, bb->num_sms, st));
+      TN_CUDA(launch_maxpool3s2(stem, blk[0], n, d.Hs, d.Ws, 64, d.Hp, d.Wp, pl.ctot[0], 0, st));
+    }
   }
   for (int b = 0; b < 4; ++b) {
     const int H = pl.Hb[b], W = pl.Wb[b], ct = pl.ctot[b];
@@ -311,8 +317,12 @@ int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int 
   if (dry) return TN_OK;
   {
     // 7x7/2 stem == 4x4/1 conv on the zero-padded space-to-depth image (tn_stem.cu), BN folded, ReLU
-    TN_CUDA(launch_stem_s2d(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, bb->bn0.shift, stem, bb->num_sms, st));
-    TN_CUDA(launch_maxpool3s2(stem, xa, n, d.Hs, d.Ws, 64, d.Hp, d.Wp, 64, 0, st));
+    if (d.Ws <= 128 && !getenv("TN_NO_STEM_POOL_FUSION")) {
+      TN_CUDA(launch_stem_pool(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, d.Hp, d.Wp, bb->bn0.shift, xa, 64, bb->num_sms, st));
+    } else {
+      TN_CUDA(launch_stem_s2d(bb->stem_s2d, in4, n, d.Hs + 3, d.Ws + 3, d.Hs, d.Ws, bb->bn0.shift, stem, bb->num_sms, st));
+      TN_CUDA(launch_maxpool3s2(stem, xa, n, d.Hs, d.Ws, 64, d.Hp, d.Wp, 64, 0, st));
+    }
   }
   int H = d.Hp, W = d.Wp;
   __nv_bfloat16* x = xa;

@@ -184,6 +184,167 @@ __global__ void __launch_bounds__(kThreads, 1) stem_s2d_kernel(const __grid_cons
   if (warp == 1) tmem_dealloc<128>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Stem conv + BN + ReLU + MaxPool(3, stride 2, pad 1) in one kernel: the (n,112,112,64) stem activation (3.3 GB for 2048
+// frames, written once and read once by a separate pool kernel) never exists.  One tile = one POOLED row (f, py): the
+// three stem rows 2py-1, 2py, 2py+1 are three accumulators (3 x 16 UMMAs over six pixel strips); the epilogue takes the
+// vertical max across accumulators (same TMEM lane), the horizontal max with warp shuffles (+ one value per lane quarter
+// through shared memory), adds the folded BN shift, ReLU (both commute with max), and even columns write the pooled
+// pixel into channels [0,64) of the first dense block's concat buffer.
+struct StemPoolParams {
+  int Hz, Wz, Hs, Ws, Hp, Wp;   // padded s2d grid, stem output size, pooled output size
+  int num_tiles;                // n * Hp
+  const uint8_t* wpack;
+  const float* shift;
+  __nv_bfloat16* out;           // (n, Hp, Wp, out_cstride), channels [0,64)
+  int out_cstride;
+};
+constexpr int kPoolABuf = 6 * kStripBytes;
+constexpr int kPoolSmem = 1024 + kWBytes + 2 * kPoolABuf + 4096 /*exchange*/ + 256 + 256;
+
+__global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_constant__ CUtensorMap tmap, const StemPoolParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + kWBytes;
+  float* xch = reinterpret_cast<float*>(sA + 2 * kPoolABuf);  // [2 parity][2 halves][4 quarters][32]
+  float* sShift = xch + 1024;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sShift + 64);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    mbar_init(w_full, 1);
+    mbar_fence_init();
+  }
+  if (tid < 64) sShift[tid] = p.shift[tid];
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, kWBytes);
+      bulk_g2s(sW, p.wpack, kWBytes, w_full);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int f = t / p.Hp, py = t - f * p.Hp;
+        mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&a_full[buf], 6 * kStripRows * 32);
+        for (int s = 0; s < 6; ++s) {  // Zp rows 2py-1 .. 2py+4 of frame f, from column 0
+          const int row = (f * p.Hz + 2 * py - 1 + s) * p.Wz;
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+              ::"r"(smem_u32(sA + buf * kPoolABuf + s * kStripBytes)), "l"(&tmap), "r"(0), "r"(row), "r"(smem_u32(&a_full[buf]))
+              : "memory");
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m128(kN);
+      mbar_wait(w_full, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1, ab = it & 1;
+        mbar_wait(&a_full[buf], (it >> 1) & 1);
+        mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + buf * kPoolABuf);
+        const uint32_t w_base = smem_u32(sW);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {  // stem row 2py-1+j
+          const uint32_t d_tmem = tmem_base + ab * 192 + j * kN;
+          uint32_t acc = 0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              umma_bf16_ss(d_tmem, desc_sw32(a_base + (j + a) * kStripBytes + b * 32), desc_sw32(w_base + (a * 4 + b) * kTapBytes), idesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(&a_empty[buf]);
+        umma_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int qw = warp & 3;
+    const int hf = ew >> 2;
+    const int x = qw * 32 + lane;  // stem column of this thread
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const int f = t / p.Hp, py = t - f * p.Hp;
+      mbar_wait(&acc_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+      float m[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) m[c] = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * 192 + j * kN + hf * 32, v);
+        tmem_ld_wait();
+        const int y = 2 * py - 1 + j;
+        if (y >= 0 && y < p.Hs) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) m[c] = fmaxf(m[c], __uint_as_float(v[c]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      if (x >= p.Ws) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) m[c] = -INFINITY;  // columns past the image edge never win the max
+      }
+      float* xq = xch + (it & 1) * 256 + hf * 128;
+      if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) xq[qw * 32 + c] = m[c];
+      }
+      if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      float o[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float left = __shfl_up_sync(0xffffffffu, m[c], 1);
+        const float right = __shfl_down_sync(0xffffffffu, m[c], 1);
+        if (lane == 0) left = (qw > 0) ? xq[(qw - 1) * 32 + c] : -INFINITY;
+        o[c] = fmaxf(fmaxf(left, m[c]), right);  // lane 31 is an odd column: never a pooling centre
+      }
+      if ((x & 1) == 0 && x < p.Ws && (x >> 1) < p.Wp) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(f * p.Hp + py) * p.Wp + (x >> 1)) * p.out_cstride + hf * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float f8[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) f8[jj] = fmaxf(o[8 * c4 + jj] + sShift[hf * 32 + 8 * c4 + jj], 0.f);
+          dst[c4] = make_uint4(pack_bf16x2(f8[0], f8[1]), pack_bf16x2(f8[2], f8[3]), pack_bf16x2(f8[4], f8[5]), pack_bf16x2(f8[6], f8[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -256,6 +417,41 @@ cudaError_t launch_stem_s2d(const StemDev& sd, const __nv_bfloat16* z, int n, in
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ProfScope prof_scope(kProfConvGemm, st);
   stem_s2d_kernel<<<grid, kThreads, kSmem, st>>>(tmap, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stem_pool(const StemDev& sd, const __nv_bfloat16* z, int n, int Hz, int Wz, int Hs, int Ws, int Hp, int Wp,
+                             const float* shift, __nv_bfloat16* out, int out_cstride, int num_sms, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return cudaErrorNotSupported;
+  const long long total = static_cast<long long>(n) * Hz * Wz;
+  if (total <= 0) return cudaSuccess;
+  if (total >= (1ll << 31) - 4096 || Ws > 128) return cudaErrorInvalidValue;
+  StemPoolParams p;
+  p.Hz = Hz; p.Wz = Wz; p.Hs = Hs; p.Ws = Ws; p.Hp = Hp; p.Wp = Wp;
+  p.num_tiles = n * Hp;
+  p.wpack = sd.wpack;
+  p.shift = shift;
+  p.out = out;
+  p.out_cstride = out_cstride;
+  CUtensorMap tmap;
+  cuuint64_t gdim[2] = {16, static_cast<cuuint64_t>(total)};
+  cuuint64_t gstride[1] = {32};
+  cuuint32_t box[2] = {16, kStripRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(z), gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  ProfScope prof_scope(kProfConvGemm, st);
+  stem_pool_kernel<<<grid, kThreads, kPoolSmem, st>>>(tmap, p);
   return cudaGetLastError();
 }
 

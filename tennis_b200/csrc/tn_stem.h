@@ -17,4 +17,8 @@ bool make_stem(DeviceArena& arena, const float* w_64x3x7x7, const float* fold_sc
 cudaError_t launch_stem_s2d(const StemDev& sd, const __nv_bfloat16* z, int n, int Hz, int Wz, int Ho, int Wo, const float* shift,
                             __nv_bfloat16* out, int num_sms, cudaStream_t st);
 
+// conv + shift + ReLU + MaxPool(3,2,1) fused: out (n, Hp, Wp, out_cstride) channels [0,64); requires Ws <= 128
+cudaError_t launch_stem_pool(const StemDev& sd, const __nv_bfloat16* z, int n, int Hz, int Wz, int Hs, int Ws, int Hp, int Wp,
+                             const float* shift, __nv_bfloat16* out, int out_cstride, int num_sms, cudaStream_t st);
+
 }  // namespace tn

@@ -85,8 +85,9 @@ def test_dense_and_pool():
 
 
 def test_fused_dense_layer_kernel_matches_two_kernel_path():
-    """The experimental fused dense-layer kernel (TN_DENSE_FUSED_MIN_W) must reproduce the default path bit for bit:
-    same bf16 roundings at the same points, only the bottleneck stays on-chip."""
+    """The experimental fused dense-layer kernel (TN_DENSE_FUSED_MIN_W) must reproduce the default path: same bf16 roundings
+    at the same points, only the bottleneck stays on-chip (the BN2 shift is added in fp32 instead of by the hi/lo bias MMA,
+    so agreement is to bf16 rounding noise, not bit-exact)."""
     import os
     import subprocess
     import sys
@@ -104,4 +105,4 @@ def test_fused_dense_layer_kernel_matches_two_kernel_path():
         path = "/tmp/_tn_fused_%d.pt" % i
         subprocess.run([sys.executable, "-c", code, path], env=env, check=True, timeout=300)
         outs.append(torch.load(path))
-    assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max()
+    assert (outs[0] - outs[1]).abs().max().item() < 5e-3 * outs[0].abs().max().item()
