@@ -308,6 +308,10 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1:
             try:
+                line["gru_head"] = bench_gru_head(model, device)
+            except Exception as exc:
+                line["gru_head"] = {"error": repr(exc)}
+            try:
                 line["captioner"] = bench_captioner(device)
             except Exception as exc:  # the headline metric must still be reported
                 line["captioner"] = {"error": repr(exc)}
@@ -384,6 +388,38 @@ def bench_captioner(device, steps=3):
             "cpu_baseline": {"value": float((v_ref[:, 0] - 2).clamp(min=0).sum()) / dt_cpu, "unit": "tokens/s",
                              "cores": torch.get_num_threads(), "kind": "port", "sample": "%d of the 32 sources" % nb},
             "token_ids_equal_to_oracle_on_sample": bool(same)}
+
+
+def bench_gru_head(model, device, iters=20):
+    """north_star secondary target: the Bi-GRU(128)+max+Dense head at 256 clips x 32 frames against the HBM roofline.
+    Algorithmic bytes: features B*T*D*2 (bf16 as exchanged) + 3.56 MB weights + logits."""
+    import torch
+    B, Tn, D = 256, 32, 1024
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(B, Tn, D, generator=g).relu().to(device)
+    twin = feats.to(torch.bfloat16)
+    feats._tn_bf16 = twin
+
+    def run():
+        y = model.rnn.forward_max(feats)
+        return model.classes(y)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    bytes_alg = B * Tn * D * 2 + 3.56e6 + B * 11 * 4
+    peaks, _ = measured_peaks()
+    gbs = bytes_alg / (us * 1e-6) / 1e9
+    return {"workload": "BiGRU(128)+max+Dense(11) on (256,32,1024) bf16 features", "us_per_call": us,
+            "algorithmic_bytes": bytes_alg, "achieved_gbs": gbs, "hbm_peak_gbs": peaks["hbm_gbs"],
+            "frac_of_hbm_roofline": gbs / peaks["hbm_gbs"],
+            "note": "32 serial recurrence steps: latency-bound (SURVEY.md 7.2-5), target 0.5 not met"}
 
 
 def main():
