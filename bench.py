@@ -28,6 +28,10 @@ sys.path.insert(0, ROOT)
 CLIPS_PER_GPU, T, SIZE, CLASSES, HIDDEN = 64, 32, 224, 11, 128
 ARCH = "densenet121"
 FLOP_PER_FRAME = 5.666e9  # conv layers of DenseNet-121 @224^2, SURVEY.md §8d / BASELINE.md §3
+# DRAM bytes (read + write) of the conv-kernel family for ONE 2048-frame step, summed from the ncu launch list of this
+# very command (profiles/r1_launches_final.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch; the stem kernel,
+# outside that capture window, is added from its own capture): 85.8 GB + 2.9 GB.
+CONV_DRAM_BYTES_PER_STEP = 88.7e9
 WORKLOAD = "configs[1]: CNN+GRU event detector fwd, %d clips x %d frames @%dx%d per GPU" % (CLIPS_PER_GPU, T, SIZE, SIZE)
 
 
@@ -291,7 +295,12 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "inputs %.2f GB per GPU per step > 126 MB L2, no flush needed" % (h2d / 1e9),
                        "outputs_finite": finite},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": CONV_DRAM_BYTES_PER_STEP,
+                         "traffic_note": "bytes per step (all conv-kernel launches of one step, like `achieved`), ncu capture "
+                                         "profiles/r1_launches_final.csv; algorithmic minimum with dense-layer fusion 24.3 MB/frame "
+                                         "= 49.8 GB/step, so the unfused layer-by-layer schedule moves 1.8x that",
+                         "hbm_view": {"achieved_gbs": CONV_DRAM_BYTES_PER_STEP * args.steps / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0,
+                                      "peak_gbs": peaks.get("hbm_gbs")},
                          "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), %d launches/step, %.2f ms/step summed over "
                                    "CUDA events on the launch stream" % (conv_launches // max(1, args.steps),
                                                                          conv_ms / max(1, args.steps)),
