@@ -17,6 +17,7 @@
 
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -28,14 +29,30 @@ constexpr int kRB = 4;  // batch rows per cluster
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-template <int G, int CL>
-__global__ void rnn_scan_kernel(const RnnScanParams p) {
+// Packed fp32x2 FMA (sm_100 FFMA2): d.{x,y} += a.{x,y} * b.{x,y}, each lane a fused rn fma.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d.x), "+f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+
+constexpr int kHReg = 128;  // hidden size of the register-resident variant
+
+// WREG: the thread's W_hh^T column (kHReg weights) lives in registers for the whole scan, so a step reads
+// only the 2 KB hidden state from shared memory (broadcast LDS.128) and issues packed FFMA2s; h is laid
+// out [row][k] so that consecutive k pair up.  Otherwise the slice is staged in shared memory ([H][NJ])
+// and h is laid out [k][row].
+template <int G, int CL, bool WREG>
+__global__ void __launch_bounds__(WREG ? G * kHReg / CL : 1024, 1) rnn_scan_kernel(const RnnScanParams p) {
   extern __shared__ float smem_f[];
-  const int H = p.H;
+  const int H = WREG ? kHReg : p.H;
   const int HS = H / CL;   // hidden units owned by this CTA
   const int NJ = G * HS;   // gate columns owned by this CTA == blockDim.x
-  float* Wt = smem_f;                       // [H][NJ]
-  float* hbuf = Wt + static_cast<size_t>(H) * NJ;  // [2][H][kRB]
+  float* Wt = smem_f;                       // [H][NJ] (absent when WREG)
+  float* hbuf = Wt + (WREG ? 0 : static_cast<size_t>(H) * NJ);  // [2][H][kRB]  (WREG: [2][kRB][H])
   float* hh = hbuf + 2 * H * kRB;           // [kRB][NJ]
 
   const int tid = threadIdx.x;
@@ -46,7 +63,13 @@ __global__ void rnn_scan_kernel(const RnnScanParams p) {
   const int GH = G * H;
 
   // ---- stage the W_hh^T slice: column j=(g,u) <- row (g*H + q*HS + u) of W_hh ; global WhhT is [dir][H(k)][G*H]
-  {
+  float wreg[WREG ? kHReg : 2];
+  if (WREG) {
+    const int g = tid / HS, u = tid - g * HS;
+    const float* src = p.WhhT + static_cast<size_t>(dir) * H * GH + g * H + q * HS + u;
+#pragma unroll
+    for (int k = 0; k < kHReg; ++k) wreg[k] = __ldg(src + static_cast<size_t>(k) * GH);
+  } else {
     const float* src = p.WhhT + static_cast<size_t>(dir) * H * GH;
     for (int idx = tid; idx < H * NJ; idx += blockDim.x) {
       const int k = idx / NJ;
@@ -57,7 +80,8 @@ __global__ void rnn_scan_kernel(const RnnScanParams p) {
   }
   // initial hidden state (zeros unless h0 given): hbuf[0][k][b]
   for (int idx = tid; idx < H * kRB; idx += blockDim.x) {
-    const int k = idx / kRB, b = idx - k * kRB;
+    const int k = WREG ? idx % H : idx / kRB;
+    const int b = WREG ? idx / H : idx - k * kRB;
     float v = 0.f;
     if (p.h0 && b0 + b < p.B) v = p.h0[(static_cast<size_t>(dir) * p.B + b0 + b) * H + k];
     hbuf[idx] = v;
@@ -120,14 +144,33 @@ __global__ void rnn_scan_kernel(const RnnScanParams p) {
     float acc[kRB];
 #pragma unroll
     for (int b = 0; b < kRB; ++b) acc[b] = 0.f;
+    if (WREG) {
+      float2 acc2[kRB];
+#pragma unroll
+      for (int b = 0; b < kRB; ++b) acc2[b] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kHReg; k += 4) {
+        const float2 w01 = make_float2(wreg[k], wreg[k + 1]);
+        const float2 w23 = make_float2(wreg[k + 2], wreg[k + 3]);
+#pragma unroll
+        for (int b = 0; b < kRB; ++b) {
+          const float4 hv = *reinterpret_cast<const float4*>(hcur + b * kHReg + k);
+          ffma2(acc2[b], w01, make_float2(hv.x, hv.y));
+          ffma2(acc2[b], w23, make_float2(hv.z, hv.w));
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kRB; ++b) acc[b] = acc2[b].x + acc2[b].y;
+    } else {
 #pragma unroll 8
-    for (int k = 0; k < H; ++k) {
-      const float w = Wt[k * NJ + tid];
-      const float4 hv = *reinterpret_cast<const float4*>(hcur + k * kRB);
-      acc[0] = fmaf(w, hv.x, acc[0]);
-      acc[1] = fmaf(w, hv.y, acc[1]);
-      acc[2] = fmaf(w, hv.z, acc[2]);
-      acc[3] = fmaf(w, hv.w, acc[3]);
+      for (int k = 0; k < H; ++k) {
+        const float w = Wt[k * NJ + tid];
+        const float4 hv = *reinterpret_cast<const float4*>(hcur + k * kRB);
+        acc[0] = fmaf(w, hv.x, acc[0]);
+        acc[1] = fmaf(w, hv.y, acc[1]);
+        acc[2] = fmaf(w, hv.z, acc[2]);
+        acc[3] = fmaf(w, hv.w, acc[3]);
+      }
     }
 #pragma unroll
     for (int b = 0; b < kRB; ++b) hh[b * NJ + tid] = acc[b] + bhh;
@@ -165,7 +208,7 @@ __global__ void rnn_scan_kernel(const RnnScanParams p) {
         }
       }
       // publish (frozen rows re-publish their last state so both buffers stay coherent)
-      const int hidx = (q * HS + u) * kRB + b;
+      const int hidx = WREG ? b * H + q * HS + u : (q * HS + u) * kRB + b;
       if (CL > 1) {
         cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
@@ -189,12 +232,12 @@ __global__ void rnn_scan_kernel(const RnnScanParams p) {
   }
 }
 
-template <int G, int CL>
+template <int G, int CL, bool WREG = false>
 cudaError_t launch_t(const RnnScanParams& p, cudaStream_t st) {
   const int HS = p.H / CL;
   const int NJ = G * HS;
-  const size_t smem = (static_cast<size_t>(p.H) * NJ + 2 * p.H * kRB + kRB * NJ) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(rnn_scan_kernel<G, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = ((WREG ? 0 : static_cast<size_t>(p.H) * NJ) + 2 * p.H * kRB + kRB * NJ) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(rnn_scan_kernel<G, CL, WREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   const int tiles = (p.B + kRB - 1) / kRB;
@@ -210,7 +253,7 @@ cudaError_t launch_t(const RnnScanParams& p, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CL > 1) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, rnn_scan_kernel<G, CL>, p);
+  return cudaLaunchKernelEx(&cfg, rnn_scan_kernel<G, CL, WREG>, p);
 }
 
 }  // namespace
@@ -231,6 +274,8 @@ cudaError_t launch_rnn_scan(const RnnScanParams& p, cudaStream_t st) {
   const int cl = rnn_scan_cluster_size(G, p.H);
   if (cl < 0 || (G != 3 && G != 4)) return cudaErrorInvalidValue;
   ProfScope prof_scope(kProfOther, st);
+  // flagship hidden size: weights in registers (GRU: 384 threads x 128 weights; LSTM: a 2-CTA cluster of 256)
+  if (p.H == kHReg && !getenv("TN_RNN_NO_WREG")) return G == 3 ? launch_t<3, 1, true>(p, st) : launch_t<4, 2, true>(p, st);
   if (G == 3) {
     switch (cl) {
       case 1: return launch_t<3, 1>(p, st);
