@@ -1,5 +1,7 @@
 #include "tn_common.h"
 
+#include <stdlib.h>
+
 #include <math.h>
 #include <string.h>
 
@@ -163,6 +165,11 @@ void prof_end(int kind, cudaStream_t st) {
   cudaEvent_t e = s.get();
   cudaEventRecord(e, st);
   s.end[kind].push_back(e);
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("TN_NO_PDL") == nullptr;
+  return on;
 }
 
 }  // namespace tn

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   float* xch = reinterpret_cast<float*>(tail + 128);     // [2 parity][2 halves][4 quarters][2][16]
 
   const int tid = threadIdx.x;
+  griddep_launch_dependents();
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
@@ -92,12 +93,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
+    mbar_arrive_expect_tx(w_full, kWBytes);
+    for (int b = 0; b < 6; ++b) bulk_g2s(sW + b * kWBlob, p.wpack + b * kWBlob, kWBlob, w_full);
+  }
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, kWBytes);
-      for (int b = 0; b < 6; ++b) bulk_g2s(sW + b * kWBlob, p.wpack + b * kWBlob, kWBlob, w_full);
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int buf = it % p.nbuf;
@@ -325,8 +329,7 @@ cudaError_t launch_conv3x3_halo(const Conv3x3Dev& cv, const __nv_bfloat16* in_pa
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ProfScope prof_scope(kProfConvGemm, st);
-  conv3x3_halo_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
-  return cudaGetLastError();
+  return launch_pdl(conv3x3_halo_kernel, dim3(grid), dim3(kThreads), smem, st, tmap, p);
 }
 
 }  // namespace tn

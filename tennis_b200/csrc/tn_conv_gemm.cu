@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tn_common.h"
@@ -58,16 +59,22 @@ constexpr int kOnesBytes = 1024;            // 8 rows x 128 B, aliased by all 16
 constexpr int kMaxResidentChunks = 4;
 constexpr int kSmemLimit = 227 * 1024;
 
-template <int BN, bool RESIDENT>
+// MT = M tiles (of 128 rows) that share one streamed weight chunk per pipeline stage (TMA mode, streamed weights only):
+// with K > 256 every 128-row tile re-reads the whole 128 x K weight slab from L2 -- as many bytes as the activations --
+// so pairing two tiles per stage cuts the L2->SM traffic of the wide layers by a quarter to a third.
+template <int BN, bool RESIDENT, int MT = 1>
 struct Cfg {
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStage = RESIDENT ? kABytes : (kABytes + kBBytes);
+  static constexpr int kStage = RESIDENT ? kABytes : (MT * kABytes + kBBytes);
   static constexpr int kFixed = 1024 /*align*/ + kStagingBytes + kOnesBytes + kBBytes /*bias operand*/ + 1024 /*barriers*/ +
                                 (RESIDENT ? kMaxResidentChunks * kBBytes : 0);
   static constexpr int kNStageRaw = (kSmemLimit - kFixed) / kStage;
   static constexpr int kNStage = kNStageRaw > 8 ? 8 : kNStageRaw;
   static constexpr int kSmem = kFixed + kNStage * kStage;
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kAccCols = 2 * MT * BN;  // double-buffered accumulators
+  static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
+  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+  static_assert(!RESIDENT || MT == 1, "tile pairing is for streamed weights");
   static_assert(kNStage >= 3, "not enough shared memory for the stage ring");
 };
 
@@ -138,9 +145,10 @@ __device__ __forceinline__ void bn_act8_accum(uint4 x, const ScaleShift8& s, boo
   }
 }
 
-template <int BN, int MODE, bool RESIDENT>
+template <int BN, int MODE, bool RESIDENT, int MT = 1>
 __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(const ConvGemmParams p, const __grid_constant__ CUtensorMap tmap) {
-  using C = Cfg<BN, RESIDENT>;
+  using C = Cfg<BN, RESIDENT, MT>;
+  static_assert(MT == 1 || MODE == kModeTma, "tile pairing needs TMA-fetched A tiles");
   constexpr int NS = C::kNStage;
   constexpr int kEpiWarps = Warps<MODE>::kEpi;
   constexpr int kThreads = Warps<MODE>::kThreads;
@@ -164,9 +172,10 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int n_tile = blockIdx.y;
-  const int num_m_tiles = (p.M + kBM - 1) / kBM;
+  const int num_m_tiles = ((p.M + kBM - 1) / kBM + MT - 1) / MT;  // scheduling units: MT consecutive 128-row tiles
   const int nchunks = p.num_chunks;
 
+  griddep_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], kProducerWarps + ((RESIDENT || MODE == kModeTma) ? 0 : 1));
@@ -210,6 +219,12 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint8_t* wtile = p.wpack + static_cast<size_t>(n_tile) * nchunks * C::kBBytes;
+  if (RESIDENT && tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
+    mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nchunks * C::kBBytes));
+    for (int c = 0; c < nchunks; ++c)
+      bulk_g2s(sBres + c * C::kBBytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, w_full);
+  }
+  griddep_wait();
 
   const bool has_pro_any = p.pro_scale != nullptr;
   if (MODE == kModeTma && warp < kProducerWarps) {
@@ -232,11 +247,15 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
           mbar_wait(&tma_full[stage], phase);
           const uint32_t a_stage = smem_u32(sStage + stage * C::kStage);
           if (ch_ok) {
-            uint4 v[kRowsPerThread];
 #pragma unroll
-            for (int i = 0; i < kRowsPerThread; ++i) v[i] = lds128(a_stage + my_off + i * 4096);
+            for (int t = 0; t < MT; ++t) {
+              uint4 v[kRowsPerThread];
 #pragma unroll
-            for (int i = 0; i < kRowsPerThread; ++i) sts128(a_stage + my_off + i * 4096, bn_act8(v[i], ss, pro_relu));
+              for (int i = 0; i < kRowsPerThread; ++i) v[i] = lds128(a_stage + t * kABytes + my_off + i * 4096);
+#pragma unroll
+              for (int i = 0; i < kRowsPerThread; ++i)
+                sts128(a_stage + t * kABytes + my_off + i * 4096, bn_act8(v[i], ss, pro_relu));
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -251,24 +270,20 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
   } else if (MODE == kModeTma && warp == kTmaWarp) {
     // ================================================================ TMA PRODUCER (TMA mode)
     if (lane == 0) {
-      if (RESIDENT) {
-        mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nchunks * C::kBBytes));
-        for (int c = 0; c < nchunks; ++c)
-          bulk_g2s(sBres + c * C::kBBytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, w_full);
-      }
       int stage = 0;
       uint32_t phase = 1;
       for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait(&empty_bar[stage], phase);
           uint8_t* st_base = sStage + stage * C::kStage;
-          mbar_arrive_expect_tx(&tma_full[stage], static_cast<uint32_t>(kABytes + (RESIDENT ? 0 : C::kBBytes)));
+          mbar_arrive_expect_tx(&tma_full[stage], static_cast<uint32_t>(MT * kABytes + (RESIDENT ? 0 : C::kBBytes)));
+          // one box of MT*128 rows (rows past the end of the tensor are zero-filled and still counted)
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
               ::"r"(smem_u32(st_base)), "l"(&tmap), "r"((c % p.chunks_per_tap) * 64),
-                "r"(tile * kBM + (c / p.chunks_per_tap) * p.tma_tap_rows), "r"(smem_u32(&tma_full[stage]))
+                "r"(tile * (MT * kBM) + (c / p.chunks_per_tap) * p.tma_tap_rows), "r"(smem_u32(&tma_full[stage]))
               : "memory");
-          if (!RESIDENT) bulk_g2s(st_base + kABytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &tma_full[stage]);
+          if (!RESIDENT) bulk_g2s(st_base + MT * kABytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &tma_full[stage]);
           if (++stage == NS) {
             stage = 0;
             phase ^= 1u;
@@ -278,11 +293,6 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
     }
   } else if (warp < kProducerWarps) {
     // ================================================================ PRODUCERS
-    if (RESIDENT && tid == 0) {
-      mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nchunks * C::kBBytes));
-      for (int c = 0; c < nchunks; ++c)
-        bulk_g2s(sBres + c * C::kBBytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, w_full);
-    }
     const int g = tid & 7;
     const int rbase = tid >> 3;  // 0..31 ; rows rbase + 32*i
     const uint32_t a_off = static_cast<uint32_t>(rbase * 128 + ((g ^ (rbase & 7)) << 4));  // + i*4096
@@ -473,7 +483,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
         const int ab = tcount & 1;
         mbar_wait(&acc_empty[ab], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * BN;
+        const uint32_t d_tmem = tmem_base + ab * (MT * BN);
         for (int c = 0; c < nchunks; ++c) {
           if (MODE == kModeTma && !has_pro_any) mbar_wait(&tma_full[stage], phase);
           else mbar_wait(&full_bar[stage], phase);
@@ -486,10 +496,14 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
             kv = min(64, p.Cin - kc);
           }
           const uint32_t a_addr = smem_u32(sStage + stage * C::kStage);
-          const uint32_t b_addr = RESIDENT ? smem_u32(sBres + c * C::kBBytes) : a_addr + kABytes;
-          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint32_t b_addr = RESIDENT ? smem_u32(sBres + c * C::kBBytes) : a_addr + MT * kABytes;
           const uint64_t db = umma_desc_sw128(b_addr);
-          for (int k = 0; k < kv / 16; ++k) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) {
+            const uint64_t da = umma_desc_sw128(a_addr + t * kABytes);
+            for (int k = 0; k < kv / 16; ++k)
+              umma_bf16_ss(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           if (++stage == NS) {
             stage = 0;
@@ -499,7 +513,8 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
         if (has_shift) {
           // SBO = 0: all sixteen 8-row groups of the A operand alias the same 8 "ones" rows
           const uint64_t d_ones = umma_desc_sw128(smem_u32(sOnes)) & ~(static_cast<uint64_t>(0x3FFF) << 32);
-          umma_bf16_ss(d_tmem, d_ones, umma_desc_sw128(smem_u32(sBias)), idesc, 1u);
+#pragma unroll
+          for (int t = 0; t < MT; ++t) umma_bf16_ss(d_tmem + t * BN, d_ones, umma_desc_sw128(smem_u32(sBias)), idesc, 1u);
         }
         umma_commit(&acc_full[ab]);
       }
@@ -527,8 +542,17 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
     int tcount = 0;
     for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
+      mbar_wait(&acc_full[ab], (tcount >> 1) & 1);
+      tc_fence_after();
+      if (cb_begin >= cb_end) {  // nothing to read for this warp (narrow tile): release immediately
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        continue;
+      }
+#pragma unroll 1
+      for (int t = 0; t < MT; ++t) {
       // output row of MY accumulator row (lane); -1 = past the end
-      const int m = tile * kBM + qw * 32 + lane;
+      const int m = (tile * MT + t) * kBM + qw * 32 + lane;
       int orow = -1;
       if (m < p.M) {
         orow = m;
@@ -547,21 +571,14 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
           orow = (f * (p.Ho + 2) + oy + 1) * (p.Wo + 2) + ox + 1;
         }
       }
-      mbar_wait(&acc_full[ab], (tcount >> 1) & 1);
-      tc_fence_after();
-      if (cb_begin >= cb_end) {  // nothing to read for this warp (narrow tile): release immediately
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[ab]);
-        continue;
-      }
       for (int cb0 = cb_begin; cb0 < cb_end; cb0 += cpg) {
         // ---- phase A: my row -> 128-byte staging row, epilogue math applied, output dtype
         for (int u = 0; u < cpg && cb0 + u < cb_end; ++u) {
           const int cb = cb0 + u;
           uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * BN + cb * 32, v);
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + (ab * MT + t) * BN + cb * 32, v);
           tmem_ld_wait();
-          if (cb + 1 == cb_end) {  // last read of this accumulator by this warp: hand it back to the MMA warp
+          if (cb + 1 == cb_end && t == MT - 1) {  // last read of this accumulator by this warp: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
@@ -610,6 +627,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
         }
         __syncwarp();  // staging rows are rewritten by the next group
       }
+      }  // t
     }
   }
   tc_fence_before();
@@ -630,9 +648,9 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int BN, int MODE, bool RESIDENT>
+template <int BN, int MODE, bool RESIDENT, int MT = 1>
 cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN, RESIDENT>;
+  using C = Cfg<BN, RESIDENT, MT>;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (MODE == kModeTma) {
@@ -645,7 +663,7 @@ cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
       gdim[1] = static_cast<cuuint64_t>(p.tma_rows);
       gstride[0] = static_cast<cuuint64_t>(p.tma_row_bytes);
     }
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kBM)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(MT * kBM)};
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p.in), gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -654,18 +672,17 @@ cudaError_t launch_t(const ConvGemmParams& p, int num_sms, cudaStream_t stream) 
   }
   static bool configured = false;  // per instantiation; handles are single-device (see tennis_b200.h)
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, MODE, RESIDENT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int m_tiles = ((p.M + kBM - 1) / kBM + MT - 1) / MT;
   const int n_tiles = (p.Cout + BN - 1) / BN;
   int gx = num_sms / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > m_tiles) gx = m_tiles;
   dim3 grid(gx, n_tiles);
-  conv_gemm_kernel<BN, MODE, RESIDENT><<<grid, Warps<MODE>::kThreads, C::kSmem, stream>>>(p, tmap);
-  return cudaGetLastError();
+  return launch_pdl(conv_gemm_kernel<BN, MODE, RESIDENT, MT>, grid, dim3(Warps<MODE>::kThreads), C::kSmem, stream, p, tmap);
 }
 
 template <int BN>
@@ -682,6 +699,12 @@ cudaError_t launch_bn(const ConvGemmParams& p, int num_sms, cudaStream_t stream)
       if (p.mode == kModeConv) return launch_t<BN, kModeConv, true>(p, num_sms, stream);
       if (p.mode == kModeStem) return launch_t<BN, kModeStem, true>(p, num_sms, stream);
     }
+  }
+  if constexpr (BN <= 128) {
+    // streamed weights: pair two M tiles per weight chunk when there is enough work to keep every SM busy
+    // (TN_TILE_PAIR_MIN=<tiles> overrides the threshold; the parity tests use it to force either path)
+    static const int pair_min = getenv("TN_TILE_PAIR_MIN") ? atoi(getenv("TN_TILE_PAIR_MIN")) : 4 * num_sms;
+    if (tma_ok && (p.M + kBM - 1) / kBM >= pair_min) return launch_t<BN, kModeTma, false, 2>(p, num_sms, stream);
   }
   if (tma_ok) return launch_t<BN, kModeTma, false>(p, num_sms, stream);
   switch (p.mode) {

@@ -56,6 +56,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 
 // ---------------------------------------------------------------- bulk async copy (UBLKCP)
 // global -> shared, completion signalled as transaction bytes on an mbarrier.  16-byte granularity.
+// Programmatic dependent launch (see launch_pdl in tn_common.h).  launch_dependents lets the next kernel on the stream
+// begin its prologue once every CTA of this grid has issued it; wait blocks until the previous grid has completed and
+// its writes are visible.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

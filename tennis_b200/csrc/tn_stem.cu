@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_s2d_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  griddep_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 1);
@@ -80,11 +81,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_s2d_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
+    mbar_arrive_expect_tx(w_full, kWBytes);
+    bulk_g2s(sW, p.wpack, kWBytes, w_full);
+  }
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, kWBytes);
-      bulk_g2s(sW, p.wpack, kWBytes, w_full);
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_con
   uint64_t* w_full = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  griddep_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 1);
@@ -232,11 +237,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
+    mbar_arrive_expect_tx(w_full, kWBytes);
+    bulk_g2s(sW, p.wpack, kWBytes, w_full);
+  }
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, kWBytes);
-      bulk_g2s(sW, p.wpack, kWBytes, w_full);
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -416,8 +424,7 @@ cudaError_t launch_stem_s2d(const StemDev& sd, const __nv_bfloat16* z, int n, in
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ProfScope prof_scope(kProfConvGemm, st);
-  stem_s2d_kernel<<<grid, kThreads, kSmem, st>>>(tmap, p);
-  return cudaGetLastError();
+  return launch_pdl(stem_s2d_kernel, dim3(grid), dim3(kThreads), kSmem, st, tmap, p);
 }
 
 cudaError_t launch_stem_pool(const StemDev& sd, const __nv_bfloat16* z, int n, int Hz, int Wz, int Hs, int Ws, int Hp, int Wp,
@@ -451,8 +458,7 @@ cudaError_t launch_stem_pool(const StemDev& sd, const __nv_bfloat16* z, int n, i
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ProfScope prof_scope(kProfConvGemm, st);
-  stem_pool_kernel<<<grid, kThreads, kPoolSmem, st>>>(tmap, p);
-  return cudaGetLastError();
+  return launch_pdl(stem_pool_kernel, dim3(grid), dim3(kThreads), kPoolSmem, st, tmap, p);
 }
 
 }  // namespace tn

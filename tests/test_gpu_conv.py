@@ -52,6 +52,8 @@ CASES = [
     ("3x3_c256", 1, 10, 10, 128, 128, 256, 3, 1, 1, True, False, False),
     ("1x1_c512", 1, 16, 16, 256, 256, 512, 1, 2, 0, True, False, False),
     ("1x1_n768", 1, 1, 300, 1024, 1024, 768, 1, 1, 0, False, True, False),
+    # >= 4*148 M tiles and K > 256: two M tiles share each streamed weight chunk (odd tile count -> ragged last pair)
+    ("1x1_k320_paired", 25, 56, 56, 320, 320, 128, 1, 1, 0, True, True, True),
 ]
 
 

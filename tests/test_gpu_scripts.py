@@ -60,3 +60,17 @@ def test_train_frozen_backbone_cnn_gru(tmp_path):
                 "--data_shape", "224", "--batch_size", "4", "--every", "24,48,48", "--epochs", "1", "--synthetic", "--model_id",
                 "t043"], str(tmp_path))
     assert "validation" in out
+
+
+@pytest.mark.parametrize("env_extra", [{"TN_TILE_PAIR_MIN": "1"}, {"TN_NO_PDL": "1", "TN_TILE_PAIR_MIN": "1000000"},
+                                       {"TN_RNN_NO_WREG": "1"}],
+                         ids=["paired_tiles_forced", "no_pdl_no_pairing", "rnn_smem_weights"])
+def test_smoke_parity_under_kernel_variants(env_extra):
+    """Every launch-path switch must give the same oracle parity: DenseNet-121 + Bi-GRU logits vs the CPU oracle with
+    tile pairing forced on for every streamed-weight 1x1 conv, with PDL and pairing off, and with the shared-memory
+    RNN scan."""
+    env = dict(os.environ, PYTHONPATH=ROOT, **env_extra)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "argmax equal: True" in r.stdout
