@@ -249,6 +249,8 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
   __nv_bfloat16* bott = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * (pl.Hb[0] + 2) * (pl.Wb[0] + 2) * kBott);
   __nv_bfloat16* blk[4];
   for (int b = 0; b < 4; ++b) blk[b] = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * pl.Hb[b] * pl.Wb[b] * pl.ctot[b]);
+  // pooled, activated transition input (largest at transition 1)
+  __nv_bfloat16* pooled = ws.get<__nv_bfloat16>(static_cast<size_t>(n) * pl.Hb[1] * pl.Wb[1] * pl.ctot[0]);
   if (dry) return TN_OK;
 
   // stem: conv7x7/2 -> BN -> ReLU (epilogue) ; max-pool 3/2/1 into channels [0,64) of block 1
@@ -294,9 +296,18 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
     if (b < 3) {
       // transition: BN+ReLU -> 1x1 conv -> avgpool 2x2, computed as conv1x1(avgpool(relu(bn(x))))
       const int Ho = pl.Hb[b + 1], Wo = pl.Wb[b + 1];
-      ConvGemmParams p = conv_params(bb->trans[b].conv, blk[b], ct, n, H, W, Ho, Wo, 2, 0, &bb->trans[b].bn, blk[b + 1],
-                                     pl.ctot[b + 1], 0, nullptr, false);
-      TN_CUDA(launch_conv_gemm(p, st));
+      if ((H % 2) == 0 && (W % 2) == 0 && (ct % 64) == 0 && !getenv("TN_TRANS_GATHER_POOL")) {
+        // streaming pre-pass (BN+ReLU+pool, 1/4 of the bytes out) + a plain TMA-fed 1x1 GEMM on the pooled rows
+        TN_CUDA(launch_bn_relu_pool2(blk[b], n, H, W, ct, ct, bb->trans[b].bn.scale, bb->trans[b].bn.shift, pooled, st));
+        ConvGemmParams p = conv_params(bb->trans[b].conv, pooled, ct, n, Ho, Wo, Ho, Wo, 1, 0, nullptr, blk[b + 1],
+                                       pl.ctot[b + 1], 0, nullptr, false);
+        p.mode = kModeConv;
+        TN_CUDA(launch_conv_gemm(p, st));
+      } else {  // in-GEMM gather of the four pooled pixels (odd maps)
+        ConvGemmParams p = conv_params(bb->trans[b].conv, blk[b], ct, n, H, W, Ho, Wo, 2, 0, &bb->trans[b].bn, blk[b + 1],
+                                       pl.ctot[b + 1], 0, nullptr, false);
+        TN_CUDA(launch_conv_gemm(p, st));
+      }
     }
   }
   TN_CUDA(launch_tail_pool(blk[3], n, pl.Hb[3], pl.Wb[3], pl.ctot[3], pl.ctot[3], 7, 7, pl.ph, pl.pw, bb->bn_final.scale,

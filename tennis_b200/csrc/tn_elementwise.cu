@@ -164,6 +164,62 @@ cudaError_t launch_tail_pool(const __nv_bfloat16* in, int n, int H, int W, int C
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- transition pre-pass: BN -> ReLU -> AvgPool 2x2 (bf16 out)
+// DenseNet transition = BN -> ReLU -> conv1x1 -> avgpool2; the pool commutes with the 1x1 conv, so the activated input is
+// pooled first (this kernel, a pure streaming pass) and the GEMM then runs on 4x fewer rows through the TMA-fed path.
+__global__ void bn_relu_pool2_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int cstride, int Ho, int Wo,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     __nv_bfloat16* __restrict__ out, size_t total) {
+  const int cg = C / 8;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % cg);
+  size_t t = i / cg;
+  const int ox = static_cast<int>(t % Wo);
+  t /= Wo;
+  const int oy = static_cast<int>(t % Ho);
+  const size_t f = t / Ho;
+  const __nv_bfloat16* base = in + ((f * H + 2 * oy) * W + 2 * ox) * cstride + c8 * 8;
+  uint4 v[4];
+  v[0] = __ldg(reinterpret_cast<const uint4*>(base));
+  v[1] = __ldg(reinterpret_cast<const uint4*>(base + cstride));
+  v[2] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(W) * cstride));
+  v[3] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(W + 1) * cstride));
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c8 * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c8 * 8) + 1);
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c8 * 8)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c8 * 8) + 1);
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16x2(w4[j]);
+      acc[2 * j] += fmaxf(fmaf(x.x, sc[2 * j], sh[2 * j]), 0.f);
+      acc[2 * j + 1] += fmaxf(fmaf(x.y, sc[2 * j + 1], sh[2 * j + 1]), 0.f);
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0] * 0.25f, acc[1] * 0.25f);
+  o.y = pack_bf16x2(acc[2] * 0.25f, acc[3] * 0.25f);
+  o.z = pack_bf16x2(acc[4] * 0.25f, acc[5] * 0.25f);
+  o.w = pack_bf16x2(acc[6] * 0.25f, acc[7] * 0.25f);
+  *reinterpret_cast<uint4*>(out + i * 8) = o;
+}
+
+cudaError_t launch_bn_relu_pool2(const __nv_bfloat16* in, int n, int H, int W, int C, int cstride, const float* scale,
+                                 const float* shift, __nv_bfloat16* out, cudaStream_t st) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = static_cast<size_t>(n) * Ho * Wo * (C / 8);
+  if (total == 0) return cudaSuccess;
+  if ((C % 8) != 0 || (cstride % 8) != 0) return cudaErrorInvalidValue;
+  ProfScope prof_scope(kProfOther, st);
+  bn_relu_pool2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, H, W, C, cstride, Ho, Wo, scale, shift,
+                                                                                  out, total);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- small dense layer (fp32), one warp per output
 // y[r, j] = b[j] + sum_k x[r, k] * W[j, k]     (Gluon Dense: weight (out, in))
 __global__ void dense_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,

@@ -15,6 +15,9 @@ cudaError_t launch_s2d_convert(const void* in, int is_u8_nhwc, __nv_bfloat16* ou
                                const float* scale3, const float* shift3, cudaStream_t st);
 cudaError_t launch_maxpool3s2(const __nv_bfloat16* in, __nv_bfloat16* out, int n, int H, int W, int C, int Ho, int Wo,
                               int out_cstride, int out_coff, cudaStream_t st);
+// Transition pre-pass: out[n, H/2, W/2, C] = avgpool2x2(relu(in * scale + shift)), bf16, dense channel stride C.
+cudaError_t launch_bn_relu_pool2(const __nv_bfloat16* in, int n, int H, int W, int C, int cstride, const float* scale,
+                                 const float* shift, __nv_bfloat16* out, cudaStream_t st);
 cudaError_t launch_tail_pool(const __nv_bfloat16* in, int n, int H, int W, int C, int cstride, int kh, int kw, int ph,
                              int pw, const float* scale, const float* shift, float* feats, __nv_bfloat16* feats_bf16,
                              cudaStream_t st);
