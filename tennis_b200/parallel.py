@@ -80,62 +80,154 @@ class ShardedCNNRNN(object):
     __call__ = forward
 
 
+def modelled_makespan(sizes, copy_ms, fixed_ms, compute_ms):
+    """Makespan of a chunked copy/compute pipeline: chunk k's kernels start when its copy has landed and chunk k-1's
+    kernels are done; copies run back to back at `copy_ms` per item, a chunk of n items computes in fixed_ms + n*compute_ms."""
+    t_copy = t_done = 0.0
+    for n in sizes:
+        t_copy += copy_ms * n
+        t_done = max(t_done, t_copy) + fixed_ms + compute_ms * n
+    return t_done
+
+
+def plan_chunks(B, copy_ms, fixed_ms, compute_ms, max_chunks=8, units=32):
+    """Chunk boundaries [0, ..., B] minimising `modelled_makespan` (hill climbing over a coarse grid of `units`)."""
+    U = max(1, min(units, B))
+
+    def cost(sz):
+        return modelled_makespan([B * u / float(U) for u in sz], copy_ms, fixed_ms, compute_ms)
+
+    best = None
+    for k in range(1, min(max_chunks, U) + 1):
+        seeds = [[U // k + (1 if i < U % k else 0) for i in range(k)]]
+        w = list(range(1, k + 1))
+        arith = [max(1, int(U * x / float(sum(w)))) for x in w]
+        arith[-1] += U - sum(arith)
+        if arith[-1] >= 1:
+            seeds.append(arith)
+        for sz in seeds:
+            sz = list(sz)
+            c = cost(sz)
+            improved = True
+            while improved:
+                improved = False
+                for i in range(len(sz)):
+                    for j in range(len(sz)):
+                        if i == j or sz[i] <= 1:
+                            continue
+                        sz[i] -= 1
+                        sz[j] += 1
+                        c2 = cost(sz)
+                        if c2 < c - 1e-9:
+                            c, improved = c2, True
+                        else:
+                            sz[i] += 1
+                            sz[j] -= 1
+            if best is None or c < best[0] - 1e-9:
+                best = (c, list(sz))
+    cuts, acc = [0], 0
+    for u in best[1]:
+        acc += u
+        nxt = B if acc == U else int(round(B * acc / float(U)))
+        if nxt > cuts[-1]:
+            cuts.append(nxt)
+    if cuts[-1] != B:
+        cuts.append(B)
+    return cuts
+
+
 class HostPipeline(object):
     """End-to-end step from HOST memory: pinned host clips -> chunked H2D on a copy stream overlapped with the
-    backbone of the previous chunk -> temporal head -> logits back on the host.  This is the call a user of the
-    reference makes when they write `split_and_load(batch) ; model(x) ; out.asnumpy()` (train.py:410-431)."""
+    backbone of the previous chunks -> temporal head -> logits back on the host.  This is the call a user of the
+    reference makes when they write `split_and_load(batch) ; model(x) ; out.asnumpy()` (train.py:410-431).
 
-    def __init__(self, sharded, chunks=4):
+    `forward(x)` is that synchronous call.  `submit(x)` / `result(h)` split it so a loader loop can keep one step in
+    flight (the H2D of step s+1 overlaps the kernels of step s, like MXNet's asynchronous engine does for the
+    reference's loop); at most two steps may be outstanding."""
+
+    def __init__(self, sharded, chunks=8):
         self.sh = sharded
         self.chunks = chunks
         self.copy_stream = torch.cuda.Stream()
         self._dev_bufs = None
+        self._consumed = [None, None]   # per device buffer: event recorded after its last consumer kernel
+        self._turn = 0
+        self._model = {}                # (shape, dtype) -> (copy_ms, fixed_ms, compute_ms) per clip, measured once
 
     def _bufs(self, shape, dtype, device):
         key = (tuple(shape), dtype)
         if self._dev_bufs is None or self._dev_bufs[0] != key:
+            torch.cuda.current_stream().synchronize()
             self._dev_bufs = (key, [torch.empty(shape, dtype=dtype, device=device) for _ in range(2)])
+            self._consumed = [None, None]
         return self._dev_bufs[1]
 
-    def _schedule(self, B):
-        if B < 16 or self.chunks <= 1:
-            n = max(1, min(self.chunks, B))
-            per = (B + n - 1) // n
-            return [min(B, i * per) for i in range(n)] + [B]
-        cuts, size, lo = [0], max(1, B // 16), 0
-        while lo < B:
-            lo = lo + size if B - (lo + size) >= size else B  # fold a short tail into the last chunk
-            cuts.append(lo)
-            size *= 2
-        return cuts
+    def _calibrate(self, clips_host, buf):
+        """Measure, once per input format, the three numbers the chunk plan needs: host->device ms per clip and the
+        backbone's fixed + per-clip ms (two chunk sizes).  Host->device of a 224x224 fp32 frame takes about as long as
+        its DenseNet forward, a uint8 frame a quarter of that, so the best plan depends on the format."""
+        B = clips_host.shape[0]
+        main = torch.cuda.current_stream()
 
-    def forward(self, clips_host):
-        """clips_host: pinned (B,T,3,H,W) fp32 [or (B,T,H,W,3) uint8] host tensor -> (B*world, C) fp32 host tensor."""
+        def timed(fn):
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            fn()
+            e1.record(main)
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+
+        nc = max(1, B // 8)
+        copy_ms = timed(lambda: buf[:nc].copy_(clips_host[:nc], non_blocking=True)) / nc
+        n1, n2 = max(1, B // 16), max(2, B // 4)
+        if n2 <= n1 or B < 4:
+            return copy_ms, 0.0, timed(lambda: self.sh.features_local(buf[:B])) / B
+        t1 = timed(lambda: self.sh.features_local(buf[:n1]))
+        t2 = timed(lambda: self.sh.features_local(buf[:n2]))
+        per = max(1e-6, (t2 - t1) / (n2 - n1))
+        return copy_ms, max(0.0, t1 - per * n1), per
+
+    def _schedule(self, B, model=None):
+        if model is None or self.chunks <= 1:
+            n = max(1, min(self.chunks, B))
+            return sorted(set(int(round(B * k / float(n))) for k in range(n + 1)))
+        return plan_chunks(B, model[0], model[1], model[2], max_chunks=self.chunks)
+
+    def submit(self, clips_host):
+        """Queue one step; returns a handle for `result`.  clips_host: pinned (B,T,3,H,W) fp32 [or (B,T,H,W,3) uint8]."""
         assert not clips_host.is_cuda
         B, T = clips_host.shape[:2]
         dev = torch.device("cuda", torch.cuda.current_device())
-        # chunk schedule: a small first chunk so compute starts after ~1/16 of the copy, then growing chunks so the
-        # kernels keep large grids (H2D of chunk i+1 overlaps the backbone of chunk i)
-        bounds = self._schedule(B)
-        nch = len(bounds) - 1
-        per = max(bounds[i + 1] - bounds[i] for i in range(nch))
         main = torch.cuda.current_stream()
-        bufs = self._bufs((per,) + tuple(clips_host.shape[1:]), clips_host.dtype, dev)
-        feats_all, twin_all = [], []
+        slot = self._turn & 1
+        self._turn += 1
+        buf = self._bufs(tuple(clips_host.shape), clips_host.dtype, dev)[slot]
+        key = (tuple(clips_host.shape), clips_host.dtype)
+        if key not in self._model:
+            if self._consumed[slot] is not None:
+                self._consumed[slot].synchronize()
+            self._model[key] = self._calibrate(clips_host, buf) if self.chunks > 1 and B >= 4 else None
+        bounds = self._schedule(B, self._model[key])
+        self.last_plan = {"cuts": bounds, "model_ms_per_clip": self._model[key]}  # (copy, fixed, compute); for reports
+        nch = len(bounds) - 1
         ready = [torch.cuda.Event() for _ in range(nch)]
-        consumed = [torch.cuda.Event() for _ in range(nch)]
-        for i in range(nch):
-            lo, hi = bounds[i], bounds[i + 1]
-            with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
-                    self.copy_stream.wait_event(consumed[i - 2])
-                bufs[i % 2][: hi - lo].copy_(clips_host[lo:hi], non_blocking=True)
+        with torch.cuda.stream(self.copy_stream):
+            if self._consumed[slot] is not None:  # the step that last used this buffer must have read it
+                self.copy_stream.wait_event(self._consumed[slot])
+            for i in range(nch):
+                lo, hi = bounds[i], bounds[i + 1]
+                buf[lo:hi].copy_(clips_host[lo:hi], non_blocking=True)
                 ready[i].record(self.copy_stream)
+        feats_all, twin_all = [], []
+        for i in range(nch):
             main.wait_event(ready[i])
-            f, t = self.sh.features_local(bufs[i % 2][: hi - lo])
-            consumed[i].record(main)
+            f, t = self.sh.features_local(buf[bounds[i]:bounds[i + 1]])
             feats_all.append(f)
             twin_all.append(t)
+        done = torch.cuda.Event()
+        done.record(main)
+        self._consumed[slot] = done
         feats = torch.cat(feats_all, 0)
         twin = torch.cat(twin_all, 0) if twin_all[0] is not None else None
         if self.sh.world > 1:
@@ -145,6 +237,21 @@ class HostPipeline(object):
             logits = self.sh.head(g.reshape(Bg, T, -1), None)
         else:
             logits = self.sh.head(feats.reshape(B, T, -1), None if twin is None else twin.reshape(B, T, -1))
-        return logits.cpu()  # device -> host read of the step's result (sync point, train.py:427-431)
+        host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+        host.copy_(logits, non_blocking=True)  # device -> host read of the step's result, queued behind the head
+        fin = torch.cuda.Event()
+        fin.record(main)
+        return (host, fin, logits)
+
+    @staticmethod
+    def result(handle):
+        """Wait for a submitted step and return its (B*world, C) fp32 host logits (the sync point, train.py:427-431)."""
+        host, fin, _ = handle
+        fin.synchronize()
+        return host
+
+    def forward(self, clips_host):
+        """clips_host: pinned (B,T,3,H,W) fp32 [or (B,T,H,W,3) uint8] host tensor -> (B*world, C) fp32 host tensor."""
+        return self.result(self.submit(clips_host))
 
     __call__ = forward

@@ -112,10 +112,27 @@ def test_bleu_known_values():
 
 
 def test_host_pipeline_chunk_schedule():
-    from tennis_b200.parallel import HostPipeline
+    from tennis_b200.parallel import HostPipeline, modelled_makespan, plan_chunks
     h = HostPipeline.__new__(HostPipeline)
-    h.chunks = 4
+    h.chunks = 8
     for B in (1, 3, 16, 17, 64, 100, 256):
-        cuts = h._schedule(B)
-        assert cuts[0] == 0 and cuts[-1] == B and all(b > a for a, b in zip(cuts, cuts[1:]))
-    assert h._schedule(64) == [0, 4, 12, 28, 64]
+        for model in (None, (0.35, 0.8, 0.32), (0.09, 0.8, 0.32), (1.0, 0.0, 0.1)):
+            cuts = h._schedule(B, model)
+            assert cuts[0] == 0 and cuts[-1] == B and all(b > a for a, b in zip(cuts, cuts[1:]))
+    h.chunks = 1
+    assert h._schedule(64, (0.35, 0.8, 0.32)) == [0, 64]
+
+    def span(cuts, m):
+        return modelled_makespan([b - a for a, b in zip(cuts, cuts[1:])], *m)
+
+    # copy about as slow as compute (fp32 frames): the plan beats one big chunk, the doubling schedule and uniform chunks,
+    # and does not end on a large chunk (its kernels cannot start before the whole copy has landed)
+    m = (0.349, 0.79, 0.3226)
+    cuts = plan_chunks(64, *m)
+    assert span(cuts, m) <= min(span([0, 64], m), span([0, 4, 12, 28, 64], m), span(list(range(0, 65, 8)), m)) + 1e-9
+    assert cuts[-1] - cuts[-2] <= 16
+    # copy 4x faster than compute (uint8 frames): few chunks, small first one
+    m8 = (0.087, 0.79, 0.3226)
+    cuts8 = plan_chunks(64, *m8)
+    assert len(cuts8) - 1 <= 4 and cuts8[1] <= 16
+    assert span(cuts8, m8) <= span(cuts, m8)
