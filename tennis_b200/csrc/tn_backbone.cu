@@ -22,6 +22,10 @@ struct DenseLayer {
   BnDev bn1, bn2;
   ConvDev conv1, conv2;
   Conv3x3Dev conv2h;  // same weights, packed for the halo kernel
+  // conv1 with BN1+ReLU in clamp form (bn1 scale folded into the weights, threshold term folded into the shift)
+  ConvDev conv1c;
+  const uint4* clamp1 = nullptr;
+  const float* shift1c = nullptr;
   int cin;
 };
 struct Transition {
@@ -142,11 +146,14 @@ bool take_stem_bn(Cursor& cur, DeviceArena& arena, ConvDev* cv, BnDev* bn, StemD
   return make_conv(arena, ws.data(), 64, 64, 4, 1, kModeConv, cv, hs.data());
 }
 // conv followed (in parameter order) by the BatchNorm whose scale is folded into its weights; the shift stays in `bn`
-bool take_conv_bn(Cursor& cur, DeviceArena& arena, int Cout, int Cin, int R, int S, int mode, ConvDev* cv, BnDev* bn) {
+bool take_conv_bn(Cursor& cur, DeviceArena& arena, int Cout, int Cin, int R, int S, int mode, ConvDev* cv, BnDev* bn,
+                  std::vector<float>* hs_out = nullptr, std::vector<float>* hb_out = nullptr) {
   const float* w = cur.take(static_cast<size_t>(Cout) * Cin * R * S);
   if (!w) return false;
   std::vector<float> hs, hb;
   if (!take_bn(cur, arena, Cout, bn, &hs, &hb)) return false;
+  if (hs_out) *hs_out = hs;
+  if (hb_out) *hb_out = hb;
   return make_conv(arena, w, Cout, Cin, R, S, mode, cv, hs.data());
 }
 
@@ -239,6 +246,15 @@ bool densenet_plan(int h, int w, DensePlan* pl) {
   return true;
 }
 
+// Frames per pass of one dense block (see densenet_forward).  Defaults are set from measurements on B200.
+int chunk_frames(int b, int n) {
+  static const int dflt[4] = {0, 0, 0, 0};
+  static const char* names[4] = {"TN_CHUNK_B1", "TN_CHUNK_B2", "TN_CHUNK_B3", "TN_CHUNK_B4"};
+  const char* e = getenv(names[b]);  // read per call: the tuning sweep (tools/chunk_sweep.py) changes it in-process
+  int c = e ? atoi(e) : dflt[b];
+  return (c <= 0 || c > n) ? n : c;
+}
+
 int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int w, float* feats, void* feats_bf16,
                      Bump& ws, bool dry, cudaStream_t st) {
   DensePlan pl;
@@ -268,29 +284,44 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
   for (int b = 0; b < 4; ++b) {
     const int H = pl.Hb[b], W = pl.Wb[b], ct = pl.ctot[b];
     const bool halo = conv3x3_halo_supported(H, W) && static_cast<long long>(n) * (H + 2) * (W + 2) < (1ll << 31) - 4096;
-    if (halo) TN_CUDA(launch_zero_border(bott, n, H + 2, W + 2, kBott, st));
+    // Frame-chunked schedule: the dense layers of a block run chunk by chunk so that the bottleneck tile (and, for small
+    // enough chunks, the concat buffer) of a chunk stays resident in the 126 MB L2 between the 1x1 conv that writes it and the
+    // 3x3 conv that reads it.  The bottleneck buffer is reused by every chunk (same addresses -> dirty lines are overwritten
+    // in L2 and never reach HBM).  TN_CHUNK_B<1..4>=<frames> overrides; 0 = whole batch in one pass.
+    const int cs = chunk_frames(b, n);
+    if (halo) TN_CUDA(launch_zero_border(bott, cs, H + 2, W + 2, kBott, st));
     // EXPERIMENTAL (off by default): one fused kernel per dense layer, bottleneck kept in shared memory (tn_dense_fused.cu).
     // Numerically identical to the two-kernel path, but with one tile in flight per SM its phases serialise and it measures
     // slower (31.8 vs 25.8 ms/2048 frames); enable with TN_DENSE_FUSED_MIN_W=<min map width>, e.g. 28 for blocks 1-2.
     const char* fused_env = getenv("TN_DENSE_FUSED_MIN_W");
     const int fused_min_w = fused_env ? atoi(fused_env) : (1 << 30);
     const bool fused = dense_fused_supported(H, W) && W >= fused_min_w;
-    for (const DenseLayer& L : bb->layers[b]) {
-      if (fused) {
-        TN_CUDA(launch_dense_layer_fused(blk[b], ct, n, H, W, L.cin, L.bn1.scale, L.bn1.shift, L.conv1.wpack, L.conv1.num_chunks,
-                                         L.bn2.shift, L.conv2h.wpack, bb->num_sms, st));
-        continue;
-      }
-      // BN1+ReLU (prologue) -> 1x1 conv -> BN2+ReLU (epilogue) -> bottleneck
-      ConvGemmParams p1 = conv_params(L.conv1, blk[b], ct, n, H, W, H, W, 1, 0, &L.bn1, bott, kBott, 0, &L.bn2, true);
-      p1.out_pad = halo ? 1 : 0;
-      TN_CUDA(launch_conv_gemm(p1, st));
-      // 3x3 conv, 32 new channels written in place at channel offset cin
-      if (halo) {
-        TN_CUDA(launch_conv3x3_halo(L.conv2h, bott, n, H, W, blk[b], ct, L.cin, bb->num_sms, st));
-      } else {
-        ConvGemmParams p2 = conv_params(L.conv2, bott, kBott, n, H, W, H, W, 1, 1, nullptr, blk[b], ct, L.cin, nullptr, false);
-        TN_CUDA(launch_conv_gemm(p2, st));
+    const bool clamp = getenv("TN_NO_CLAMP_PROLOGUE") == nullptr;  // A/B switch for the measurement in DESIGN.md 4.1
+    for (int f0 = 0; f0 < n; f0 += cs) {
+      const int nf = (n - f0 < cs) ? (n - f0) : cs;
+      __nv_bfloat16* xb = blk[b] + static_cast<size_t>(f0) * H * W * ct;
+      for (const DenseLayer& L : bb->layers[b]) {
+        if (fused) {
+          TN_CUDA(launch_dense_layer_fused(xb, ct, nf, H, W, L.cin, L.bn1.scale, L.bn1.shift, L.conv1.wpack, L.conv1.num_chunks,
+                                           L.bn2.shift, L.conv2h.wpack, bb->num_sms, st));
+          continue;
+        }
+        // BN1+ReLU (prologue) -> 1x1 conv -> BN2+ReLU (epilogue) -> bottleneck
+        ConvGemmParams p1 = conv_params(clamp ? L.conv1c : L.conv1, xb, ct, nf, H, W, H, W, 1, 0, clamp ? nullptr : &L.bn1, bott,
+                                        kBott, 0, &L.bn2, true);
+        if (clamp) {  // BN1+ReLU as an exact bf16 clamp; scale in the weights, threshold term in the shift
+          p1.pro_clamp = L.clamp1;
+          p1.epi_shift = L.shift1c;
+        }
+        p1.out_pad = halo ? 1 : 0;
+        TN_CUDA(launch_conv_gemm(p1, st));
+        // 3x3 conv, 32 new channels written in place at channel offset cin
+        if (halo) {
+          TN_CUDA(launch_conv3x3_halo(L.conv2h, bott, nf, H, W, xb, ct, L.cin, bb->num_sms, st));
+        } else {
+          ConvGemmParams p2 = conv_params(L.conv2, bott, kBott, nf, H, W, H, W, 1, 1, nullptr, xb, ct, L.cin, nullptr, false);
+          TN_CUDA(launch_conv_gemm(p2, st));
+        }
       }
     }
     if (b < 3) {
@@ -438,8 +469,12 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
       for (int l = 0; l < kDenseCfg[b] && ok; ++l) {
         DenseLayer L;
         L.cin = c;
-        ok = ok && take_bn(cur, bb->arena, c, &L.bn1);
-        ok = ok && take_conv_bn(cur, bb->arena, kBott, c, 1, 1, tn::kModeConv, &L.conv1, &L.bn2);
+        std::vector<float> s1, b1, s2, b2;
+        ok = ok && take_bn(cur, bb->arena, c, &L.bn1, &s1, &b1);
+        const float* w1 = cur.p;
+        ok = ok && take_conv_bn(cur, bb->arena, kBott, c, 1, 1, tn::kModeConv, &L.conv1, &L.bn2, &s2, &b2);
+        ok = ok && tn::make_conv1x1_clamp(bb->arena, w1, kBott, c, s1.data(), b1.data(), s2.data(), b2.data(), &L.conv1c,
+                                          &L.clamp1, &L.shift1c);
         const float* w2 = cur.p;
         ok = ok && take_conv(cur, bb->arena, kGrowth, kBott, 3, 3, tn::kModeConv, &L.conv2);
         ok = ok && make_conv3x3(bb->arena, w2, &L.conv2h);

@@ -127,6 +127,57 @@ bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int
   return out->wpack != nullptr;
 }
 
+bool make_conv1x1_clamp(DeviceArena& arena, const float* w, int Cout, int Cin, const float* in_scale, const float* in_shift,
+                        const float* out_scale, const float* out_shift, ConvDev* out, const uint4** clamp_dev,
+                        const float** shift_dev) {
+  // relu(s*x + b) = s * (clamp(x, lo, hi) - t) with t = -b/s (see ConvGemmParams::pro_clamp).  t is rounded to bf16 (the
+  // comparison against bf16 x is then exact); the weights carry s (and the following BatchNorm's scale) and are rounded to
+  // bf16 once; the constant -sum_c Wq[n][c]*t[c] is accumulated in double from the ROUNDED weights so that a channel that is
+  // clamped everywhere cancels exactly.  Channels whose scale is zero (or so small that t leaves the bf16 range) are
+  // constants relu(b): their weight is dropped and W*relu(b) goes into the shift.
+  const uint16_t kPosInf = 0x7F80, kNegInf = 0xFF80;
+  std::vector<float> wf(static_cast<size_t>(Cout) * Cin);
+  std::vector<float> tq(Cin, 0.f);
+  std::vector<uint16_t> clamp(static_cast<size_t>(2) * ((Cin + 7) / 8) * 8, 0);
+  std::vector<double> bias(Cout, 0.0);
+  for (int n = 0; n < Cout; ++n) bias[n] = out_shift ? out_shift[n] : 0.0;
+  for (int c = 0; c < Cin; ++c) {
+    const float s = in_scale[c], b = in_shift[c];
+    const float t = (s != 0.f) ? -b / s : 0.f;
+    const bool constant = (s == 0.f) || !(fabsf(t) < 1e30f);
+    uint16_t lo = kNegInf, hi = kPosInf;
+    if (!constant) {
+      const __nv_bfloat16 tb = __float2bfloat16(t);
+      uint16_t bits;
+      memcpy(&bits, &tb, 2);
+      tq[c] = __bfloat162float(tb);
+      if (s > 0.f) lo = bits;
+      else hi = bits;
+    }
+    const size_t slot = static_cast<size_t>(c / 8) * 16 + (c % 8);
+    clamp[slot] = lo;
+    clamp[slot + 8] = hi;
+    for (int n = 0; n < Cout; ++n) {
+      const float os = out_scale ? out_scale[n] : 1.f;
+      const float wv = w[static_cast<size_t>(n) * Cin + c];
+      if (constant) {
+        wf[static_cast<size_t>(n) * Cin + c] = 0.f;
+        bias[n] += static_cast<double>(wv) * os * fmaxf(b, 0.f);
+      } else {
+        const float folded = wv * s * os;
+        wf[static_cast<size_t>(n) * Cin + c] = folded;
+        bias[n] -= static_cast<double>(__bfloat162float(__float2bfloat16(folded))) * tq[c];
+      }
+    }
+  }
+  if (!make_conv(arena, wf.data(), Cout, Cin, 1, 1, kModeConv, out, nullptr)) return false;
+  std::vector<float> sh(Cout);
+  for (int n = 0; n < Cout; ++n) sh[n] = static_cast<float>(bias[n]);
+  *clamp_dev = static_cast<const uint4*>(arena.upload(clamp.data(), clamp.size() * sizeof(uint16_t)));
+  *shift_dev = static_cast<const float*>(arena.upload(sh.data(), Cout * sizeof(float)));
+  return *clamp_dev && *shift_dev;
+}
+
 // ---------------------------------------------------------------- launch counters / event timing
 namespace {
 struct ProfState {

@@ -57,6 +57,12 @@ bool make_bn(DeviceArena& arena, const float* gamma, const float* beta, const fl
 bool make_conv(DeviceArena& arena, const float* w, int Cout, int Cin, int R, int S, int mode, ConvDev* out,
                const float* fold_scale = nullptr);
 
+// 1x1 conv whose BN+ReLU pre-activation runs in the "clamp" form (ConvGemmParams::pro_clamp): packs w (Cout,Cin) with the input
+// BatchNorm scale (and the optional output-side scale) folded in, uploads the per-channel clamp bounds and the corrected shift.
+bool make_conv1x1_clamp(DeviceArena& arena, const float* w, int Cout, int Cin, const float* in_scale, const float* in_shift,
+                        const float* out_scale, const float* out_shift, ConvDev* out, const uint4** clamp_dev,
+                        const float** shift_dev);
+
 // ---- optional per-launch device timing (bench.py roofline): CUDA events on the launch stream around each kernel.
 enum ProfKind : int { kProfConvGemm = 0, kProfOther = 1 };
 void prof_begin(int kind, cudaStream_t st);

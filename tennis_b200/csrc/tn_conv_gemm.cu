@@ -111,6 +111,13 @@ __device__ __forceinline__ uint32_t cvt_pack(float a, float b, bool relu) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+// min(max(x, lo), hi) on two packed bf16
+__device__ __forceinline__ uint32_t clamp_bf16x2(uint32_t x, uint32_t lo, uint32_t hi) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 t;\n\tmax.bf16x2 t, %1, %2;\n\tmin.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "r"(x), "r"(lo), "r"(hi));
+  return r;
+}
+
 struct ScaleShift8 {
   float sc[8], sh[8];
 };
@@ -174,6 +181,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
   const int n_tile = blockIdx.y;
   const int num_m_tiles = ((p.M + kBM - 1) / kBM + MT - 1) / MT;  // scheduling units: MT consecutive 128-row tiles
   const int nchunks = p.num_chunks;
+  const int nsr = (p.stage_cap > 0 && p.stage_cap < NS) ? p.stage_cap : NS;  // ring depth actually used (tuning knob)
 
   griddep_launch_dependents();
   if (tid == 0) {
@@ -191,13 +199,17 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
   }
   if (warp == kMmaWarp) tmem_alloc<C::kTmemCols>(tmem_slot);
   // Per-channel shift (folded BN beta / bias) is added BY THE TENSOR CORE: one extra K=16 UMMA per tile with
-  // A = [1 1 0 ... 0] for every row and B[n] = [hi(shift[n]) lo(shift[n]) 0 ... 0] (bf16 hi/lo split keeps ~16 bits).
+  // A = [1 1 1 0 ... 0] for every row and B[n] = [hi mid lo 0 ... 0] of shift[n] (three-way bf16 split = 24 bits: the
+  // clamp prologue folds sum_c W'[n][c]*t[c] into the shift, which can exceed the output magnitude).
   const bool has_shift = p.epi_shift != nullptr;
   if (has_shift) {
     for (int i = tid; i < kOnesBytes / 16; i += kThreads) {  // 8 rows x 8 chunks; row r's K-chunk 0 lives at slot (r & 7)
       const int r = i >> 3, slot = i & 7;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (slot == (r & 7)) v.x = 0x3F803F80u;  // (1.0, 1.0) bf16
+      if (slot == (r & 7)) {  // (1.0, 1.0, 1.0) bf16
+        v.x = 0x3F803F80u;
+        v.y = 0x00003F80u;
+      }
       *reinterpret_cast<uint4*>(sOnes + i * 16) = v;
     }
     for (int i = tid; i < BN * 8; i += kThreads) {
@@ -207,8 +219,11 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
       if (slot == (r & 7) && n < p.Cout) {
         const float sh = p.epi_shift[n];
         const __nv_bfloat16 hi = __float2bfloat16(sh);
-        const __nv_bfloat16 lo = __float2bfloat16(sh - __bfloat162float(hi));
-        v.x = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+        const float r1 = sh - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16(r1);
+        const __nv_bfloat16 lo = __float2bfloat16(r1 - __bfloat162float(mid));
+        v.x = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(mid)) << 16);
+        v.y = static_cast<uint32_t>(__bfloat16_as_ushort(lo));
       }
       *reinterpret_cast<uint4*>(sBias + i * 16) = v;
     }
@@ -226,11 +241,55 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
   }
   griddep_wait();
 
-  const bool has_pro_any = p.pro_scale != nullptr;
+  const bool has_pro_any = p.pro_scale != nullptr || p.pro_clamp != nullptr;
   if (MODE == kModeTma && warp < kProducerWarps) {
     // ================================================================ TRANSFORMERS (TMA mode)
     // The raw 128x64 bf16 tile landed in its final swizzled position; apply BN+ReLU in place.
-    if (has_pro_any) {
+    if (p.pro_clamp != nullptr) {
+      // clamp form: two packed bf16 min/max per channel pair, exact (see ConvGemmParams::pro_clamp)
+      const int j = tid & 7;
+      const int rbase = tid >> 3;
+      const int g = j ^ (rbase & 7);  // channel group stored at 16-byte slot j of my rows
+      const uint32_t my_off = static_cast<uint32_t>(rbase * 128 + (j << 4));  // + i*4096
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c) {
+          const int ch = (c % p.chunks_per_tap) * 64 + g * 8;
+          const bool ch_ok = ch < p.Cin;
+          uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+          if (ch_ok) {
+            lo = __ldg(p.pro_clamp + (ch >> 3) * 2);
+            hi = __ldg(p.pro_clamp + (ch >> 3) * 2 + 1);
+          }
+          mbar_wait(&tma_full[stage], phase);
+          const uint32_t a_stage = smem_u32(sStage + stage * C::kStage);
+          if (ch_ok) {
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+              uint4 v[kRowsPerThread];
+#pragma unroll
+              for (int i = 0; i < kRowsPerThread; ++i) v[i] = lds128(a_stage + t * kABytes + my_off + i * 4096);
+#pragma unroll
+              for (int i = 0; i < kRowsPerThread; ++i) {
+                v[i].x = clamp_bf16x2(v[i].x, lo.x, hi.x);
+                v[i].y = clamp_bf16x2(v[i].y, lo.y, hi.y);
+                v[i].z = clamp_bf16x2(v[i].z, lo.z, hi.z);
+                v[i].w = clamp_bf16x2(v[i].w, lo.w, hi.w);
+                sts128(a_stage + t * kABytes + my_off + i * 4096, v[i]);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[stage]);
+          if (++stage == nsr) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else if (has_pro_any) {
       const int j = tid & 7;
       const int rbase = tid >> 3;
       const int g = j ^ (rbase & 7);  // channel group stored at 16-byte slot j of my rows
@@ -260,7 +319,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[stage]);
-          if (++stage == NS) {
+          if (++stage == nsr) {
             stage = 0;
             phase ^= 1u;
           }
@@ -272,8 +331,24 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 1;
+      // L2 prefetch cursor: runs p.l2_prefetch K-chunks ahead of the loads.  The stage ring holds only NS x kStage bytes per SM,
+      // too few to cover the loaded DRAM latency; a prefetched box costs no shared memory and turns the later load into an L2 hit.
+      int pf_tile = blockIdx.x, pf_c = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile >= num_m_tiles) return;
+        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap),
+                     "r"((pf_c % p.chunks_per_tap) * 64), "r"(pf_tile * (MT * kBM) + (pf_c / p.chunks_per_tap) * p.tma_tap_rows)
+                     : "memory");
+        if (++pf_c == nchunks) {
+          pf_c = 0;
+          pf_tile += gridDim.x;
+        }
+      };
+      if (p.l2_prefetch > 0)
+        for (int i = 0; i < p.l2_prefetch + NS; ++i) prefetch_next();
       for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
+          if (p.l2_prefetch > 0) prefetch_next();
           mbar_wait(&empty_bar[stage], phase);
           uint8_t* st_base = sStage + stage * C::kStage;
           mbar_arrive_expect_tx(&tma_full[stage], static_cast<uint32_t>(MT * kABytes + (RESIDENT ? 0 : C::kBBytes)));
@@ -284,7 +359,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
                 "r"(tile * (MT * kBM) + (c / p.chunks_per_tap) * p.tma_tap_rows), "r"(smem_u32(&tma_full[stage]))
               : "memory");
           if (!RESIDENT) bulk_g2s(st_base + MT * kABytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &tma_full[stage]);
-          if (++stage == NS) {
+          if (++stage == nsr) {
             stage = 0;
             phase ^= 1u;
           }
@@ -452,7 +527,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
       if (++s_c == nchunks) s_c = 0;
-      if (++s_stage == NS) {
+      if (++s_stage == nsr) {
         s_stage = 0;
         s_phase ^= 1u;
       }
@@ -505,7 +580,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
               umma_bf16_ss(d_tmem + t * BN, da + 2 * k, db + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == NS) {
+          if (++stage == nsr) {
             stage = 0;
             phase ^= 1u;
           }
@@ -693,6 +768,7 @@ cudaError_t launch_bn(const ConvGemmParams& p, int num_sms, cudaStream_t stream)
                       (p.mode == kModeConv && p.R == 1 && p.S == 1 && p.stride == 1 && p.pad == 0 && p.H == p.Ho &&
                        p.W == p.Wo && (p.in_cstride % 64) == 0 && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
                        p.num_chunks * 64 <= p.in_cstride);
+  if (p.pro_clamp != nullptr && !tma_ok) return cudaErrorInvalidValue;  // the clamp prologue exists in the TMA-fed kernels only
   if constexpr (BN <= 128) {
     if (p.num_chunks <= kMaxResidentChunks) {  // weights stay resident in shared memory
       if (tma_ok) return launch_t<BN, kModeTma, true>(p, num_sms, stream);
@@ -740,12 +816,19 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, cudaStream_t stream) {
   }
   if (p.M <= 0) return cudaSuccess;
   if (p.epi_scale != nullptr) return cudaErrorInvalidValue;  // per-channel scales are folded into the packed weights
+  ConvGemmParams pp = p;
+  if (pp.l2_prefetch == 0) {  // default distance; TN_L2_PREFETCH=<chunks> (-1 = off) overrides, read per call for tuning sweeps
+    const char* e = getenv("TN_L2_PREFETCH");
+    pp.l2_prefetch = e ? atoi(e) : 0;
+  }
+  if (pp.l2_prefetch < 0) pp.l2_prefetch = 0;
+  if (const char* e = getenv("TN_STAGE_CAP")) pp.stage_cap = atoi(e);
   ProfScope prof_scope(kProfConvGemm, stream);
   switch (conv_gemm_pick_bn(p.Cout)) {
-    case 32: return launch_bn<32>(p, num_sms, stream);
-    case 64: return launch_bn<64>(p, num_sms, stream);
-    case 128: return launch_bn<128>(p, num_sms, stream);
-    default: return launch_bn<256>(p, num_sms, stream);
+    case 32: return launch_bn<32>(pp, num_sms, stream);
+    case 64: return launch_bn<64>(pp, num_sms, stream);
+    case 128: return launch_bn<128>(pp, num_sms, stream);
+    default: return launch_bn<256>(pp, num_sms, stream);
   }
 }
 

@@ -25,6 +25,12 @@ struct ConvGemmParams {
   const float* pro_scale;
   const float* pro_shift;
   int pro_relu;
+  // "clamp" form of the same pre-activation (TMA-fed 1x1 convs only; replaces pro_scale/pro_shift when non-null):
+  //   relu(s*x + b) = s * (clamp(x, lo, hi) - t),  t = -b/s,  (lo, hi) = (t, +inf) for s > 0, (-inf, t) for s < 0,
+  // with s folded into the packed weights and -sum_c W'[n][c]*t[c] folded into epi_shift by make_conv1x1_clamp()
+  // (tn_common.cu).  The in-place transform is then two packed bf16 min/max per channel pair and is EXACT (no rounding of
+  // the activated operand).  Layout: per group of 8 channels one uint4 of lo (8 bf16) followed by one uint4 of hi.
+  const uint4* pro_clamp;
   // packed weights: [n_tile][chunk][BN rows x 128 B, 128B-swizzled K-major image]
   const uint8_t* wpack;
   int num_chunks;      // K-chunks of 64 per output tile
@@ -50,6 +56,8 @@ struct ConvGemmParams {
   const __nv_bfloat16* res;  // optional residual, NHWC bf16 at the output resolution
   int res_cstride;
   int M;  // F * Ho * Wo
+  int stage_cap;    // > 0: use at most this many ring stages (latency experiments)
+  int l2_prefetch;  // TMA modes: K-chunks prefetched into L2 ahead of the stage ring (0 = library default, < 0 = off)
 };
 
 int conv_gemm_pick_bn(int cout);

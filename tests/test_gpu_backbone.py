@@ -27,6 +27,61 @@ def test_backbone_features_match_oracle(arch, size, n):
     assert (out_bf.float().cpu() - out.cpu()).abs().max().item() <= 1e-2 * max(1.0, scale)
 
 
+def test_backbone_negative_and_zero_bn_scales():
+    """BN1+ReLU runs as a bf16 clamp with the scale folded into the 1x1 weights (tn_common.cu::make_conv1x1_clamp):
+    gamma < 0 flips the clamp side, gamma == 0 makes the channel the constant relu(beta).  Both must match the oracle."""
+    from oracle import vision as O
+    from tennis_b200 import ops
+    p = {k: v.clone() for k, v in O.synthetic_params("densenet121", seed=1234).items()}
+    g = torch.Generator().manual_seed(5)
+    touched = 0
+    for k in p:
+        if k.endswith("bn1.gamma"):
+            r = torch.rand(p[k].shape, generator=g)
+            p[k] = torch.where(r < 0.25, -p[k], p[k])          # a quarter of the channels: negative scale
+            p[k] = torch.where(r > 0.95, torch.zeros_like(p[k]), p[k])  # 5 %: exactly zero
+            touched += 1
+    assert touched == 58
+    _, x = O.synthetic_frames(2, 224, seed=100)
+    with torch.no_grad():
+        ref = O.FEATURES["densenet121"](x, p)
+    out = ops.Backbone("densenet121", O.flatten_params("densenet121", p))(x.cuda())
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print("negative/zero bn1 scales: max|ref|=%.4f max err=%.5f" % (scale, err))
+    assert err < FEAT_TOL["densenet121"] * max(1.0, scale)
+
+
+def test_clamp_prologue_not_less_accurate_than_scale_shift_prologue():
+    """The clamp form rounds nothing on the activated operand; its error against the fp32 oracle must not exceed the
+    scale/shift form's (TN_NO_CLAMP_PROLOGUE=1) by more than noise."""
+    import os
+    from oracle import vision as O
+    from tennis_b200 import ops
+    p = O.synthetic_params("densenet121", seed=1234)
+    _, x = O.synthetic_frames(3, 224, seed=100)
+    with torch.no_grad():
+        ref = O.FEATURES["densenet121"](x, p)
+    bb = ops.Backbone("densenet121", O.flatten_params("densenet121", p))
+    errs = {}
+    try:
+        for name, val in (("clamp", None), ("scale_shift", "1")):
+            if val is None:
+                os.environ.pop("TN_NO_CLAMP_PROLOGUE", None)
+            else:
+                os.environ["TN_NO_CLAMP_PROLOGUE"] = val
+            out = bb(x.cuda())
+            torch.cuda.synchronize()
+            e = (out.cpu() - ref).abs()
+            errs[name] = (e.max().item(), e.mean().item())
+    finally:
+        os.environ.pop("TN_NO_CLAMP_PROLOGUE", None)
+    print("max/mean |cuda - oracle|:", errs)
+    assert errs["clamp"][1] < 1.25 * errs["scale_shift"][1]
+    assert errs["clamp"][0] < FEAT_TOL["densenet121"] * max(1.0, ref.abs().max().item())
+
+
 def test_backbone_u8_input_matches_f32_input():
     from oracle import vision as O
     from tennis_b200 import ops
@@ -100,6 +155,7 @@ def test_fused_dense_layer_kernel_matches_two_kernel_path():
     for i, env_val in enumerate([None, "28"]):
         env = dict(os.environ)
         env.pop("TN_DENSE_FUSED_MIN_W", None)
+        env["TN_NO_CLAMP_PROLOGUE"] = "1"  # the fused kernel applies BN1+ReLU in the scale/shift form: compare like with like
         if env_val:
             env["TN_DENSE_FUSED_MIN_W"] = env_val
         path = "/tmp/_tn_fused_%d.pt" % i

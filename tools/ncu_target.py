@@ -1,0 +1,20 @@
+"""One warm-up forward, then ONE DenseNet-121 forward between cudaProfilerStart/Stop (for `ncu --profile-from-start off`).
+usage: python tools/ncu_target.py [n_frames]"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from oracle import vision as O  # noqa: E402  (only for synthetic weights)
+from tennis_b200 import ops  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+p = O.synthetic_params("densenet121", seed=1234)
+bb = ops.Backbone("densenet121", O.flatten_params("densenet121", p))
+x = torch.randn(n, 3, 224, 224, device="cuda")
+bb(x)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+bb(x)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
