@@ -296,7 +296,11 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
     const char* fused_env = getenv("TN_DENSE_FUSED_MIN_W");
     const int fused_min_w = fused_env ? atoi(fused_env) : (1 << 30);
     const bool fused = dense_fused_supported(H, W) && W >= fused_min_w;
-    const bool clamp = getenv("TN_NO_CLAMP_PROLOGUE") == nullptr;  // A/B switch for the measurement in DESIGN.md 4.1
+    // BN1+ReLU as a bf16 clamp (ConvGemmParams::pro_clamp) is opt-in: measured on B200 it is no faster than the fp32
+    // scale/shift transform (the 1x1 kernels are bound by the memory system, not by the transformer warps) and its
+    // systematic threshold rounding raises the mean feature error by ~16 % (profiles/r1_ab_clamp_prologue.log).
+    const char* clamp_env = getenv("TN_CLAMP_PROLOGUE");
+    const bool clamp = clamp_env != nullptr && clamp_env[0] == '1';
     for (int f0 = 0; f0 < n; f0 += cs) {
       const int nf = (n - f0 < cs) ? (n - f0) : cs;
       __nv_bfloat16* xb = blk[b] + static_cast<size_t>(f0) * H * W * ct;

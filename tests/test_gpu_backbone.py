@@ -27,10 +27,16 @@ def test_backbone_features_match_oracle(arch, size, n):
     assert (out_bf.float().cpu() - out.cpu()).abs().max().item() <= 1e-2 * max(1.0, scale)
 
 
-def test_backbone_negative_and_zero_bn_scales():
-    """BN1+ReLU runs as a bf16 clamp with the scale folded into the 1x1 weights (tn_common.cu::make_conv1x1_clamp):
-    gamma < 0 flips the clamp side, gamma == 0 makes the channel the constant relu(beta).  Both must match the oracle."""
+@pytest.mark.parametrize("clamp", [False, True])
+def test_backbone_negative_and_zero_bn_scales(clamp, monkeypatch):
+    """Negative and zero BatchNorm scales in front of the 1x1 convs, for both forms of the pre-activation: fp32 scale/shift
+    (default) and the opt-in bf16 clamp with the scale folded into the weights (tn_common.cu::make_conv1x1_clamp), where
+    gamma < 0 flips the clamp side and gamma == 0 makes the channel the constant relu(beta)."""
     from oracle import vision as O
+    if clamp:
+        monkeypatch.setenv("TN_CLAMP_PROLOGUE", "1")
+    else:
+        monkeypatch.delenv("TN_CLAMP_PROLOGUE", raising=False)
     from tennis_b200 import ops
     p = {k: v.clone() for k, v in O.synthetic_params("densenet121", seed=1234).items()}
     g = torch.Generator().manual_seed(5)
@@ -53,9 +59,9 @@ def test_backbone_negative_and_zero_bn_scales():
     assert err < FEAT_TOL["densenet121"] * max(1.0, scale)
 
 
-def test_clamp_prologue_not_less_accurate_than_scale_shift_prologue():
-    """The clamp form rounds nothing on the activated operand; its error against the fp32 oracle must not exceed the
-    scale/shift form's (TN_NO_CLAMP_PROLOGUE=1) by more than noise."""
+def test_clamp_prologue_accuracy_vs_scale_shift_prologue():
+    """The opt-in clamp form (TN_CLAMP_PROLOGUE=1) must stay within the stated bf16 tolerance and within 1.5x of the default
+    scale/shift form's mean error against the fp32 oracle (measured: +16 %, from the bf16 rounding of the threshold)."""
     import os
     from oracle import vision as O
     from tennis_b200 import ops
@@ -66,19 +72,19 @@ def test_clamp_prologue_not_less_accurate_than_scale_shift_prologue():
     bb = ops.Backbone("densenet121", O.flatten_params("densenet121", p))
     errs = {}
     try:
-        for name, val in (("clamp", None), ("scale_shift", "1")):
+        for name, val in (("clamp", "1"), ("scale_shift", None)):
             if val is None:
-                os.environ.pop("TN_NO_CLAMP_PROLOGUE", None)
+                os.environ.pop("TN_CLAMP_PROLOGUE", None)
             else:
-                os.environ["TN_NO_CLAMP_PROLOGUE"] = val
+                os.environ["TN_CLAMP_PROLOGUE"] = val
             out = bb(x.cuda())
             torch.cuda.synchronize()
             e = (out.cpu() - ref).abs()
             errs[name] = (e.max().item(), e.mean().item())
     finally:
-        os.environ.pop("TN_NO_CLAMP_PROLOGUE", None)
+        os.environ.pop("TN_CLAMP_PROLOGUE", None)
     print("max/mean |cuda - oracle|:", errs)
-    assert errs["clamp"][1] < 1.25 * errs["scale_shift"][1]
+    assert errs["clamp"][1] < 1.5 * errs["scale_shift"][1]
     assert errs["clamp"][0] < FEAT_TOL["densenet121"] * max(1.0, ref.abs().max().item())
 
 
@@ -155,7 +161,7 @@ def test_fused_dense_layer_kernel_matches_two_kernel_path():
     for i, env_val in enumerate([None, "28"]):
         env = dict(os.environ)
         env.pop("TN_DENSE_FUSED_MIN_W", None)
-        env["TN_NO_CLAMP_PROLOGUE"] = "1"  # the fused kernel applies BN1+ReLU in the scale/shift form: compare like with like
+        env.pop("TN_CLAMP_PROLOGUE", None)
         if env_val:
             env["TN_DENSE_FUSED_MIN_W"] = env_val
         path = "/tmp/_tn_fused_%d.pt" % i
