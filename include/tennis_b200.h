@@ -177,6 +177,51 @@ int tn_gnmt_beam_search(tn_gnmt_t* g, const float* mem, const int32_t* src_len, 
                         float* scores, int32_t* valid_len, int* out_len, void* workspace, size_t workspace_bytes,
                         tn_stream_t stream);
 
+/* ------------------------------------------------------------------ captioner training (G9; train_gnmt.py:330-337)
+ * Building blocks of `with autograd.record(): out, _ = model(src, tgt[:, :-1], src_vl, tgt_vl - 1); loss = ...; loss.backward()`:
+ * the GRU/LSTM cells of GNMTEncoder/GNMTDecoder unrolled step by step with saved activations (gnmt.py:143-145,345-404),
+ * scaled-Luong attention (gluonnlp DotProductAttentionCell), Embedding, MaskedSoftmaxCELoss and output Dropout, each with its
+ * backward.  fp32 throughout; matrices are row-major with explicit row strides (a time step of a (B,T,C) tensor is addressed in
+ * place).  The Python side (tennis_b200/models/captioning/train_graph.py) sequences them. */
+/* C[M,N] = alpha * op(A) op(B) + beta * C; op(A) = A (M x K, lda) or A^T (A stored K x M); op(B) = B (K x N) or B^T (N x K). */
+int tn_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb,
+             float beta, float* C, int ldc, tn_stream_t stream);
+/* One cell step on B rows: gi = x W_i2h^T and gh = h_prev W_h2h^T without biases (row strides in floats), Gluon gate order.
+ * Writes h (and optionally a second strided copy h_out2), c (LSTM) and the 4H saved values per row that the backward needs
+ * (LSTM: i f g o; GRU: r z n and W_hn h + b_hn).  h_prev / c_prev NULL = zero state. */
+int tn_rnn_cell_forward(int cell, int B, int H, const float* gi, long long gi_stride, const float* gh, long long gh_stride,
+                        const float* bi, const float* bh, const float* h_prev, long long hp_stride, const float* c_prev,
+                        long long cp_stride, float* h_out, long long ho_stride, float* h_out2, long long ho2_stride, float* c_out,
+                        long long co_stride, float* save, long long sv_stride, tn_stream_t stream);
+/* Backward of step t.  dh/dc (B,H): in = gradient w.r.t. this step's state from step t+1, out = the direct part of the gradient
+ * w.r.t. the previous state (the caller adds dgh W_h2h).  dy/dy2: gradients w.r.t. this step's output(s).  With valid_len, rows
+ * with t >= len produce zeros and at t == len-1 the final-state gradients dh_last/dc_last enter (MXNet unroll(valid_length),
+ * SURVEY.md A.4).  dgi (and dgh for GRU, where they differ): gate pre-activation gradients, strided rows. */
+int tn_rnn_cell_backward(int cell, int B, int H, int t, const int32_t* valid_len, const float* save, long long sv_stride,
+                         const float* h_prev, long long hp_stride, const float* c_prev, long long cp_stride, const float* c_cur,
+                         long long cc_stride, const float* dy, long long dy_stride, const float* dy2, long long dy2_stride,
+                         const float* dh_last, const float* dc_last, float* dh, float* dc, float* dgi, long long dgi_stride,
+                         float* dgh, long long dgh_stride, tn_stream_t stream);
+/* q (B,H) = projected query; w (B,T) = softmax((q/sqrt(H)) mem^T masked by src_len) * mask; ctx = w mem, written to one or two
+ * strided destinations.  Backward accumulates into dmem (B,T,H) and writes dq. */
+int tn_attention_forward(const float* q, long long q_stride, const float* mem, const int32_t* src_len, int B, int T, int H,
+                         float* w, float* ctx1, long long c1_stride, float* ctx2, long long c2_stride, tn_stream_t stream);
+int tn_attention_backward(const float* q, long long q_stride, const float* mem, const int32_t* src_len, int B, int T, int H,
+                          const float* w, const float* dctx1, long long d1_stride, const float* dctx2, long long d2_stride,
+                          float* dq, long long dq_stride, float* dmem, tn_stream_t stream);
+/* dweight[ids[r]] += dy[r] (ids are float token ids, as the scripts pass them). */
+int tn_embedding_backward(const float* ids, const float* dy, long long dy_stride, float* dweight, int N, int E, int V,
+                          tn_stream_t stream);
+/* MaskedSoftmaxCELoss with gradient: loss (B) as tn_masked_softmax_ce; dpred (B,T,V) = head_grad[b]/T (softmax - onehot) on valid
+ * tokens, 0 elsewhere (dpred/head_grad may be NULL); workspace_bt: B*T floats. */
+int tn_masked_softmax_ce_grad(const float* pred, const float* label, const float* valid_len, const float* head_grad,
+                              float* loss, float* dpred, float* workspace_bt, int B, int T, int V, tn_stream_t stream);
+/* Inverted-dropout mask in {0, 1/(1-p)} from a counter-based generator; y = x * mask with rows t >= seq_len[b] zeroed
+ * (Dropout at gnmt.py:152,389 + SequenceMask at :157-159,298-301); either mask or seq_len may be NULL. */
+int tn_dropout_mask(float* mask, size_t n, float p, unsigned long long seed, tn_stream_t stream);
+int tn_mul_mask(const float* x, const float* mask, const int32_t* seq_len, float* y, int B, int T, int C, tn_stream_t stream);
+int tn_axpy(float* y, const float* x, float a, size_t n, tn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,24 @@ SIGNATURES.update({
 })
 
 SIGNATURES["tn_masked_softmax_ce"] = (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p])
+
+_LL = ctypes.c_longlong
+SIGNATURES.update({
+    "tn_sgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_int,
+                         c_void_p]),
+    "tn_rnn_cell_forward": (c_int, [c_int, c_int, c_int, c_void_p, _LL, c_void_p, _LL, c_void_p, c_void_p, c_void_p, _LL,
+                                    c_void_p, _LL, c_void_p, _LL, c_void_p, _LL, c_void_p, _LL, c_void_p, _LL, c_void_p]),
+    "tn_rnn_cell_backward": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, _LL, c_void_p, _LL, c_void_p, _LL, c_void_p,
+                                     _LL, c_void_p, _LL, c_void_p, _LL, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _LL,
+                                     c_void_p, _LL, c_void_p]),
+    "tn_attention_forward": (c_int, [c_void_p, _LL, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, _LL, c_void_p,
+                                     _LL, c_void_p]),
+    "tn_attention_backward": (c_int, [c_void_p, _LL, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, _LL, c_void_p,
+                                      _LL, c_void_p, _LL, c_void_p, c_void_p]),
+    "tn_embedding_backward": (c_int, [c_void_p, c_void_p, _LL, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tn_masked_softmax_ce_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                          c_int, c_void_p]),
+    "tn_dropout_mask": (c_int, [c_void_p, c_size_t, c_float, ctypes.c_ulonglong, c_void_p]),
+    "tn_mul_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tn_axpy": (c_int, [c_void_p, c_void_p, c_float, c_size_t, c_void_p]),
+})

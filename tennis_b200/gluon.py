@@ -365,7 +365,12 @@ class MaskedSoftmaxCELoss(object):
     """gluonnlp.loss.MaskedSoftmaxCELoss forward (train_gnmt.py:256): (B,T,V) logits, (B,T) labels, (B,) valid lengths -> (B,)."""
 
     def __call__(self, pred, label, valid_length):
-        from . import ops
+        from . import autograd, ops
+        if autograd.is_recording():
+            from .models.captioning.train_graph import masked_softmax_ce
+            loss, _ = masked_softmax_ce(pred, label, valid_length)
+            autograd.tag(loss, lambda g, a=(pred, label, valid_length): masked_softmax_ce(a[0], a[1], a[2], head_grad=g)[1], pred)
+            return loss
         return ops.masked_softmax_ce(pred, label, valid_length)
 
 

@@ -250,7 +250,17 @@ class NMTModel(Block):
         return logits, states, []
 
     def forward(self, src_seq, tgt_seq, src_valid_length=None, tgt_valid_length=None):
-        """encode -> init_state_from_encoder -> decode_seq -> (logits (B,T_tgt,V), additional outputs)."""
+        """encode -> init_state_from_encoder -> decode_seq -> (logits (B,T_tgt,V), additional outputs).
+        Under autograd.record() (train_gnmt.py:330-334) the same computation runs through the training graph, which keeps
+        the activations and tags the logits with its backward."""
+        from ... import autograd
+        if autograd.is_recording():
+            from .train_graph import GNMTTrainGraph
+            self._train_calls = getattr(self, "_train_calls", 0) + 1
+            graph = GNMTTrainGraph(self, seed=self._train_calls)
+            logits = graph.forward(self.src_embed(src_seq), tgt_seq, src_valid_length, tgt_valid_length)
+            autograd.tag(logits, graph.backward, None)
+            return logits, [[], []]
         encoder_outputs, enc_add = self.encode(src_seq, valid_length=src_valid_length)
         decoder_states = self.decoder.init_state_from_encoder(encoder_outputs, encoder_valid_length=src_valid_length)
         outputs, _, dec_add = self.decode_seq(tgt_seq, decoder_states, tgt_valid_length)
