@@ -16,7 +16,7 @@ from tennis_b200.dataset import TennisSet
 from tennis_b200.gluon import MaskedSoftmaxCELoss
 from tennis_b200.metrics.vision import compute_bleu
 from tennis_b200.models.captioning.gnmt import BeamSearchScorer
-from tennis_b200.utils.captioning import get_comp_str, get_dataloaders, write_sentences
+from tennis_b200.utils.captioning import evaluate_captioner, get_comp_str, get_dataloaders, write_sentences
 from tennis_b200.utils.translation import BeamSearchTranslator
 from tennis_b200.vocab import load_embedding_file
 
@@ -26,29 +26,11 @@ loss_function = MaskedSoftmaxCELoss()
 
 
 def run_eval(data_loader, model, translator, vocab, ctx):
-    translation_out, all_ids = [], []
-    avg_loss, denom, ntok = 0.0, 0, 0
     tic = time.time()
-    for src, tgt, src_vl, tgt_vl, inst_ids in data_loader:
-        src, tgt = src.to(ctx).float(), tgt.to(ctx).float()
-        src_vl, tgt_vl = src_vl.to(ctx), tgt_vl.to(ctx)
-        out, _ = model(src, tgt[:, :-1], src_vl, tgt_vl - 1)
-        loss = loss_function(out, tgt[:, 1:], tgt_vl - 1).mean().item()
-        all_ids.extend(inst_ids.tolist())
-        avg_loss += loss * (tgt.shape[1] - 1)
-        denom += tgt.shape[1] - 1
-        samples, _, vlen = translator.translate(src_seq=src, src_valid_length=src_vl)
-        best, vbest = samples[:, 0, :].cpu().numpy(), vlen[:, 0].cpu().numpy()
-        for i in range(best.shape[0]):
-            toks = [vocab.idx_to_token[e] for e in best[i][1:(vbest[i] - 1)]]
-            ntok += len(toks)
-            translation_out.append(toks)
-    real = [None] * len(all_ids)
-    for ind, sent in zip(all_ids, translation_out):
-        real[ind] = sent
+    loss, real, ntok = evaluate_captioner(data_loader, model, loss_function, translator, vocab, ctx)
     dt = time.time() - tic
     logging.info('decoded %d caption tokens in %.2fs (%.1f tokens/sec)', ntok, dt, ntok / max(dt, 1e-9))
-    return avg_loss / max(1, denom), real
+    return loss, real
 
 
 def main(_argv):

@@ -95,3 +95,28 @@ def get_comp_str(tgts, prds):
         out += 'GT:\t' + (' '.join(tgt) if isinstance(tgt, (list, tuple)) else tgt) + '\n'
         out += '\nPD:\t' + (' '.join(prd) if isinstance(prd, (list, tuple)) else prd) + '\n\n\n'
     return out
+
+
+def evaluate_captioner(data_loader, model, loss_function, translator, vocab, ctx):
+    """The `evaluate` of train_gnmt.py:258-295 / evaluate_gnmt.py: teacher-forced MaskedSoftmaxCE loss + beam-search
+    translation of every batch, sentences restored to instance order.  -> (avg loss, sentences, caption tokens decoded)."""
+    translation_out, all_ids = [], []
+    avg_loss, denom, ntok = 0.0, 0, 0
+    for src, tgt, src_vl, tgt_vl, inst_ids in data_loader:
+        src, tgt = src.to(ctx).float(), tgt.to(ctx).float()
+        src_vl, tgt_vl = src_vl.to(ctx), tgt_vl.to(ctx)
+        out, _ = model(src, tgt[:, :-1], src_vl, tgt_vl - 1)
+        loss = float(loss_function(out, tgt[:, 1:], tgt_vl - 1).cpu().numpy().mean())
+        all_ids.extend(inst_ids.tolist())
+        avg_loss += loss * (tgt.shape[1] - 1)
+        denom += tgt.shape[1] - 1
+        samples, _, vlen = translator.translate(src_seq=src, src_valid_length=src_vl)
+        best, vbest = samples[:, 0, :].cpu().numpy(), vlen[:, 0].cpu().numpy()
+        for i in range(best.shape[0]):  # best beam, BOS/EOS stripped (train_gnmt.py:289-294)
+            toks = [vocab.idx_to_token[e] for e in best[i][1:(vbest[i] - 1)]]
+            ntok += len(toks)
+            translation_out.append(toks)
+    real = [None] * len(all_ids)
+    for ind, sent in zip(all_ids, translation_out):
+        real[ind] = sent
+    return avg_loss / max(1, denom), real, ntok

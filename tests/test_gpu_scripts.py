@@ -42,6 +42,24 @@ def test_evaluate_gnmt_synthetic(tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "models", "captioning", "experiments", "t101", "best_test_out.txt"))
 
 
+def test_train_gnmt_synthetic_and_resume(tmp_path):
+    """Captioner training on features (the published setting): epochs, checkpoints, valid_best, per-epoch outputs, resume."""
+    args = [os.path.join(ROOT, "train_gnmt.py"), "--feats_model", "0006", "--cell_type", "gru", "--batch_size", "4",
+            "--test_batch_size", "4", "--tgt_max_len", "10", "--epochs", "2", "--log_interval", "1", "--num_hidden", "32",
+            "--synthetic", "--model_id", "t102"]
+    out = _run(args, str(tmp_path))
+    exp = os.path.join(str(tmp_path), "models", "captioning", "experiments", "t102")
+    for f in ("0000.params", "0001.params", "valid_best.params", "epoch1_valid_out.txt", "best_test_out.txt", "val_gt.txt"):
+        assert os.path.exists(os.path.join(exp, f)), f
+    assert "[Epoch 1] valid Loss=" in out and "Best model test Loss=" in out and "Learning rate change" in out
+    out2 = _run(args[:args.index("--epochs")] + ["--epochs", "3"] + args[args.index("--epochs") + 2:], str(tmp_path))
+    assert "Loaded model params" in out2 and os.path.exists(os.path.join(exp, "0002.params"))
+    # the trained checkpoint is what evaluate_gnmt.py picks up
+    out3 = _run([os.path.join(ROOT, "evaluate_gnmt.py"), "--feats_model", "0006", "--cell_type", "gru", "--num_hidden", "32",
+                 "--test_batch_size", "4", "--tgt_max_len", "10", "--synthetic", "--model_id", "t102"], str(tmp_path))
+    assert "Loaded model params" in out3 and "valid_best.params" in out3
+
+
 def test_train_head_on_features_synthetic_and_resume(tmp_path):
     """The published CNN-RNN setting (features -> BiGRU -> max -> Dense): two epochs, checkpoints, scores.txt, resume."""
     args = [os.path.join(ROOT, "train.py"), "--feats_model", "0006", "--temp_pool", "gru", "--window", "8", "--batch_size", "16",
