@@ -13,7 +13,9 @@
 //      shared memory in the UMMA 128B-swizzled layout (image-border positions are written as zeros = the 3x3's padding);
 //   5. the MMA warp runs the 3x3 conv from that tile exactly like tn_conv3x3.cu (row-shifted descriptors for dy, N = 96 =
 //      3 dx taps stacked), and the epilogue combines the dx taps and stores the 32 new channels at their channel offset.
-// Shared memory (W=56): A/B1 ring 2 x 45 KB, bottleneck tile 58 KB, 3x3 weights 72 KB  = 220 KB.  TMEM: 2x128 + 96 columns.
+// Wide maps (W = 56) are cut into 14-column patches: a 16 x 10 halo tile yields 14 x 8 outputs (1.43x recompute instead of
+// 2.07x for two full rows).  Shared memory (W=56): A/B1 ring 3 x 36 KB, bottleneck tile 40 KB, 3x3 weights 72 KB = 223 KB.
+// TMEM: 2x128 + 96 columns.
 #include <cuda.h>
 #include <string.h>
 
@@ -34,11 +36,13 @@ constexpr int kN1 = 128, kN2 = 96;
 constexpr int kB1Bytes = kN1 * 128;     // one 64-wide K-chunk of the 1x1 weights
 constexpr int kW2Blob = kN2 * 128;
 constexpr int kW2Bytes = 6 * kW2Blob;   // 72 KB
-constexpr int kNS = 2;                  // ring stages
+constexpr int kMaxNS = 4;               // ring stages: as many as fit (FusedParams::ns)
 constexpr int kTmemCols = 512;          // acc1: 2 x 128, acc2: 96
 
 struct FusedParams {
-  int F, H, W, Wp, TR, NY;       // NY = TR + 2 halo rows
+  int ns;                        // ring stages in use (2..kMaxNS)
+  int F, H, W, Wp, TR, NY;       // tile = TR image rows x PW image columns; Wp = PW + 2 (row pitch of the halo tile); NY = TR + 2
+  int PW, tiles_x;               // PW == W (row bands) or a divisor-sized column patch (W = 56: 14 -> 16 x 10 halo tile)
   int halo_rows;                 // NY * Wp  (<= 256)
   int a_bytes;                   // halo_rows * 128 rounded up to 1024
   int tiles_per_frame, num_tiles;
@@ -73,16 +77,16 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = p.a_bytes + kB1Bytes;
-  uint8_t* sRing = smem;                                   // kNS x (A | B1)
-  uint8_t* sHalo = sRing + kNS * stage_bytes;              // 2 halves x a_bytes (bottleneck tile, bf16, swizzled)
+  uint8_t* sRing = smem;                                   // ns x (A | B1)
+  uint8_t* sHalo = sRing + p.ns * stage_bytes;              // 2 halves x a_bytes (bottleneck tile, bf16, swizzled)
   uint8_t* sW2 = sHalo + 2 * p.a_bytes;                    // 72 KB
   uint8_t* tail = sW2 + kW2Bytes;
   float* sShift2 = reinterpret_cast<float*>(tail);         // [128]
   float* xch = sShift2 + 128;                              // [2 halves][4 quarters][2][16]
-  uint64_t* tma_full = reinterpret_cast<uint64_t*>(xch + 256);  // [kNS]
-  uint64_t* a_ready = tma_full + kNS;                      // [kNS]  transformers done
-  uint64_t* empty_bar = a_ready + kNS;                     // [kNS]  MMA1 done with the stage
-  uint64_t* acc1_full = empty_bar + kNS;
+  uint64_t* tma_full = reinterpret_cast<uint64_t*>(xch + 256);  // [kMaxNS]
+  uint64_t* a_ready = tma_full + kMaxNS;                   // [kMaxNS]  transformers done
+  uint64_t* empty_bar = a_ready + kMaxNS;                  // [kMaxNS]  MMA1 done with the stage
+  uint64_t* acc1_full = empty_bar + kMaxNS;
   uint64_t* acc1_empty = acc1_full + 1;
   uint64_t* halo_full = acc1_empty + 1;
   uint64_t* halo_empty = halo_full + 1;
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < kNS; ++s) {
+    for (int s = 0; s < kMaxNS; ++s) {
       mbar_init(&tma_full[s], 1);
       mbar_init(&a_ready[s], kTransWarps);
       mbar_init(&empty_bar[s], 1);
@@ -125,18 +129,20 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
       uint32_t phase = 1;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int f = t / p.tiles_per_frame;
-        const int yt = t - f * p.tiles_per_frame;
-        const int y0 = yt * p.TR - 1;  // unpadded image row of the first halo row
+        const int tt = t - f * p.tiles_per_frame;
+        const int yt = tt / p.tiles_x, xt = tt - yt * p.tiles_x;
+        const int y0 = yt * p.TR - 1;  // unpadded image row / column of the first halo row / column
+        const int x0 = xt * p.PW - 1;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(&empty_bar[stage], phase);
           uint8_t* st = sRing + stage * stage_bytes;
           mbar_arrive_expect_tx(&tma_full[stage], static_cast<uint32_t>(p.halo_rows * 128 + kB1Bytes));
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-              ::"r"(smem_u32(st)), "l"(&tmap), "r"(c * 64), "r"(-1), "r"(y0), "r"(f), "r"(smem_u32(&tma_full[stage]))
+              ::"r"(smem_u32(st)), "l"(&tmap), "r"(c * 64), "r"(x0), "r"(y0), "r"(f), "r"(smem_u32(&tma_full[stage]))
               : "memory");
           bulk_g2s(st + p.a_bytes, p.w1pack + static_cast<size_t>(c) * kB1Bytes, kB1Bytes, &tma_full[stage]);
-          if (++stage == kNS) {
+          if (++stage == p.ns) {
             stage = 0;
             phase ^= 1u;
           }
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[stage]);
-        if (++stage == kNS) {
+        if (++stage == p.ns) {
           stage = 0;
           phase ^= 1u;
         }
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kNS) {
+          if (++stage == p.ns) {
             stage = 0;
             phase ^= 1u;
           }
@@ -251,8 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int f = t / p.tiles_per_frame;
-      const int yt = t - f * p.tiles_per_frame;
-      const int yp0 = yt * p.TR;  // padded row index of the first HALO row (padded row 0 = top border)
+      const int tt = t - f * p.tiles_per_frame;
+      const int yt = tt / p.tiles_x, xt = tt - yt * p.tiles_x;
+      const int yp0 = yt * p.TR;  // padded row / column index of the first HALO row / column (padded index 0 = border)
+      const int xp0 = xt * p.PW;
       // ------------------------------------------------ epilogue 1: TMEM -> (+shift2, ReLU, bf16) -> bottleneck tile in smem
       mbar_wait(acc1_full, it & 1);
       tc_fence_after();
@@ -262,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
         const bool in_tile = r < p.halo_rows;
         const int yy = r / p.Wp, xx = r - yy * p.Wp;
         const int yp = yp0 + yy;
-        const bool interior = in_tile && xx >= 1 && xx <= p.W && yp >= 1 && yp <= p.H;
+        const int xp = xp0 + xx;
+        const bool interior = in_tile && xp >= 1 && xp <= p.W && yp >= 1 && yp <= p.H;
         const uint32_t row_addr = smem_u32(sHalo) + r * 128;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
@@ -333,8 +342,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         const int yy = r / p.Wp, xx = r - yy * p.Wp;
         const int y = yp0 + yy;  // output image row (unpadded): padded row yp0+1+yy -> image row yp0+yy
-        if (yy < p.TR && xx >= 1 && xx <= p.W && y < p.H) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(f * p.H + y) * p.W + (xx - 1)) * p.out_cstride + p.out_coff + hf * 16);
+        const int xo = xp0 + xx - 1;  // output image column
+        if (yy < p.TR && xx >= 1 && xx <= p.PW && xo < p.W && y < p.H) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(f * p.H + y) * p.W + xo) * p.out_cstride + p.out_coff + hf * 16);
           dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
           dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
         }
@@ -361,8 +371,19 @@ EncodeTiledFn get_encode() {
 
 constexpr int kSmemLimit = 227 * 1024;
 
-bool geometry(int H, int W, int* TR, int* halo_rows, int* a_bytes, int* smem) {
-  const int Wp = W + 2;
+// Ring depth: as many stages as fit beside the bottleneck tile and the 3x3 weights (2..4).
+int ring_stages(int a_bytes) {
+  const int fixed = 1024 + 2 * a_bytes + kW2Bytes + 512 + 1024 + 256;
+  int ns = (kSmemLimit - fixed) / (a_bytes + kB1Bytes);
+  return ns > kMaxNS ? kMaxNS : ns;
+}
+
+bool geometry(int H, int W, int* TR, int* PW, int* halo_rows, int* a_bytes, int* smem) {
+  // Wide maps are cut into column patches so that the one-pixel halo costs less: W = 56 -> 14 x 8 outputs from a 16 x 10
+  // halo tile (1.43x recompute of the 1x1 conv instead of 2.07x for two full rows), and the smaller tile buys a deeper ring.
+  *PW = W;
+  if (W + 2 > 32 && W % 14 == 0) *PW = 14;
+  const int Wp = *PW + 2;
   if (Wp > 128) return false;
   *TR = 128 / Wp;
   if (*TR > H) *TR = H;
@@ -370,15 +391,17 @@ bool geometry(int H, int W, int* TR, int* halo_rows, int* a_bytes, int* smem) {
   *halo_rows = (*TR + 2) * Wp;
   if (*halo_rows > 256) return false;
   *a_bytes = static_cast<int>(align_up(static_cast<size_t>(*halo_rows) * 128, 1024));
-  *smem = 1024 + kNS * (*a_bytes + kB1Bytes) + 2 * *a_bytes + kW2Bytes + 512 + 1024 + 256;
+  const int ns = ring_stages(*a_bytes);
+  if (ns < 2) return false;
+  *smem = 1024 + ns * (*a_bytes + kB1Bytes) + 2 * *a_bytes + kW2Bytes + 512 + 1024 + 256;
   return *smem <= kSmemLimit;
 }
 
 }  // namespace
 
 bool dense_fused_supported(int H, int W) {
-  int TR, hr, ab, sm;
-  return geometry(H, W, &TR, &hr, &ab, &sm) && (W + 2) <= 256 && (TR + 2) <= 256;
+  int TR, PW, hr, ab, sm;
+  return geometry(H, W, &TR, &PW, &hr, &ab, &sm) && (PW + 2) <= 256 && (TR + 2) <= 256;
 }
 
 cudaError_t launch_dense_layer_fused(const __nv_bfloat16* blk, int blk_cstride, int F, int H, int W, int Cin, const float* bn1_scale,
@@ -388,13 +411,15 @@ cudaError_t launch_dense_layer_fused(const __nv_bfloat16* blk, int blk_cstride, 
   if (!encode) return cudaErrorNotSupported;
   FusedParams p;
   int smem;
-  if (!geometry(H, W, &p.TR, &p.halo_rows, &p.a_bytes, &smem)) return cudaErrorInvalidValue;
+  if (!geometry(H, W, &p.TR, &p.PW, &p.halo_rows, &p.a_bytes, &smem)) return cudaErrorInvalidValue;
   p.F = F;
   p.H = H;
   p.W = W;
-  p.Wp = W + 2;
+  p.Wp = p.PW + 2;
   p.NY = p.TR + 2;
-  p.tiles_per_frame = (H + p.TR - 1) / p.TR;
+  p.ns = ring_stages(p.a_bytes);
+  p.tiles_x = (W + p.PW - 1) / p.PW;
+  p.tiles_per_frame = ((H + p.TR - 1) / p.TR) * p.tiles_x;
   p.num_tiles = F * p.tiles_per_frame;
   p.Cin = Cin;
   p.nchunks = w1_chunks;
@@ -410,7 +435,7 @@ cudaError_t launch_dense_layer_fused(const __nv_bfloat16* blk, int blk_cstride, 
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(blk_cstride), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(F)};
   cuuint64_t gstride[3] = {static_cast<cuuint64_t>(blk_cstride) * 2, static_cast<cuuint64_t>(W) * blk_cstride * 2,
                            static_cast<cuuint64_t>(H) * W * blk_cstride * 2};
-  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.Wp), static_cast<cuuint32_t>(p.NY), 1};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.Wp), static_cast<cuuint32_t>(p.NY), 1};  // halo tile: (PW+2) x (TR+2) pixels
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(blk), gdim, gstride, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
