@@ -28,10 +28,10 @@ sys.path.insert(0, ROOT)
 CLIPS_PER_GPU, T, SIZE, CLASSES, HIDDEN = 64, 32, 224, 11, 128
 ARCH = "densenet121"
 FLOP_PER_FRAME = 5.666e9  # conv layers of DenseNet-121 @224^2, SURVEY.md §8d / BASELINE.md §3
-# DRAM bytes (read + write) of the conv-kernel family for ONE 2048-frame step, summed from the ncu launch list of this
-# very command (profiles/r1_launches_final.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch; the stem kernel,
-# outside that capture window, is added from its own capture): 85.8 GB + 2.9 GB.
-CONV_DRAM_BYTES_PER_STEP = 88.7e9
+# DRAM bytes (read + write) of the conv-kernel family (1x1 GEMMs, 3x3 halo kernel, stem, transition GEMMs) for ONE 2048-frame
+# step, summed from the ncu launch list of the same forward (profiles/r1_launches_final2.csv, summarised by
+# tools/launch_summary.py: dram__bytes_read.sum + dram__bytes_write.sum per launch).
+CONV_DRAM_BYTES_PER_STEP = 83.1e9
 WORKLOAD = "configs[1]: CNN+GRU event detector fwd, %d clips x %d frames @%dx%d per GPU" % (CLIPS_PER_GPU, T, SIZE, SIZE)
 
 
@@ -317,8 +317,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": CONV_DRAM_BYTES_PER_STEP,
                          "traffic_note": "bytes per step (all conv-kernel launches of one step, like `achieved`), ncu capture "
-                                         "profiles/r1_launches_final.csv; algorithmic minimum with dense-layer fusion 24.3 MB/frame "
-                                         "= 49.8 GB/step, so the unfused layer-by-layer schedule moves 1.8x that",
+                                         "profiles/r1_launches_final2.csv; algorithmic minimum with dense-layer fusion 24.3 MB/frame "
+                                         "= 49.8 GB/step, so the unfused layer-by-layer schedule moves 1.7x that",
                          "hbm_view": {"achieved_gbs": CONV_DRAM_BYTES_PER_STEP * args.steps / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0,
                                       "peak_gbs": peaks.get("hbm_gbs")},
                          "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), %d launches/step, %.2f ms/step summed over "
@@ -328,11 +328,13 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic": "5.666 GFLOP/frame x %d frames/step" % (B * T)},
             "cpu_baseline": {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"], "kind": "port",
                              "sample": "%d x 1 clip (32 frames) through the torch-fp32 CPU oracle of the same model" % cpu["steps"]},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "pinned host fp32 clips (the reference's tensor format) -> chunked H2D/compute pipeline -> logits.cpu()",
-                    "chunk_plan": plan_f32},
-            "e2e_pipelined": {"value": e2e_pipelined_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                              "path": "same fp32 host clips through HostPipeline.submit()/result() with one step kept in flight"},
+            "e2e": {"value": e2e_pipelined_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "pinned host fp32 clips (the reference's tensor format) -> HostPipeline.submit()/result(): every step's "
+                            "H2D copy, forward and logits D2H are inside the timed region, one step is kept in flight (the copy "
+                            "of step s+1 runs under the kernels of step s)"},
+            "e2e_serial": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                           "path": "same clips, one blocking call per step (chunked H2D/compute overlap inside the call only)",
+                           "chunk_plan": plan_f32},
             "e2e_u8": {"value": e2e_u8_value, "unit": "frames/s", "h2d_bytes_per_step": clips_u8.numel(), "d2h_bytes_per_step": d2h,
                        "path": "pinned host uint8 NHWC frames (decoder output), ToTensor+Normalize on the device"},
             "gpu_launches": int(prof["conv_launches"] + prof["other_launches"]),
