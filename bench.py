@@ -346,6 +346,10 @@ def run_ours(args, rank, world, local_rank):
             except Exception as exc:
                 line["gru_head"] = {"error": repr(exc)}
             try:
+                line["training"] = bench_training(device)
+            except Exception as exc:
+                line["training"] = {"error": repr(exc)}
+            try:
                 line["captioner"] = bench_captioner(device)
             except Exception as exc:  # the headline metric must still be reported
                 line["captioner"] = {"error": repr(exc)}
@@ -422,6 +426,105 @@ def bench_captioner(device, steps=3):
             "cpu_baseline": {"value": float((v_ref[:, 0] - 2).clamp(min=0).sum()) / dt_cpu, "unit": "tokens/s",
                              "cores": torch.get_num_threads(), "kind": "port", "sample": "%d of the 32 sources" % nb},
             "token_ids_equal_to_oracle_on_sample": bool(same)}
+
+
+def bench_training(device, steps=4):
+    """Training rows of SURVEY.md 8a, timed as the scripts run them (one optimiser step = forward with saved activations,
+    loss, backward, update), beside the CPU oracle + torch.autograd on a bounded sample:
+      head      : CNNRNN(None, 11, 'gru') on pre-extracted features, 256 clips x 32 x 1024 (train.py:404-424, the 0042 setting)
+      captioner : NMTModel LSTM H=128 on B=128 sources of <=224 x 1024-d features, targets <= 30 tokens, Adam (train_gnmt.py:330-337)
+    """
+    import torch
+    from oracle import captioning as C
+    from oracle import vision as O
+    from tennis_b200 import autograd
+    from tennis_b200.gluon import (Dropout, Embedding, HybridSequential, MaskedSoftmaxCELoss, SoftmaxCrossEntropyLoss,
+                                   Trainer)
+    from tennis_b200.models.captioning.gnmt import NMTModel, get_gnmt_encoder_decoder
+    from tennis_b200.models.vision.definitions import CNNRNN
+    from tennis_b200.vocab import Vocab, count_tokens
+    out = {}
+    # ---- temporal head on features
+    B, Tn, D, H = 256, 32, 1024, HIDDEN
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn(B, Tn, D, generator=g).relu().to(device)
+    labels = torch.randint(0, CLASSES, (B,), generator=g).to(device)
+    head = CNNRNN(None, CLASSES, hidden_size=H, type="gru")
+    head.initialize(ctx=device)
+    for k, v in O.synthetic_rnn_params("gru", D, H, seed=4321).items():
+        prm = head.rnn._reg_params[k]
+        prm.shape, prm._data = tuple(v.shape), v.to(device)
+        prm._version += 1
+    head(feats)  # materialise the deferred classifier shape
+    loss_fn = SoftmaxCrossEntropyLoss()
+    tr = Trainer(head.collect_params(), 'sgd', {'learning_rate': 1e-3, 'momentum': 0.9, 'wd': 1e-4})
+
+    def head_step():
+        with autograd.record():
+            loss = loss_fn(head(feats), labels)
+        autograd.backward([loss])
+        tr.step(B)
+        return loss
+    for _ in range(2):
+        head_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = head_step()
+    lh = float(loss.cpu().numpy().mean())
+    dt = (time.perf_counter() - t0) / steps
+    out["head"] = {"workload": "BiGRU(128)+max+Dense(11) training step on (256,32,1024) features, SGD momentum",
+                   "ms_per_step": dt * 1e3, "clips_per_s": B / dt, "frames_per_s": B * Tn / dt, "loss_finite": lh == lh}
+    # ---- captioner
+    Bc, Ts, Dc, Hc, E, V, Tt = 128, 224, 1024, 128, 100, 254, 30
+    p = C.synthetic_gnmt_params(seed=10000, scale=0.1, cell="lstm", H=Hc, D_src=Dc, E=E, V=V)
+    vocab = Vocab(count_tokens(["w%03d" % i for i in range(V - 4)]))
+    src_embed = HybridSequential()
+    src_embed.add(Dropout(0.0))
+    enc, dec = get_gnmt_encoder_decoder(cell_type="lstm", hidden_size=Hc, dropout=0.2, num_layers=2, num_bi_layers=1)
+    model = NMTModel(src_vocab=None, tgt_vocab=vocab, encoder=enc, decoder=dec, embed_size=E, prefix="gnmt_",
+                     src_embed=src_embed, tgt_embed=Embedding(V, E))
+    params = model.collect_params()
+    for k, v in p.items():
+        params[k].shape, params[k]._data = tuple(v.shape), v.clone().to(device)
+        params[k]._version += 1
+    x, vl = C.synthetic_sources(Bc, Ts, Dc, seed=100, min_len=64)
+    tgt = torch.randint(4, V, (Bc, Tt), generator=g).float()
+    tvl = torch.randint(6, Tt + 1, (Bc,), generator=g).float()
+    tvl[0] = Tt
+    xs, vls, ts, tvls = x.to(device), vl.to(device), tgt.to(device), tvl.to(device)
+    scale = float((Tt - 1) / (tvl - 1).mean())
+    mce = MaskedSoftmaxCELoss()
+    trc = Trainer(model.collect_params(), 'adam', {'learning_rate': 1e-3})
+
+    def cap_step():
+        with autograd.record():
+            o, _ = model(xs, ts[:, :-1], vls, tvls - 1)
+            lv = mce(o, ts[:, 1:], tvls - 1)
+        autograd.backward([lv], [torch.full_like(lv, scale / Bc)])
+        trc.step(1)
+        return lv
+    cap_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lv = cap_step()
+    lc = float(lv.cpu().numpy().mean()) * scale
+    dt = (time.perf_counter() - t0) / steps
+    words = float(vl.sum() + (tvl - 1).sum())  # the reference's "wps" numerator (train_gnmt.py:339-340)
+    # CPU port: oracle forward + torch.autograd on 8 sentences
+    nb = 8
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    t1 = time.perf_counter()
+    o = C.nmt_forward(q, x[:nb], tgt[:nb, :-1], vl[:nb], tvl[:nb] - 1, cell="lstm", H=Hc)
+    (C.masked_softmax_ce(o, tgt[:nb, 1:], tvl[:nb] - 1).mean() * scale).backward()
+    dt_cpu = time.perf_counter() - t1
+    words_cpu = float(vl[:nb].sum() + (tvl[:nb] - 1).sum())
+    out["captioner"] = {"workload": "GNMT LSTM H=128 training step: B=128, T_src<=224 x 1024-d, T_tgt<=30, V=254, dropout 0.2, Adam",
+                        "ms_per_step": dt * 1e3, "words_per_s": words / dt, "loss": lc,
+                        "cpu_baseline": {"value": words_cpu / dt_cpu, "unit": "words/s", "cores": torch.get_num_threads(),
+                                         "kind": "port", "sample": "forward + autograd backward of %d of the 128 sentences" % nb}}
+    return out
 
 
 def bench_gru_head(model, device, iters=20):

@@ -114,6 +114,10 @@ void tn_birnn_destroy(tn_birnn_t* r);
 /* on=1: compute the input projection in split-bf16 (x = hi + lo, three tensor-core products): ~fp32-accurate gates for the
  * captioner's encoder, where token ids must match; default 0 (plain bf16 operands, fp32 accumulate). */
 int tn_birnn_set_precise(tn_birnn_t* r, int on);
+/* Training: refresh the handle's packed copies from the (updated) fp32 parameters ON THE DEVICE, asynchronously on `stream`
+ * (same four arrays as tn_birnn_create, but device pointers) -- what gluon.Trainer.step leaves behind at train.py:424. */
+int tn_birnn_update_weights(tn_birnn_t* r, const float* const* i2h_weight, const float* const* h2h_weight,
+                            const float* const* i2h_bias, const float* const* h2h_bias, tn_stream_t stream);
 size_t tn_birnn_workspace_bytes(const tn_birnn_t* r, int B, int T);
 /* x: device (B,T,D) fp32, or bf16 when x_is_bf16; valid_len: device int32 (B) or NULL;
  * y (B,T,ndir*H) / ymax (B,ndir*H) / h_final, c_final (ndir,B,H): device fp32, each may be NULL. */

@@ -52,6 +52,8 @@ SIGNATURES = {
                                 POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
     "tn_birnn_destroy": (None, [c_void_p]),
     "tn_birnn_set_precise": (c_int, [c_void_p, c_int]),
+    "tn_birnn_update_weights": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                        c_void_p]),
     "tn_birnn_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "tn_birnn_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -113,6 +113,68 @@ int tn_birnn_set_precise(tn_birnn_t* r, int on) {
   return TN_OK;
 }
 
+
+}  // extern "C"
+
+namespace {
+// Device-side re-pack of the layer's weights (training: the optimiser updates the fp32 parameters every step; rebuilding
+// the handle through the host cost ~50 ms per step).  Same shared-memory image as tn::make_conv (K-major, 128-byte swizzle).
+__device__ __forceinline__ size_t wpack_offset(int co, int ci, int BN, int nchunks) {
+  const int t = co / BN, n = co - t * BN, c = ci >> 6, kk = ci & 63;
+  return (static_cast<size_t>(t) * nchunks + c) * BN * 128 + static_cast<size_t>(n) * 128 + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
+}
+__global__ void birnn_repack_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int GH, int D, int ndir,
+                                    uint8_t* __restrict__ proj, int bn1, int nch1, uint8_t* __restrict__ proj3, int bn3, int nch3) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(ndir) * GH * D) return;
+  const int co = static_cast<int>(idx / D), ci = static_cast<int>(idx - static_cast<size_t>(co) * D);
+  const int d = co / GH;
+  const float w = (d == 0 ? w0 : w1)[static_cast<size_t>(co - d * GH) * D + ci];
+  const __nv_bfloat16 hi = __float2bfloat16(w);
+  const __nv_bfloat16 lo = __float2bfloat16(w - __bfloat162float(hi));
+  *reinterpret_cast<__nv_bfloat16*>(proj + wpack_offset(co, ci, bn1, nch1)) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(proj3 + wpack_offset(co, ci, bn3, nch3)) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(proj3 + wpack_offset(co, D + ci, bn3, nch3)) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(proj3 + wpack_offset(co, 2 * D + ci, bn3, nch3)) = lo;
+}
+__global__ void birnn_small_update_kernel(const float* __restrict__ whh0, const float* __restrict__ whh1, const float* __restrict__ bi0,
+                                          const float* __restrict__ bi1, const float* __restrict__ bh0, const float* __restrict__ bh1,
+                                          int GH, int H, int ndir, float* __restrict__ WhhT, float* __restrict__ bih,
+                                          float* __restrict__ bhh) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(ndir) * GH * H) return;
+  const int d = static_cast<int>(idx / (static_cast<size_t>(GH) * H));
+  const int rem = static_cast<int>(idx - static_cast<size_t>(d) * GH * H);
+  const int j = rem / H, k = rem - j * H;
+  WhhT[(static_cast<size_t>(d) * H + k) * GH + j] = (d == 0 ? whh0 : whh1)[rem];
+  if (k == 0) {
+    bih[d * GH + j] = (d == 0 ? bi0 : bi1)[j];
+    bhh[d * GH + j] = (d == 0 ? bh0 : bh1)[j];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int tn_birnn_update_weights(tn_birnn_t* r, const float* const* i2h_weight, const float* const* h2h_weight,
+                            const float* const* i2h_bias, const float* const* h2h_bias, tn_stream_t stream) {
+  if (!r || !i2h_weight || !h2h_weight || !i2h_bias || !h2h_bias) return tn::set_error(TN_ERR_INVALID, "null argument");
+  for (int d = 0; d < r->ndir; ++d)
+    if (!i2h_weight[d] || !h2h_weight[d] || !i2h_bias[d] || !h2h_bias[d]) return tn::set_error(TN_ERR_INVALID, "null device weight");
+  const int GH = r->gates * r->H, D = r->D, H = r->H, nd = r->ndir;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n1 = static_cast<size_t>(nd) * GH * D, n2 = static_cast<size_t>(nd) * GH * H;
+  birnn_repack_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, st>>>(
+      i2h_weight[0], nd > 1 ? i2h_weight[1] : nullptr, GH, D, nd, const_cast<uint8_t*>(r->proj.wpack),
+      tn::conv_gemm_pick_bn(r->proj.Cout), r->proj.num_chunks, const_cast<uint8_t*>(r->proj3.wpack),
+      tn::conv_gemm_pick_bn(r->proj3.Cout), r->proj3.num_chunks);
+  birnn_small_update_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(
+      h2h_weight[0], nd > 1 ? h2h_weight[1] : nullptr, i2h_bias[0], nd > 1 ? i2h_bias[1] : nullptr, h2h_bias[0],
+      nd > 1 ? h2h_bias[1] : nullptr, GH, H, nd, const_cast<float*>(r->WhhT), const_cast<float*>(r->bih), const_cast<float*>(r->bhh));
+  TN_CUDA(cudaGetLastError());
+  return TN_OK;
+}
+
 size_t tn_birnn_workspace_bytes(const tn_birnn_t* r, int B, int T) {
   if (!r || B < 0 || T < 0) return 0;
   const size_t M = static_cast<size_t>(B) * T;

@@ -4,7 +4,7 @@
 //
 //   rnn_bwd_kernel   reverse scan.  Per step: recompute hh = W_hh h_{t-1} + b_hh (coalesced reads of W_hh^T), gate
 //                    derivatives, write d(gx) and d(hh) pre-activation gradients, dh_{t-1} = z*dh + W_hh^T-contract.
-//   gemm_tn_kernel   dW = A^T B over the (b,t) rows: dW_ih = dgx^T X, dW_hh = dhh^T H_prev.
+//   gemm_tn          dW = A^T B over the (b,t) rows (shared fp32 SGEMM): dW_ih = dgx^T X, dW_hh = dhh^T H_prev.
 #include <math.h>
 #include <string.h>
 
@@ -167,41 +167,22 @@ __global__ void __launch_bounds__(512) rnn_bwd_kernel(const RnnBwdParams p) {
   }
 }
 
-// C[n1][n2] (+)= sum_m A[m*lda + a_off + n1] * B[m*ldb + b_off + n2]   (A^T B), 32x32 tiles
-__global__ void __launch_bounds__(256) gemm_tn_kernel(const float* __restrict__ A, int lda, int a_off, const float* __restrict__ Bm,
-                                                      int ldb, int b_off, float* __restrict__ C, int ldc, int M, int N1, int N2) {
-  __shared__ float sa[32][33], sb[32][33];
-  const int n1_0 = blockIdx.y * 32, n2_0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of threads
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int m0 = 0; m0 < M; m0 += 32) {
-    for (int r = ty; r < 32; r += 8) {
-      const int m = m0 + r;
-      sa[r][tx] = (m < M && n1_0 + tx < N1) ? A[static_cast<size_t>(m) * lda + a_off + n1_0 + tx] : 0.f;
-      sb[r][tx] = (m < M && n2_0 + tx < N2) ? Bm[static_cast<size_t>(m) * ldb + b_off + n2_0 + tx] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const float bv = sb[r][tx];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(sa[r][ty + 8 * i], bv, acc[i]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n1 = n1_0 + ty + 8 * i, n2 = n2_0 + tx;
-    if (n1 < N1 && n2 < N2) C[static_cast<size_t>(n1) * ldc + n2] = acc[i];
-  }
-}
-
-__global__ void colsum_kernel(const float* __restrict__ A, int lda, int off, float* __restrict__ out, int M, int N) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
+// out[j] = sum_m A[m*lda + off + j]: one block per 32 columns, 8 row lanes, shared-memory reduction
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, int lda, int off, float* __restrict__ out, int M, int N) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   float acc = 0.f;
-  for (int m = 0; m < M; ++m) acc += A[static_cast<size_t>(m) * lda + off + j];
-  out[j] = acc;
+  if (j < N)
+    for (int m = ty; m < M; m += 8) acc += A[static_cast<size_t>(m) * lda + off + j];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][tx];
+    out[j] = s;
+  }
 }
 
 __global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, size_t n) {
@@ -300,12 +281,10 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
-cudaError_t gemm_tn(const float* A, int lda, int a_off, const float* Bm, int ldb, int b_off, float* C, int ldc, int M, int N1,
-                    int N2, cudaStream_t st) {
-  dim3 grid((N2 + 31) / 32, (N1 + 31) / 32);
-  ProfScope ps(kProfOther, st);
-  gemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, a_off, Bm, ldb, b_off, C, ldc, M, N1, N2);
-  return cudaGetLastError();
+// C (N1 x N2) = A[:, a_off : a_off+N1]^T  B[:, b_off : b_off+N2]  over M rows: the shared fp32 SGEMM (tn_seq_train.cu)
+int gemm_tn(const float* A, int lda, int a_off, const float* Bm, int ldb, int b_off, float* C, int ldc, int M, int N1, int N2,
+            cudaStream_t st) {
+  return tn_sgemm(1, 0, N1, N2, M, 1.0f, A + a_off, lda, Bm + b_off, ldb, 0.0f, C, ldc, st);
 }
 
 }  // namespace
@@ -401,11 +380,13 @@ int tn_birnn_backward(tn_birnn_t* r, const void* x, int x_is_bf16, int B, int T,
   }
   TN_CUDA(cudaGetLastError());
   for (int d = 0; d < ndir; ++d) {
-    TN_CUDA(gemm_tn(dgx, ndir * GH, d * GH, xin, D, 0, dW_ih + static_cast<size_t>(d) * GH * D, D, static_cast<int>(M), GH, D, st));
-    TN_CUDA(gemm_tn(dhh, ndir * GH, d * GH, hprev, ndir * H, d * H, dW_hh + static_cast<size_t>(d) * GH * H, H, static_cast<int>(M), GH, H, st));
+    int rc = gemm_tn(dgx, ndir * GH, d * GH, xin, D, 0, dW_ih + static_cast<size_t>(d) * GH * D, D, static_cast<int>(M), GH, D, st);
+    if (rc != TN_OK) return rc;
+    rc = gemm_tn(dhh, ndir * GH, d * GH, hprev, ndir * H, d * H, dW_hh + static_cast<size_t>(d) * GH * H, H, static_cast<int>(M), GH, H, st);
+    if (rc != TN_OK) return rc;
   }
-  colsum_kernel<<<(ndir * GH + 127) / 128, 128, 0, st>>>(dgx, ndir * GH, 0, db_ih, static_cast<int>(M), ndir * GH);
-  colsum_kernel<<<(ndir * GH + 127) / 128, 128, 0, st>>>(dhh, ndir * GH, 0, db_hh, static_cast<int>(M), ndir * GH);
+  colsum_kernel<<<(ndir * GH + 31) / 32, 256, 0, st>>>(dgx, ndir * GH, 0, db_ih, static_cast<int>(M), ndir * GH);
+  colsum_kernel<<<(ndir * GH + 31) / 32, 256, 0, st>>>(dhh, ndir * GH, 0, db_hh, static_cast<int>(M), ndir * GH);
   TN_CUDA(cudaGetLastError());
   return TN_OK;
 }

@@ -177,8 +177,8 @@ class BiRNN:
         self._h = c_void_p()
         check(lib().tn_birnn_create(ctypes.byref(self._h), device, _lib.CELL_GRU if cell == "gru" else _lib.CELL_LSTM, D,
                                     H, self.ndir, arrs[0], arrs[1], arrs[2], arrs[3]))
-        if precise:
-            check(lib().tn_birnn_set_precise(self._h, 1))
+        self._precise = False
+        self.set_precise(precise)
         self._ws = None
         self._ws_bytes = 0
 
@@ -189,6 +189,26 @@ class BiRNN:
                 self._h = c_void_p()
         except Exception:  # interpreter shutdown
             pass
+
+    def set_precise(self, on):
+        if bool(on) != getattr(self, "_precise", False):
+            check(lib().tn_birnn_set_precise(self._h, int(bool(on))))
+            self._precise = bool(on)
+
+    def update_weights(self, params):
+        """Refresh the packed weights from fp32 CUDA tensors (same keys as the constructor) without leaving the device."""
+        dirs = ["l0", "r0"][: self.ndir]
+        arrs, keep = [], []
+        for suffix in ("_i2h_weight", "_h2h_weight", "_i2h_bias", "_h2h_bias"):
+            arr = (c_void_p * 2)()
+            for i, d in enumerate(dirs):
+                t = params[d + suffix]
+                _require_cuda(t)
+                t = t.contiguous().float()
+                keep.append(t)
+                arr[i] = t.data_ptr()
+            arrs.append(arr)
+        check(lib().tn_birnn_update_weights(self._h, arrs[0], arrs[1], arrs[2], arrs[3], stream_ptr()))
 
     def __call__(self, x, valid_len=None, want_y=True, want_max=False, want_state=False):
         """x: (B,T,D) fp32 or bf16 cuda.  Returns dict(y, ymax, h, c) with the requested entries."""

@@ -27,12 +27,20 @@ class _RNNLayer(Block):
             if p._data is None and n.endswith('_i2h_weight'):
                 p._finish_deferred((self._gates * self._hidden_size, D))
                 p.reset_ctx(x.device)
-        key = (x.device.index or 0, precise) + tuple(p._version for p in self._reg_params.values())
-        if self._engine is None or self._engine_key != key:
-            params = {n: p.data() for n, p in self._reg_params.items()}
-            self._engine = ops.BiRNN(self._cell, D, self._hidden_size, params, self._bidirectional, device=x.device.index or 0,
-                                     precise=precise)
-            self._engine_key = key
+        static = (x.device.index or 0, D)
+        versions = tuple(p._version for p in self._reg_params.values())
+        params = {n: p.data() for n, p in self._reg_params.items()}
+        if self._engine is None or self._engine_key[0] != static:
+            self._engine = ops.BiRNN(self._cell, D, self._hidden_size, params, self._bidirectional, device=x.device.index or 0)
+            self._engine_key = (static, versions)
+        elif self._engine_key[1] != versions:
+            # parameters changed (Trainer.step, set_data, load_parameters): re-pack on the device instead of rebuilding
+            if all(t.is_cuda for t in params.values()):
+                self._engine.update_weights(params)
+            else:
+                self._engine = ops.BiRNN(self._cell, D, self._hidden_size, params, self._bidirectional, device=x.device.index or 0)
+            self._engine_key = (static, versions)
+        self._engine.set_precise(precise)
         return self._engine
 
     @staticmethod
