@@ -206,6 +206,14 @@ int tn_rnn_cell_backward(int cell, int B, int H, int t, const int32_t* valid_len
                          long long cc_stride, const float* dy, long long dy_stride, const float* dy2, long long dy2_stride,
                          const float* dh_last, const float* dc_last, float* dh, float* dc, float* dgi, long long dgi_stride,
                          float* dgh, long long dgh_stride, tn_stream_t stream);
+/* Whole-sequence drivers of the two calls above (the per-step loop of cell.unroll, gnmt.py:143-145, in C instead of Python).
+ * GI (B,T,G*H) = X W_i2h^T; Hb / Cb (B,T+1,H): slot 0 = initial state, slot t+1 = state after step t; S (B,T,4H); scratch (B,G*H).
+ * Backward: dh / dc zero-initialised, on return the gradients w.r.t. the initial state; DGH = DGI for LSTM; dWh accumulated. */
+int tn_rnn_unroll_forward(int cell, int B, int T, int H, const float* GI, const float* Wh, const float* bi, const float* bh,
+                          float* Hb, float* Cb, float* S, float* scratch, tn_stream_t stream);
+int tn_rnn_unroll_backward(int cell, int B, int T, int H, const int32_t* valid_len, const float* S, const float* Hb, const float* Cb,
+                           const float* Wh, const float* dY, const float* dh_last, const float* dc_last, float* dh, float* dc,
+                           float* DGI, float* DGH, float* dWh, tn_stream_t stream);
 /* q (B,H) = projected query; w (B,T) = softmax((q/sqrt(H)) mem^T masked by src_len) * mask; ctx = w mem, written to one or two
  * strided destinations.  Backward accumulates into dmem (B,T,H) and writes dq. */
 int tn_attention_forward(const float* q, long long q_stride, const float* mem, const int32_t* src_len, int B, int T, int H,

@@ -148,6 +148,10 @@ SIGNATURES.update({
     "tn_rnn_cell_backward": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, _LL, c_void_p, _LL, c_void_p, _LL, c_void_p,
                                      _LL, c_void_p, _LL, c_void_p, _LL, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _LL,
                                      c_void_p, _LL, c_void_p]),
+    "tn_rnn_unroll_forward": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "tn_rnn_unroll_backward": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tn_attention_forward": (c_int, [c_void_p, _LL, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, _LL, c_void_p,
                                      _LL, c_void_p]),
     "tn_attention_backward": (c_int, [c_void_p, _LL, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, _LL, c_void_p,

@@ -525,4 +525,55 @@ int tn_axpy(float* y, const float* x, float a, size_t n, tn_stream_t stream) {
   return TN_OK;
 }
 
+/* Whole-sequence drivers of the two calls above: the per-step loop of cell.unroll (gnmt.py:143-145) runs here instead of in
+ * Python, one h2h GEMM + one cell kernel per step on `stream`.  Layouts: GI (B,T,G*H) = X W_i2h^T; Hb / Cb (B,T+1,H) with
+ * slot 0 = initial state and slot t+1 = state after step t; S (B,T,4H) saved gate values; scratch (B,G*H). */
+int tn_rnn_unroll_forward(int cell, int B, int T, int H, const float* GI, const float* Wh, const float* bi, const float* bh,
+                          float* Hb, float* Cb, float* S, float* scratch, tn_stream_t stream) {
+  if (cell != TN_CELL_GRU && cell != TN_CELL_LSTM) return set_error(TN_ERR_INVALID, "unknown cell %d", cell);
+  if (B <= 0 || T <= 0 || H <= 0) return TN_OK;
+  if (!GI || !Wh || !bi || !bh || !Hb || !S || !scratch || (cell == TN_CELL_LSTM && !Cb)) return set_error(TN_ERR_INVALID, "null device pointer");
+  const int G = cell == TN_CELL_GRU ? 3 : 4;
+  const long long GH = static_cast<long long>(G) * H, hs = static_cast<long long>(T + 1) * H;
+  for (int t = 0; t < T; ++t) {
+    const float* hp = Hb + static_cast<size_t>(t) * H;
+    int rc = tn_sgemm(0, 1, B, static_cast<int>(GH), H, 1.f, hp, static_cast<int>(hs), Wh, H, 0.f, scratch, static_cast<int>(GH), stream);
+    if (rc != TN_OK) return rc;
+    rc = tn_rnn_cell_forward(cell, B, H, GI + static_cast<size_t>(t) * GH, T * GH, scratch, GH, bi, bh, hp, hs,
+                             Cb ? Cb + static_cast<size_t>(t) * H : nullptr, hs, Hb + static_cast<size_t>(t + 1) * H, hs, nullptr, 0,
+                             Cb ? Cb + static_cast<size_t>(t + 1) * H : nullptr, hs, S + static_cast<size_t>(t) * 4 * H,
+                             static_cast<long long>(T) * 4 * H, stream);
+    if (rc != TN_OK) return rc;
+  }
+  return TN_OK;
+}
+
+/* Reverse-time loop: dY (B,T,H) output gradients; dh / dc (B,H) zero-initialised running state gradients, on return the
+ * gradients w.r.t. the initial state; DGI (and DGH for GRU; pass DGI for LSTM) (B,T,G*H) gate gradients of every step;
+ * dWh (G*H,H) zero-initialised, accumulated. */
+int tn_rnn_unroll_backward(int cell, int B, int T, int H, const int32_t* valid_len, const float* S, const float* Hb, const float* Cb,
+                           const float* Wh, const float* dY, const float* dh_last, const float* dc_last, float* dh, float* dc,
+                           float* DGI, float* DGH, float* dWh, tn_stream_t stream) {
+  if (cell != TN_CELL_GRU && cell != TN_CELL_LSTM) return set_error(TN_ERR_INVALID, "unknown cell %d", cell);
+  if (B <= 0 || T <= 0 || H <= 0) return TN_OK;
+  if (!S || !Hb || !Wh || !dY || !dh || !DGI || !DGH || !dWh || (cell == TN_CELL_LSTM && (!Cb || !dc))) return set_error(TN_ERR_INVALID, "null device pointer");
+  const int G = cell == TN_CELL_GRU ? 3 : 4;
+  const long long GH = static_cast<long long>(G) * H, hs = static_cast<long long>(T + 1) * H;
+  for (int t = T - 1; t >= 0; --t) {
+    float* dgh = DGH + static_cast<size_t>(t) * GH;
+    int rc = tn_rnn_cell_backward(cell, B, H, t, valid_len, S + static_cast<size_t>(t) * 4 * H, static_cast<long long>(T) * 4 * H,
+                                  Hb + static_cast<size_t>(t) * H, hs, Cb ? Cb + static_cast<size_t>(t) * H : nullptr, hs,
+                                  Cb ? Cb + static_cast<size_t>(t + 1) * H : nullptr, hs, dY + static_cast<size_t>(t) * H,
+                                  static_cast<long long>(T) * H, nullptr, 0, dh_last, dc_last, dh, dc,
+                                  DGI + static_cast<size_t>(t) * GH, T * GH, cell == TN_CELL_GRU ? dgh : nullptr, T * GH, stream);
+    if (rc != TN_OK) return rc;
+    rc = tn_sgemm(0, 0, B, H, static_cast<int>(GH), 1.f, dgh, static_cast<int>(T * GH), Wh, H, 1.f, dh, H, stream);  // dh += dgh W_h2h
+    if (rc != TN_OK) return rc;
+    rc = tn_sgemm(1, 0, static_cast<int>(GH), H, B, 1.f, dgh, static_cast<int>(T * GH), Hb + static_cast<size_t>(t) * H,
+                  static_cast<int>(hs), 1.f, dWh, H, stream);  // dW_h2h += dgh^T h_{t-1}
+    if (rc != TN_OK) return rc;
+  }
+  return TN_OK;
+}
+
 }  // extern "C"

@@ -2,9 +2,9 @@
 NMTModel.forward = encode -> init_state_from_encoder -> decode_seq -> tgt_proj  (reference train_gnmt.py:330-334,
 models/captioning/gnmt.py:136-160,224-304,345-404; gluonnlp NMTModel / DotProductAttentionCell).
 
-Python only sequences kernels of libtennis_b200.so (csrc/tn_seq_train.cu: tn_sgemm, tn_rnn_cell_*, tn_attention_*,
-tn_embedding_backward, tn_mul_mask, tn_dropout_mask) step by step; torch tensors are the containers (allocation, views,
-gathers by index).  fp32 throughout, so the logits agree with the inference engines to ~1e-5 and the gradients with autograd
+Python only sequences entry points of libtennis_b200.so (csrc/tn_seq_train.cu: tn_sgemm, tn_rnn_unroll_forward/backward for
+whole-sequence cells, tn_rnn_cell_* + tn_attention_* for the attention-coupled decoder layer, tn_embedding_backward,
+tn_mul_mask, tn_dropout_mask); torch tensors are the containers (allocation, views, gathers by index).  fp32 throughout, so the logits agree with the inference engines to ~1e-5 and the gradients with autograd
 of the CPU oracle to ~1e-4 (tests/test_gpu_gnmt_train.py).
 
 Structure used for the backward pass: only decoder layer 0 is coupled to the attention (its input at step t carries the
@@ -118,10 +118,9 @@ class _Unroll(object):
             self.Cb[:, 0] = c0
         self.S = torch.empty(B, T, 4 * H, device=dev)
         gh = torch.empty(B, G * H, device=dev)
-        for t in range(T):
-            sgemm(self.Hb[:, t], self.Wh, gh, tb=True)
-            cell_forward(cell_type, self.GI[:, t], gh, self.bi, self.bh, self.Hb[:, t], None if self.Cb is None else self.Cb[:, t],
-                         self.Hb[:, t + 1], None, None if self.Cb is None else self.Cb[:, t + 1], self.S[:, t])
+        check(lib().tn_rnn_unroll_forward(_lib.CELL_GRU if cell_type == "gru" else _lib.CELL_LSTM, B, T, H, dptr(self.GI),
+                                          dptr(self.Wh), dptr(self.bi), dptr(self.bh), dptr(self.Hb), dptr(self.Cb), dptr(self.S),
+                                          dptr(gh), stream_ptr()))
 
     def outputs(self):
         """(B,T,H), zero past valid_length (SequenceMask inside unroll)."""
@@ -145,12 +144,9 @@ class _Unroll(object):
         DGI = torch.empty(B, T, G * H, device=dev)
         DGH = torch.empty(B, T, G * H, device=dev) if self.cell == "gru" else DGI
         dWh = torch.zeros_like(self.Wh)
-        for t in range(T - 1, -1, -1):
-            cell_backward(self.cell, t, self.lens, self.S[:, t], self.Hb[:, t], None if self.Cb is None else self.Cb[:, t],
-                          None if self.Cb is None else self.Cb[:, t + 1], dY[:, t], None, dh_last, dc_last, dh, dc, DGI[:, t],
-                          DGH[:, t] if self.cell == "gru" else None)
-            sgemm(DGH[:, t], self.Wh, dh, beta=1.0)
-            sgemm(DGH[:, t], self.Hb[:, t], dWh, ta=True, beta=1.0)
+        check(lib().tn_rnn_unroll_backward(_lib.CELL_GRU if self.cell == "gru" else _lib.CELL_LSTM, B, T, H, dptr(self.lens),
+                                           dptr(self.S), dptr(self.Hb), dptr(self.Cb), dptr(self.Wh), dptr(dY), dptr(dh_last),
+                                           dptr(dc_last), dptr(dh), dptr(dc), dptr(DGI), dptr(DGH), dptr(dWh), stream_ptr()))
         D = self.X.shape[2]
         X2, DGI2, DGH2 = self.X.reshape(B * T, D), DGI.reshape(B * T, G * H), DGH.reshape(B * T, G * H)
         ones = torch.ones(B * T, 1, device=dev)
