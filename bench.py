@@ -194,6 +194,9 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py --impl ours needs a CUDA device: tennis_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    from tennis_b200.parallel import bind_to_gpu_numa_node
+    full_affinity = os.sched_getaffinity(0)
+    numa_node = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: host clips live next to their GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.check(_lib.lib().tn_device_check(local_rank))
@@ -304,6 +307,7 @@ def run_ours(args, rank, world, local_rank):
         flops = FLOP_PER_FRAME * B * T * args.steps  # algorithmic conv FLOPs executed by this rank's conv-GEMM launches
         achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        os.sched_setaffinity(0, full_affinity)  # the CPU baseline gets every host core again
         cpu = time_cpu_port(budget_s=12.0, clips_per_step=1, warmup=1)
         line = {
             "metric": "frames/sec (224x224 CNN+GRU fwd)", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -313,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
                        "global_clips": B * world, "frames_per_step": B * T * world,
                        "parallelism": "frame-sharded dp%d, NCCL all-gather of features" % world,
                        "l2": "inputs %.2f GB per GPU per step > 126 MB L2, no flush needed" % (h2d / 1e9),
-                       "outputs_finite": finite},
+                       "outputs_finite": finite, "numa_node_of_rank0": numa_node},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": CONV_DRAM_BYTES_PER_STEP,
                          "traffic_note": "bytes per step (all conv-kernel launches of one step, like `achieved`), ncu capture "

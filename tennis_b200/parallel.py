@@ -10,6 +10,34 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated afterwards are
+    node-local and H2D copies do not cross the socket interconnect (one process per GPU: eight ranks otherwise share whatever
+    node the launcher started them on).  Best effort: returns the node id, or None when the topology cannot be read."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(int(device_index))  # CUDA ordinal (honours CUDA_VISIBLE_DEVICES)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # no sysfs topology (containers) or no PCI ids: leave the affinity alone
+        return None
+
+
 def shard_range(n_items, rank, world):
     """Contiguous shard [lo, hi) of `n_items` for `rank`; the last rank takes the remainder
     (mirrors gluon.utils.split_and_load(even_split=False))."""
