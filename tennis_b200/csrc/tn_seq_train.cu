@@ -26,24 +26,40 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int tx = tid & 15, ty = tid >> 4;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = tid; i < 16 * 64; i += 256) {
+  // The next K tile is fetched into registers while the current one is multiplied: the per-step GEMMs of the recurrences run
+  // on a handful of CTAs, where an unprefetched loop pays the full global-load latency every 16 columns of K.
+  // split-K (gridDim.z > 1, beta == 1 only): this CTA reduces K range [kbeg, kend) and adds its partial sum atomically
+  const int kchunk = ((K + static_cast<int>(gridDim.z) - 1) / static_cast<int>(gridDim.z) + 15) / 16 * 16;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  if (kbeg >= kend) return;
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = tid + q * 256;
       int k, m;
       if (TA) { k = i >> 6; m = i & 63; } else { m = i >> 4; k = i & 15; }
-      const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[static_cast<size_t>(gk) * lda + gm] : A[static_cast<size_t>(gm) * lda + gk];
-      As[k][m] = v;
-    }
-    for (int i = tid; i < 16 * 64; i += 256) {
-      int k, n;
+      const int gm = m0 + m;
+      int gk = k0 + k;
+      ra[q] = (gm < M && gk < kend) ? (TA ? A[static_cast<size_t>(gk) * lda + gm] : A[static_cast<size_t>(gm) * lda + gk]) : 0.f;
+      int n;
       if (TB) { n = i >> 4; k = i & 15; } else { k = i >> 6; n = i & 63; }
-      const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < N && gk < K) v = TB ? B[static_cast<size_t>(gn) * ldb + gk] : B[static_cast<size_t>(gk) * ldb + gn];
-      Bs[k][n] = v;
+      const int gn = n0 + n;
+      gk = k0 + k;
+      rb[q] = (gn < N && gk < kend) ? (TB ? B[static_cast<size_t>(gn) * ldb + gk] : B[static_cast<size_t>(gk) * ldb + gn]) : 0.f;
+    }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = tid + q * 256;
+      if (TA) As[i >> 6][i & 63] = ra[q]; else As[i & 15][i >> 4] = ra[q];
+      if (TB) Bs[i & 15][i >> 4] = rb[q]; else Bs[i >> 6][i & 63] = rb[q];
     }
     __syncthreads();
+    if (k0 + 16 < kend) fetch(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       float a[4], b[4];
@@ -67,7 +83,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float* c = C + static_cast<size_t>(gm) * ldc + gn;
-      *c = (beta == 0.f) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * *c;
+      if (gridDim.z > 1) atomicAdd(c, alpha * acc[i][j]);
+      else *c = (beta == 0.f) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * *c;
     }
   }
 }
@@ -404,6 +421,13 @@ int tn_sgemm(int transA, int transB, int M, int N, int K, float alpha, const flo
   if (!A || !B || !C) return set_error(TN_ERR_INVALID, "null device pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((N + 63) / 64, (M + 63) / 64);
+  // accumulating GEMMs with few output tiles and a long K (dh += dgh W_h2h, dW_h2h += dgh^T h, every step of a BPTT loop):
+  // split K across CTAs so that more than a handful of SMs work on them
+  if (beta == 1.f && grid.x * grid.y < 32 && K >= 256) {
+    int splits = 64 / static_cast<int>(grid.x * grid.y);
+    if (splits > K / 64) splits = K / 64;
+    if (splits > 1) grid.z = splits;
+  }
   ProfScope prof_scope(kProfOther, st);
   if (!transA && !transB) sgemm_kernel<0, 0><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   else if (!transA && transB) sgemm_kernel<0, 1><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
