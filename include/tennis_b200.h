@@ -132,6 +132,8 @@ int tn_birnn_forward(tn_birnn_t* r, const void* x, int x_is_bf16, const int32_t*
  * optimiser updates of gluon.Trainer.step (train.py:298-299,424; train_gnmt.py:310,337).  The CNN backward is not built. */
 int tn_birnn_forward_train(tn_birnn_t* r, const void* x, int x_is_bf16, int B, int T, float* y, float* ymax, float* gx,
                            float* cseq, void* workspace, size_t workspace_bytes, tn_stream_t stream);
+/* On return the first B*T*ndir*G*H floats of `workspace` hold d(loss)/d(x W_i2h^T) for every (b,t) and direction: a caller that
+ * trains the CNN end to end multiplies them by W_i2h (tn_sgemm) to get the gradient w.r.t. the features. */
 size_t tn_birnn_backward_workspace_bytes(const tn_birnn_t* r, int B, int T);
 int tn_birnn_backward(tn_birnn_t* r, const void* x, int x_is_bf16, int B, int T, const float* gx, const float* y,
                       const float* cseq, const float* ymax, const float* d_ymax, const float* dy, float* dW_ih, float* dW_hh,
@@ -233,6 +235,31 @@ int tn_masked_softmax_ce_grad(const float* pred, const float* label, const float
 int tn_dropout_mask(float* mask, size_t n, float p, unsigned long long seed, tn_stream_t stream);
 int tn_mul_mask(const float* x, const float* mask, const int32_t* seq_len, float* y, int B, int T, int C, tn_stream_t stream);
 int tn_axpy(float* y, const float* x, float a, size_t n, tn_stream_t stream);
+
+/* ------------------------------------------------------------------ CNN training (V7 with a trainable backbone)
+ * `with ag.record(): out = net(x); ...; ag.backward(losses)` (train.py:415-421) through gluoncv DenseNet-121 / ResNet-18 v2:
+ * training-mode BatchNorm (batch statistics, biased variance, running = momentum*running + (1-momentum)*batch)
+ * fused with ReLU, convolutions as im2col + tn_sgemm, max / average pooling, each with its backward.  fp32 NHWC: a row is a
+ * pixel, `ld*` is the channel count of the buffer (DenseNet's concat stays a channel offset).  First correct path (SIMT);
+ * sequenced by tennis_b200/models/vision/train_graph.py. */
+int tn_im2col_nhwc(const float* x, long long ldx, int N, int H, int W, int C, int R, int S, int stride, int pad, float* col,
+                   tn_stream_t stream);
+int tn_col2im_nhwc(const float* dcol, int N, int H, int W, int C, int R, int S, int stride, int pad, float* dx, long long lddx,
+                   tn_stream_t stream); /* dx += scatter(dcol) */
+int tn_bn_train_forward(const float* x, long long ldx, long long M, int C, const float* gamma, const float* beta, float eps,
+                        float momentum, float* running_mean, float* running_var, int relu, float* mean, float* var, float* y,
+                        long long ldy, tn_stream_t stream);
+int tn_bn_train_backward(const float* x, long long ldx, const float* y, long long ldy, const float* dy, long long lddy, long long M,
+                         int C, const float* mean, const float* var, const float* gamma, float eps, int relu, float* dgamma,
+                         float* dbeta, float* dx, long long lddx, int accumulate, tn_stream_t stream);
+int tn_maxpool_nhwc_forward(const float* x, long long ldx, int N, int H, int W, int C, int k, int stride, int pad, float* y,
+                            long long ldy, int32_t* idx, tn_stream_t stream);
+int tn_maxpool_nhwc_backward(const float* dy, long long lddy, const int32_t* idx, long long rows, int C, float* dx, long long lddx,
+                             tn_stream_t stream); /* dx += */
+int tn_avgpool_nhwc_forward(const float* x, long long ldx, int N, int H, int W, int C, int kh, int kw, float* y, long long ldy,
+                            tn_stream_t stream); /* window = stride = (kh,kw), floor */
+int tn_avgpool_nhwc_backward(const float* dy, long long lddy, int N, int H, int W, int C, int kh, int kw, float* dx, long long lddx,
+                             int accumulate, tn_stream_t stream);
 
 #ifdef __cplusplus
 }

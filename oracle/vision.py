@@ -96,10 +96,35 @@ def flatten_params(arch, params):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+_BN_TRAINING = [False]  # set by the `training=` argument of the feature functions below
+
+
 def _bn(x, p, prefix):
+    if _BN_TRAINING[0]:
+        # training mode (under autograd.record()): normalise with the batch statistics (biased variance); the running estimates
+        # are updated as running = 0.9 * running + 0.1 * batch with the BIASED batch variance (MXNet)
+        if p.get("_update_running", False):
+            with torch.no_grad():
+                mu = x.mean(dim=(0, 2, 3))
+                var = x.var(dim=(0, 2, 3), unbiased=False)
+                p[prefix + ".running_mean"].mul_(0.9).add_(0.1 * mu)
+                p[prefix + ".running_var"].mul_(0.9).add_(0.1 * var)
+        return F.batch_norm(x, None, None, p[prefix + ".gamma"], p[prefix + ".beta"], training=True, eps=BN_EPS)
     # inference BatchNorm with running statistics: (x - mean) / sqrt(var + eps) * gamma + beta
     return F.batch_norm(x, p[prefix + ".running_mean"], p[prefix + ".running_var"], p[prefix + ".gamma"],
                         p[prefix + ".beta"], training=False, eps=BN_EPS)
+
+
+def _with_mode(fn):
+    def wrapped(x, p, training=False):
+        prev = _BN_TRAINING[0]
+        _BN_TRAINING[0] = bool(training)
+        try:
+            return fn(x, p)
+        finally:
+            _BN_TRAINING[0] = prev
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
 
 
 def densenet121_features(x, p):
@@ -149,6 +174,8 @@ def resnet18_v2_features(x, p):
     return x.mean(dim=(2, 3))  # GlobalAvgPool2D + Flatten
 
 
+densenet121_features = _with_mode(densenet121_features)
+resnet18_v2_features = _with_mode(resnet18_v2_features)
 FEATURES = {"densenet121": densenet121_features, "resnet18_v2": resnet18_v2_features}
 
 

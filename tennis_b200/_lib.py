@@ -163,3 +163,17 @@ SIGNATURES.update({
     "tn_mul_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tn_axpy": (c_int, [c_void_p, c_void_p, c_float, c_size_t, c_void_p]),
 })
+
+SIGNATURES.update({
+    "tn_im2col_nhwc": (c_int, [c_void_p, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tn_col2im_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, _LL, c_void_p]),
+    "tn_bn_train_forward": (c_int, [c_void_p, _LL, _LL, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_void_p, _LL, c_void_p]),
+    "tn_bn_train_backward": (c_int, [c_void_p, _LL, c_void_p, _LL, c_void_p, _LL, _LL, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                                     c_int, c_void_p, c_void_p, c_void_p, _LL, c_int, c_void_p]),
+    "tn_maxpool_nhwc_forward": (c_int, [c_void_p, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, _LL, c_void_p,
+                                        c_void_p]),
+    "tn_maxpool_nhwc_backward": (c_int, [c_void_p, _LL, c_void_p, _LL, c_int, c_void_p, _LL, c_void_p]),
+    "tn_avgpool_nhwc_forward": (c_int, [c_void_p, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, _LL, c_void_p]),
+    "tn_avgpool_nhwc_backward": (c_int, [c_void_p, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, _LL, c_int, c_void_p]),
+})

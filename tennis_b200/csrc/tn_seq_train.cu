@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
     }
     __syncthreads();
     if (k0 + 16 < kend) fetch(k0 + 16);
+    // two-level accumulation: each 16-deep K tile is summed on its own and then added to the running total, so the rounding
+    // error grows with K/16 + 16 instead of K (the CNN training path reduces over up to 4608 products per output)
+    float part[4][4] = {};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       float a[4], b[4];
@@ -70,8 +73,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, float a
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 #pragma unroll

@@ -94,8 +94,17 @@ class Features(Block):
         from . import autograd
         if autograd.is_recording() and any(p.grad_req != 'null' for n, p in self._reg_params.items()
                                            if not n.endswith(("running_mean", "running_var"))):
-            raise NotImplementedError("the CNN backward pass is not built: train with --freeze_backbone or --feats_model "
-                                      "(the published CNN-RNN setting), see DESIGN.md section 8")
+            # trainable backbone under ag.record() (train.py:415-421): training-mode forward (batch statistics) with saved
+            # activations on the fp32 training path; the returned features carry the backward of the whole CNN
+            if x.dim() != 4 or x.dtype == torch.uint8:
+                raise ValueError("training expects normalised fp32 frames (N,3,H,W)")
+            from .models.vision.train_graph import CNNTrainGraph
+            for p in self._reg_params.values():
+                if p._data is not None and p._data.device != x.device:
+                    p.reset_ctx(x.device)
+            graph = CNNTrainGraph(self)
+            feats = graph.forward(x)
+            return autograd.tag(feats, graph.backward, None)
         eng = self._get_engine(x.device)
         feats, fb = eng(x, want_bf16=True)
         feats._tn_bf16 = fb  # bf16 twin written by the same kernel; lets the RNN skip a cast pass

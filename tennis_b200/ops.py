@@ -253,8 +253,10 @@ class BiRNN:
                                            dptr(cseq), c_void_p(self._ws[1]), self._ws_bytes, stream_ptr()))
         return {"y": y, "ymax": ymax, "gx": gx, "cseq": cseq, "x": x}
 
-    def backward(self, saved, d_ymax=None, dy=None):
-        """-> dict of gradients keyed like the Gluon parameters (l0_i2h_weight, ..., r0_h2h_bias)."""
+    def backward(self, saved, d_ymax=None, dy=None, want_dx=False, weights=None):
+        """-> dict of gradients keyed like the Gluon parameters (l0_i2h_weight, ..., r0_h2h_bias); with want_dx also
+        "dx" (B,T,D) = sum_dir d(gates_x) W_i2h, from the gate gradients tn_birnn_backward leaves at the head of its workspace
+        (`weights`: the fp32 CUDA parameters)."""
         x = saved["x"]
         B, T, D = x.shape
         G = 3 if self.cell == "gru" else 4
@@ -272,6 +274,14 @@ class BiRNN:
                                       dptr(None if dy is None else dy.contiguous().float()), dptr(dWih), dptr(dWhh), dptr(dbih),
                                       dptr(dbhh), c_void_p(ptr), need, stream_ptr()))
         out = {}
+        if want_dx:
+            from .models.captioning.train_graph import sgemm
+            off = ptr - buf.data_ptr()
+            dgx = buf[off: off + B * T * self.ndir * GH * 4].view(torch.float32).reshape(B * T, self.ndir * GH)
+            dx = torch.empty((B * T, D), dtype=torch.float32, device=dev)
+            for i, d in enumerate(["l0", "r0"][: self.ndir]):
+                sgemm(dgx[:, i * GH:(i + 1) * GH], weights[d + "_i2h_weight"].float(), dx, beta=0.0 if i == 0 else 1.0)
+            out["dx"] = dx.reshape(B, T, D)
         for i, d in enumerate(["l0", "r0"][: self.ndir]):
             out[d + "_i2h_weight"] = dWih[i * GH:(i + 1) * GH]
             out[d + "_h2h_weight"] = dWhh[i * GH:(i + 1) * GH]

@@ -56,12 +56,16 @@ class _RNNLayer(Block):
         saved = eng.forward_train(x.float())
         out = saved["ymax"] if pooled else saved["y"]
 
+        upstream = x if getattr(x, "_tn_node", None) is not None else None  # features of a trainable CNN (end-to-end training)
+
         def bwd(g, eng=eng, saved=saved, self=self):
-            grads = eng.backward(saved, d_ymax=g if pooled else None, dy=None if pooled else g)
+            grads = eng.backward(saved, d_ymax=g if pooled else None, dy=None if pooled else g, want_dx=upstream is not None,
+                                 weights={n: p.data() for n, p in self._reg_params.items()})
+            dx = grads.pop("dx", None)
             for name, gr in grads.items():
                 self._reg_params[name]._accumulate_grad(gr)
-            return None  # the per-frame features are leaves (frozen / pre-extracted backbone)
-        return autograd.tag(out, bwd, None)
+            return dx  # None when the per-frame features are leaves (frozen / pre-extracted backbone)
+        return autograd.tag(out, bwd, upstream)
 
     def forward(self, x):
         """(B,T,D) -> (B,T,ndir*H)."""

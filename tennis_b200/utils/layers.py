@@ -23,6 +23,9 @@ class TimeDistributed(Block):
         twin = getattr(y, "_tn_bf16", None)
         if twin is not None:
             out._tn_bf16 = twin.reshape((B, T) + tuple(twin.shape[1:]))
+        if getattr(y, "_tn_node", None) is not None:  # recorded (trainable model): the unfold is a view, pass the gradient through
+            from .. import autograd
+            autograd.tag(out, lambda g, shp=tuple(y.shape): g.reshape(shp), y)
         return out
 
     def forward(self, x):
