@@ -73,6 +73,14 @@ def test_train_head_on_features_synthetic_and_resume(tmp_path):
     assert "Loaded model params" in out2 and os.path.exists(os.path.join(exp, "0002.params"))
 
 
+def test_train_cnn_framewise_trainable_backbone(tmp_path):
+    """train.py's default flow with a TRAINABLE backbone: FrameModel(resnet18_v2) on single frames, one epoch."""
+    out = _run([os.path.join(ROOT, "train.py"), "--backbone", "resnet18_v2", "--data_shape", "224", "--batch_size", "4",
+                "--every", "24,48,48", "--epochs", "1", "--log_interval", "1", "--synthetic", "--model_id", "t044"], str(tmp_path))
+    assert "validation" in out
+    assert os.path.exists(os.path.join(str(tmp_path), "models", "vision", "experiments", "t044", "0000.params"))
+
+
 def test_train_frozen_backbone_cnn_gru(tmp_path):
     out = _run([os.path.join(ROOT, "train.py"), "--backbone", "resnet18_v2", "--freeze_backbone", "--temp_pool", "gru", "--window", "4",
                 "--data_shape", "224", "--batch_size", "4", "--every", "24,48,48", "--epochs", "1", "--synthetic", "--model_id",

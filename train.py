@@ -1,10 +1,12 @@
 """Event-detector training (same CLI surface as the reference's train.py).
 
-The backward pass covers the temporal head (Dense, BiGRU/LSTM + max-over-time): use `--feats_model <id>` (the published
-CNN-RNN 0042 setting) or `--freeze_backbone`; a trainable CNN raises (its backward is not built).
+Heads on pre-extracted features (`--feats_model <id>`, the published CNN-RNN 0042 setting) or on a frozen backbone
+(`--freeze_backbone`) train on the fast path (tensor-core forward, fused BPTT).  A trainable backbone runs the fp32 training
+graph of the CNN (models/vision/train_graph.py: batch-statistics BatchNorm, im2col convolutions; correct, not yet fast).
 
     python train.py --feats_model 0006 --temp_pool gru --window 30 --synthetic --epochs 2
     python train.py --backbone DenseNet121 --freeze_backbone --temp_pool gru --window 8 --data_shape 224 --synthetic
+    python train.py --backbone resnet18_v2 --data_shape 224 --batch_size 8 --synthetic --epochs 1        # CNN trained frame-wise
 """
 import logging
 import os

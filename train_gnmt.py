@@ -108,8 +108,8 @@ def main(_argv):
     exp_dir = os.path.join('models', 'captioning', 'experiments', FLAGS.model_id)
     cli.setup_logging(exp_dir)
     if FLAGS.feats_model is None and not FLAGS.freeze_backbone:
-        raise SystemExit("training the CNN backbone inside the captioner needs the CNN backward, which is not built "
-                         "(DESIGN.md section 8): pass --feats_model <id> (the published setting) or --freeze_backbone")
+        raise SystemExit("the captioner's training graph takes its source features as constants (the gradient is not routed into "
+                         "the CNN, DESIGN.md section 8): pass --feats_model <id> (the published setting) or --freeze_backbone")
     syn = {} if FLAGS.synthetic else None
     data_train = TennisSet(split='train', captions=True, max_cap_len=FLAGS.tgt_max_len, every=FLAGS.every,
                            feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
