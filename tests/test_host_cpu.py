@@ -150,3 +150,24 @@ def test_feature_all_gather_world_size_2_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_sequence_reverse_index_matches_oracle():
+    """models/captioning/train_graph.py::_reverse_index is SequenceReverse(use_sequence_length=True) as a gather (A.4)."""
+    from oracle.captioning import _sequence_reverse
+    from tennis_b200.models.captioning.train_graph import _reverse_index, _seq_reverse
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 7, 3, generator=g)
+    lens = torch.tensor([7, 1, 4, 6], dtype=torch.int32)
+    idx = _reverse_index(lens, 7)
+    got = _seq_reverse(x, idx)
+    assert torch.equal(got, _sequence_reverse(x, lens.float()))
+    assert torch.equal(_seq_reverse(got, idx), x)  # an involution: the same gather routes gradients back
+
+
+def test_numa_binding_is_best_effort_without_gpu():
+    from tennis_b200.parallel import bind_to_gpu_numa_node
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)
+    assert os.sched_getaffinity(0) <= before

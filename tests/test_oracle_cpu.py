@@ -111,3 +111,34 @@ def test_oracle_reproduces_golden_fixtures():
                           feats=True).numpy()
         assert np.abs(logits - gold["cnnrnn_feats_logits"]).max() < 1e-5
         assert np.abs(O.temporal_pooling(feats, None, "mean", feats=True).numpy() - gold["temporal_pool_mean"]).max() < 1e-6
+
+
+def test_training_mode_oracle_matches_torchvision_train_mode():
+    """The CNN-backward parity tests differentiate the oracle in TRAINING mode (batch statistics).  Pin that mode against
+    torchvision's DenseNet-121 in .train(): same features, same gradient at the first and at a late layer, and the running
+    statistics follow the MXNet convention the reference runs on (0.9 / 0.1 blend with the BIASED batch variance)."""
+    p = O.synthetic_params("densenet121", seed=1234)
+    _, x = O.synthetic_frames(2, 224, seed=3)
+    tv = _torchvision_densenet_with(p).train()
+    feats_tv = torch.flatten(torch.nn.functional.avg_pool2d(torch.relu(tv.features(x)), 7), 1)
+    feats_tv.square().sum().backward()
+    q = {k: v.clone().requires_grad_(not k.endswith(("running_mean", "running_var"))) for k, v in p.items()}
+    q["_update_running"] = True
+    feats = O.FEATURES["densenet121"](x, q, training=True)
+    feats.square().sum().backward()
+    assert (feats - feats_tv).abs().max().item() < 1e-4 * feats_tv.abs().max().item()
+    for ours, theirs in (("conv0.weight", tv.features.conv0.weight), ("block4.layer16.conv2.weight",
+                                                                       tv.features.denseblock4.denselayer16.conv2.weight),
+                         ("bn5.gamma", tv.features.norm5.weight)):
+        a, b = q[ours].grad, theirs.grad
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert cos > 0.9999, (ours, cos)
+    # running statistics of the stem BatchNorm: blend of the old value and the batch statistics of conv0's output
+    with torch.no_grad():
+        y = torch.nn.functional.conv2d(x, p["conv0.weight"], stride=2, padding=3)
+        mu, var_b = y.mean(dim=(0, 2, 3)), y.var(dim=(0, 2, 3), unbiased=False)
+    assert (q["bn0.running_mean"] - (0.9 * p["bn0.running_mean"] + 0.1 * mu)).abs().max().item() < 1e-5
+    assert (q["bn0.running_var"] - (0.9 * p["bn0.running_var"] + 0.1 * var_b)).abs().max().item() < 1e-5
+    # and inference mode is untouched by the switch
+    with torch.no_grad():
+        assert torch.equal(O.FEATURES["densenet121"](x, p), O.FEATURES["densenet121"](x, p, training=False))
