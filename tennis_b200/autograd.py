@@ -1,10 +1,11 @@
-"""A minimal tape for the head-only training step (mxnet.autograd surface used at train.py:415-421:
+"""A minimal tape for the recorded training steps (mxnet.autograd surface used at train.py:415-421 and train_gnmt.py:330-334:
 `with ag.record(): out = model(x); loss = loss_fn(out, y)` then `ag.backward(losses)`).
 
 Tensors stay plain torch CUDA tensors; an op executed while recording tags its output with `_tn_node =
-(backward_fn, input_tensor)`.  backward() walks that chain from the loss.  Only the temporal head is differentiable
-(Dense, fused (bi)RNN + max-over-time, softmax cross-entropy); the chain stops at the per-frame features — a backbone
-with trainable parameters raises, because the CNN backward is not built."""
+(backward_fn, input_tensor)`.  backward() walks that chain from the loss: loss -> classifier Dense -> fused (bi)RNN +
+max-over-time -> TimeDistributed unfold -> CNN training graph (models/vision/train_graph.py, which keeps its own internal tape
+for the branching inside the network), or loss -> NMTModel training graph (models/captioning/train_graph.py).  A node whose
+input is a leaf (pre-extracted features, frozen backbone, input frames) ends the walk."""
 import contextlib
 import threading
 
