@@ -120,26 +120,44 @@ class TennisSet(object):
                 return torch.randn(self._feat_dim, generator=g).relu()
             return torch.randn(3, self._shape, self._shape, generator=g)
         if self._load_feats:
+            packed = self._packed_video(video)
+            if packed is not None:
+                return torch.from_numpy(packed.read([frame])[0])
             return torch.from_numpy(np.load(feature_path(self.feat_dir, video, frame)).astype(np.float32))
         import cv2
         img = cv2.cvtColor(cv2.imread(image_path(self._frames_dir, video, frame), 1), cv2.COLOR_BGR2RGB)
         t = torch.from_numpy(img)
         return self._transform(t) if self._transform is not None else t
 
+    def _packed_video(self, video):
+        """The packed feature store of `video` (feature_store.py) when one exists beside the per-frame files, else None."""
+        cache = self.__dict__.setdefault("_packed_cache", {})
+        if video not in cache:
+            from .feature_store import PackedVideo
+            cache[video] = PackedVideo(self.feat_dir, video) if PackedVideo.exists(self.feat_dir, video) else None
+        return cache[video]
+
+    def _load_frames(self, video, frames):
+        """Stack of frames / features of one video; features of a packed video come from ONE gather."""
+        if self._synthetic is None and self._load_feats:
+            packed = self._packed_video(video)
+            if packed is not None:
+                return torch.from_numpy(packed.read(frames))
+        return torch.stack([self._load_frame(video, f) for f in frames])
+
     def __getitem__(self, idx):
         sample = self._samples[idx]
         if self._captions:
             vid, start, end = self._points[sample][0], int(self._points[sample][1]), int(self._points[sample][2])
             cap = self._points[sample][5]
-            imgs = [self._load_frame(vid, f) for c, f in enumerate(range(start, end)) if c % self._every == 0]
-            imgs = torch.stack(imgs)
+            imgs = self._load_frames(vid, [f for c, f in enumerate(range(start, end)) if c % self._every == 0])
             if self._inference:
                 return imgs, cap, len(imgs), len(cap), idx
             return imgs, cap, len(imgs), len(cap)
         label = self.classes.index(sample[2])
         if self._window > 1:
             frames = window_frames(sample[1], self._window, self._stride, self._every, self._video_lengths[sample[0]])
-            img = torch.stack([self._load_frame(sample[0], f) for f in frames])
+            img = self._load_frames(sample[0], frames)
         else:
             img = self._load_frame(sample[0], sample[1])
         return img, label, idx

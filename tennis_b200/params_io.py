@@ -3,7 +3,7 @@
 Writes/reads the MXNet NDArray-list ".params" layout recalled in SURVEY.md §8f-1 ([UPSTREAM], unpinned: no real
 MXNet file is available offline to validate against):
   u64 magic 0x112, u64 reserved, u64 count, then per array
-  { u32 magic 0xF993FAC9, i32 stype(0 = dense), u32 ndim, i64 dims[ndim], i32 dev_type(1 = cpu), i32 dev_id,
+  { u32 magic 0xF993FAC9 (or ...CA), i32 stype(0 = dense), u32 ndim, i64 dims[ndim], i32 dev_type(1 = cpu), i32 dev_id,
     i32 dtype flag (0 = float32, 4 = int32, 6 = int64), raw little-endian data },
   then u64 name count and per name { u64 length, bytes }.
 Keys are the structural names Gluon's save_parameters uses ("backbone.conv0.weight", "rnn.l0_i2h_weight", ...).
@@ -14,6 +14,7 @@ import numpy as np
 
 _LIST_MAGIC = 0x112
 _ND_MAGIC_V2 = 0xF993FAC9
+_ND_MAGIC_V3 = 0xF993FACA  # same record layout, written by MXNet >= 1.6 when numpy-shape semantics are on
 _DTYPE_FLAG = {np.dtype("float32"): 0, np.dtype("float64"): 1, np.dtype("float16"): 2, np.dtype("uint8"): 3,
                np.dtype("int32"): 4, np.dtype("int8"): 5, np.dtype("int64"): 6}
 _FLAG_DTYPE = {v: k for k, v in _DTYPE_FLAG.items()}
@@ -53,7 +54,7 @@ def load(filename):
     arrays = []
     for _ in range(count):
         nd_magic, stype = rd("<Ii")
-        if nd_magic != _ND_MAGIC_V2 or stype != 0:
+        if nd_magic not in (_ND_MAGIC_V2, _ND_MAGIC_V3) or stype != 0:
             raise ValueError("unsupported NDArray record (magic 0x%x, stype %d)" % (nd_magic, stype))
         (ndim,) = rd("<I")
         shape = rd("<%dq" % ndim) if ndim else ()

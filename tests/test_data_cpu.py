@@ -136,3 +136,45 @@ def test_host_pipeline_chunk_schedule():
     cuts8 = plan_chunks(64, *m8)
     assert len(cuts8) - 1 <= 4 and cuts8[1] <= 16
     assert span(cuts8, m8) <= span(cuts, m8)
+
+
+def test_packed_feature_store_roundtrip_and_dataset_read(tmp_path):
+    """feature_store.py: reference per-frame layout -> packed -> reference layout is bit-identical; window reads (with the
+    clamped, repeated frames of dataset.py:196-201) equal per-frame reads; TennisSet picks the packed video up."""
+    import os
+    from tennis_b200 import feature_store as FS
+    from tennis_b200.dataset import TennisSet, feature_path, window_frames
+    root = str(tmp_path / "data")
+    feat_dir = os.path.join(root, "features", "0006")
+    rng = np.random.RandomState(0)
+    frames = list(range(0, 2400, 3))          # spans three 1000-frame chunk directories
+    feats = rng.randn(len(frames), 16).astype(np.float32)
+    for f, row in zip(frames, feats):
+        path = feature_path(feat_dir, "V007", f)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.save(path, row)
+    assert FS.per_frame_path(feat_dir, "V007", 1203) == feature_path(feat_dir, "V007", 1203)
+    assert FS.pack_video(feat_dir, "V007") == len(frames)
+    store = FS.PackedVideo(feat_dir, "V007")
+    assert store.dim == 16 and np.array_equal(store.frames, np.array(frames))
+    win = [0, 0, 3, 6, 2397, 2397]            # clamped window: repeats at both ends
+    assert np.array_equal(store.read(win), np.stack([feats[frames.index(f)] for f in win]))
+    try:
+        store.read([4])
+        raise AssertionError("a frame that was never extracted must not be served")
+    except KeyError:
+        pass
+    # compatibility writer reproduces the per-frame files bit for bit
+    other = os.path.join(root, "features", "copy")
+    FS.write_packed(other, "V007", frames[::-1], feats[::-1])     # unsorted input is sorted on write
+    assert FS.unpack_video(other, "V007") == len(frames)
+    for f in (0, 999, 1002, 2397):
+        assert np.array_equal(np.load(feature_path(other, "V007", f)), np.load(feature_path(feat_dir, "V007", f)))
+    # the dataset serves windows from the packed video
+    os.makedirs(os.path.join(root, "splits"), exist_ok=True)
+    ds = TennisSet.__new__(TennisSet)
+    ds.feat_dir, ds._synthetic, ds._load_feats = feat_dir, None, True
+    fr = window_frames(6, 4, 3, 3, 2400)
+    got = ds._load_frames("V007", fr)
+    assert got.shape == (4, 16) and np.array_equal(got.numpy(), np.stack([feats[frames.index(f)] for f in fr]))
+    assert np.array_equal(ds._load_frame("V007", 1203).numpy(), feats[frames.index(1203)])

@@ -106,6 +106,33 @@ def test_params_codec_roundtrip_and_layout(tmp_path):
         assert back[k].dtype == arrays[k].dtype and np.array_equal(back[k], arrays[k])
 
 
+def test_params_reader_parses_hand_assembled_ndarray_list(tmp_path):
+    """The reader against bytes assembled field by field from the layout in SURVEY.md 8f-1 (independent of our writer):
+    list header, one V2 and one V3 dense record, Gluon-style names with the legacy `arg:` / `aux:` prefixes."""
+    import struct
+    from tennis_b200 import params_io
+    w = np.arange(6, dtype="<f4").reshape(2, 3)
+    m = np.array([5, 7], dtype="<i8")
+    raw = struct.pack("<QQQ", 0x112, 0, 2)
+    raw += struct.pack("<Ii", 0xF993FAC9, 0) + struct.pack("<I", 2) + struct.pack("<2q", 2, 3) + struct.pack("<iii", 1, 0, 0) + w.tobytes()
+    raw += struct.pack("<Ii", 0xF993FACA, 0) + struct.pack("<I", 1) + struct.pack("<1q", 2) + struct.pack("<iii", 2, 3, 6) + m.tobytes()
+    raw += struct.pack("<Q", 2)
+    for name in (b"arg:classes.weight", b"aux:bn0.running_mean"):
+        raw += struct.pack("<Q", len(name)) + name
+    path = str(tmp_path / "hand.params")
+    open(path, "wb").write(raw)
+    got = params_io.load(path)
+    assert list(got) == ["classes.weight", "bn0.running_mean"]
+    assert got["classes.weight"].dtype == np.float32 and np.array_equal(got["classes.weight"], w)
+    assert got["bn0.running_mean"].dtype == np.int64 and np.array_equal(got["bn0.running_mean"], m)
+    bad = bytearray(raw)
+    bad[0] = 0x13
+    open(path, "wb").write(bytes(bad))
+    import pytest as _pt
+    with _pt.raises(ValueError):
+        params_io.load(path)
+
+
 def test_time_distributed_folds_and_unfolds():
     from tennis_b200.gluon import Block
     from tennis_b200.utils.layers import TimeDistributed
