@@ -1,8 +1,8 @@
 """TennisSet: sample assembly of the reference's dataset.py for the hot path.
 
-Real mode (data/splits, data/annotations/... present): frame / feature path scheme and windowing exactly as the
-reference (dataset.py:135-150, 186-233); annotation parsing itself is out of scope and is delegated
-to a small split-file reader.  Synthetic mode (no dataset on disk, `synthetic=` given or TENNIS_SYNTHETIC=1): a seeded
+Real mode (data/splits, data/annotations/... present): split / label / point / caption files, events, OTH balancing, the
+frame / feature path scheme and windowing as the reference reads them (dataset.py:135-150, 186-233, 268-287, 302-437); frame
+extraction from the videos is not part of the path.  Synthetic mode (no dataset on disk, `synthetic=` given or TENNIS_SYNTHETIC=1): a seeded
 procedural stand-in with the same sample tuples, so the scripts, the batching code and the kernels see the shapes
 and index semantics of the real thing:
     events : (img (T,3,S,S) | (3,S,S) | feats (T,D), label int, idx int)
@@ -99,14 +99,133 @@ class TennisSet(object):
             self._points['P%04d' % i] = [v, start, start + n, 'point', cap]
 
     def _init_real(self, splits_file):
+        """The on-disk dataset as the reference reads it (dataset.py:302-437):
+            splits/<split_id>/<split>.txt          "video frame" per line
+            annotations/labels/<video>.txt         "frame CLASS" per line
+            annotations/points.txt                 "point_id video start end tag" per line
+            annotations/captions.txt               "point_id<TAB>caption" per line
+        Samples are [video, frame, class]; events are maximal runs of one class; points are kept when their video and start
+        frame belong to the split.  `save_feats` pads every video with 255 'OTH' frames on both sides (:333-345) so that
+        every window of the captioner finds its features.  Frames whose image is missing are dropped when images are what is
+        loaded (the reference extracts them from the videos first; video decoding is outside the hot path)."""
+        root = self._root
+        labels_dir = os.path.join(root, "annotations", "labels")
+        ann_dir = os.path.join(root, "annotations")
         with open(splits_file) as f:
-            rows = [line.split() for line in f if line.strip()]
-        self._samples = [[r[0], int(r[1]), r[2] if len(r) > 2 else 'OTH'] for r in rows]
-        self._videos = sorted({s[0] for s in self._samples})
-        self._video_lengths = {v: max(s[1] for s in self._samples if s[0] == v) + 1 for v in self._videos}
-        self._points = {}
+            samples = [[t[0], int(t[1])] for t in (line.split() for line in f) if len(t) >= 2]
+        videos = sorted({s[0] for s in samples})
+        labels = {v: {} for v in videos}
+        if self._save_feats:
+            for v in videos:
+                own = [s[1] for s in samples if s[0] == v]
+                lo, hi = min(own), max(own)
+                for i in range(1, 256):
+                    for fr in (lo - i, hi + i):
+                        samples.append([v, fr])
+                        labels[v][fr] = 'OTH'
+        if not self._load_feats:
+            present = [s for s in samples if os.path.exists(image_path(self._frames_dir, s[0], s[1]))]
+            if len(present) != len(samples):
+                import logging
+                logging.info("%d of %d frames of split %s have no image under %s and are ignored", len(samples) - len(present),
+                             len(samples), self._split, self._frames_dir)
+            samples = present
+        for v in videos:
+            path = os.path.join(labels_dir, v + '.txt')
+            if os.path.exists(path):
+                with open(path) as f:
+                    for t in (line.split() for line in f):
+                        if len(t) >= 2:
+                            labels[v][int(t[0])] = t[1]
+        in_set = {v: [] for v in videos}
+        for s in samples:
+            s.append(labels[s[0]].get(s[1], 'OTH'))
+            in_set[s[0]].append(s[1])
+        # events: consecutive in-split frames with the same label (dataset.py:395-410, including its initial 'OTH' event)
+        events = []
+        for v in videos:
+            cur, start, last = 'OTH', -1, -1
+            for fr in sorted(in_set[v]):
+                if start < 0:
+                    start = last = fr
+                lab = labels[v].get(fr, 'OTH')
+                if lab != cur:
+                    events.append([v, start, last, cur])
+                    cur, start = lab, fr
+                last = fr
+            events.append([v, start, last, cur])
+        points = {}
+        ppath, cpath = os.path.join(ann_dir, 'points.txt'), os.path.join(ann_dir, 'captions.txt')
+        if os.path.exists(ppath) and os.path.exists(cpath):
+            caps = {}
+            with open(cpath) as f:
+                for line in f:
+                    t = line.rstrip('\n').split('\t')
+                    if len(t) >= 2:
+                        caps[t[0]] = t[1]
+            member = {v: set(fr) for v, fr in in_set.items()}
+            with open(ppath) as f:
+                for t in (line.split() for line in f):
+                    if len(t) >= 4 and t[1] in member and int(t[2]) in member[t[1]] and t[0] in caps:
+                        rec = t[1:5] + ['point'] * max(0, 5 - len(t))
+                        points[t[0]] = rec + [caps[t[0]]]
+        elif self._captions:
+            raise FileNotFoundError("captions=True needs %s and %s" % (ppath, cpath))
+        self._samples, self._videos, self._events, self._points = samples, videos, events, points
+        self._video_lengths = self._real_video_lengths()
+        if not self._captions and self._balance:
+            self._samples = self._balance_classes()
+
+    def _real_video_lengths(self):
+        """Largest frame number on disk per video (dataset.py:439-456: from the frames tree; from the feature tree or its packed
+        store when only features exist)."""
+        out = {}
+        for v in self._videos:
+            for tree, ext in ((self._frames_dir, '.jpg'), (self.feat_dir, '.npy')):
+                vdir = os.path.join(tree, v + '.mp4')
+                if os.path.isdir(vdir):
+                    chunks = sorted(d for d in os.listdir(vdir) if d.isdigit())
+                    if chunks:
+                        files = sorted(fn for fn in os.listdir(os.path.join(vdir, chunks[-1])) if fn.endswith(ext))
+                        if files:
+                            out[v] = int(files[-1][:-len(ext)])
+                            break
+            if v not in out:
+                packed = self._packed_video(v) if self._load_feats else None
+                if packed is not None and len(packed.frames):
+                    out[v] = int(packed.frames[-1])
+                else:
+                    out[v] = max(s[1] for s in self._samples if s[0] == v)
+        return out
+
+    def _balance_classes(self, seed=None):
+        """Thin out the dominant 'OTH' class to about the size of the next largest one by uniform random sampling
+        (dataset.py:268-287)."""
+        import random
+        rng = random.Random(seed) if seed is not None else random
+        counts = self.class_counts()
+        ratio = max(counts[1:]) / float(counts[0] + 1)
+        return [s for s in self._samples if s[2] != 'OTH' or rng.uniform(0, 1) <= ratio]
+
+    def stats(self):
+        """Per-class frame / event counts, or point / frame counts for caption sets (dataset.py:97-130)."""
+        out = 'Split: %s\n' % self._split
         if self._captions:
-            raise FileNotFoundError("caption annotations need data/annotations (not available offline); use synthetic mode")
+            frames = sum(int(self._points[s][2]) - int(self._points[s][1]) for s in self._samples)
+            out += '{0: <8} {1: <8} {2: <5}\n'.format('# Points', '# Frames', 'FperP')
+            out += '{0: <8} {1: <8} {2: <5}\n'.format(len(self._samples), frames, int(frames / max(1, len(self._samples))))
+            return out
+        fcounts = self.class_counts()
+        ecounts = [0] * len(self.classes)
+        for e in getattr(self, "_events", []):
+            ecounts[self.classes.index(e[3])] += 1
+        out += '{0: <6} {1: <8} {2: <8} {3: <5}\n'.format('Class', '# Frames', '# Events', 'FperE')
+        for i, c in enumerate(self.classes):
+            out += '{0: <6} {1: <8} {2: <8} {3: <5}\n'.format(c, fcounts[i], ecounts[i], int(fcounts[i] / (ecounts[i] + .00001)))
+        return out
+
+    def __str__(self):
+        return '\n\n' + self.__class__.__name__ + '\n' + self.stats() + '\n'
 
     # ------------------------------------------------------------------ access
     def __len__(self):

@@ -178,3 +178,49 @@ def test_packed_feature_store_roundtrip_and_dataset_read(tmp_path):
     got = ds._load_frames("V007", fr)
     assert got.shape == (4, 16) and np.array_equal(got.numpy(), np.stack([feats[frames.index(f)] for f in fr]))
     assert np.array_equal(ds._load_frame("V007", 1203).numpy(), feats[frames.index(1203)])
+
+
+def test_real_mode_reads_the_reference_file_layout(tmp_path):
+    """A miniature on-disk dataset in the reference's layout (splits / labels / points / captions / per-frame features):
+    samples, events, balancing, save_feats padding, caption points and windowed feature reads (dataset.py:302-437)."""
+    import os
+    from tennis_b200.dataset import TennisSet, feature_path
+    root = str(tmp_path / "data")
+    os.makedirs(os.path.join(root, "splits", "02"))
+    os.makedirs(os.path.join(root, "annotations", "labels"))
+    frames = list(range(100, 160))
+    lab = lambda f: 'SFI' if 110 <= f < 120 else 'HFL' if 130 <= f < 135 else 'OTH'
+    with open(os.path.join(root, "splits", "02", "train.txt"), "w") as f:
+        f.write("".join("V001 %d\n" % fr for fr in frames))
+    with open(os.path.join(root, "annotations", "labels", "V001.txt"), "w") as f:
+        f.write("".join("%d %s\n" % (fr, lab(fr)) for fr in range(0, 400)))
+    with open(os.path.join(root, "annotations", "points.txt"), "w") as f:
+        f.write("P1 V001 105 125 x\nP2 V001 300 320 x\nP3 V009 10 20 x\n")
+    with open(os.path.join(root, "annotations", "captions.txt"), "w") as f:
+        f.write("P1\tthe player serves into the net\nP2\tout of split\nP3\tother video\n")
+    feat_dir = os.path.join(root, "features", "0006")
+    rng = np.random.RandomState(1)
+    table = {}
+    for fr in range(0, 420):
+        table[fr] = rng.randn(8).astype(np.float32)
+        path = feature_path(feat_dir, "V001", fr)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.save(path, table[fr])
+    ds = TennisSet(root=root, split='train', balance=False, window=4, stride=2, feats_model='0006')
+    assert len(ds) == 60 and ds.class_counts()[:2] == [45, 10] and ds.class_counts()[ds.classes.index('HFL')] == 5
+    assert [e[1:] for e in ds._events] == [[100, 109, 'OTH'], [110, 119, 'SFI'], [120, 129, 'OTH'], [130, 134, 'HFL'],
+                                           [135, 159, 'OTH']]
+    x, label, idx = ds[12]                                  # frame 112, offsets -2..1 with stride 2
+    assert label == ds.classes.index('SFI') and idx == 12
+    assert np.array_equal(x.numpy(), np.stack([table[f] for f in (108, 110, 112, 114)]))
+    assert "SFI    10       1" in ds.stats()
+    bal = TennisSet(root=root, split='train', balance=True, feats_model='0006')
+    assert 15 <= len(bal) <= 60 and bal.class_counts()[1] == 10        # only OTH frames are thinned
+    padded = TennisSet(root=root, split='train', balance=False, feats_model='0006', save_feats=True)
+    assert len(padded) == 60 + 2 * 255 and min(s[1] for s in padded._samples) == 100 - 255
+    cap = TennisSet(root=root, split='train', captions=True, feats_model='0006', max_cap_len=4)
+    assert list(cap._points) == ['P1'] and len(cap) == 1
+    feats, ids, n, ln = cap[0]
+    assert n == 20 and feats.shape == (20, 8) and np.array_equal(feats[0].numpy(), table[105])
+    assert ln == 6 and ids[0] == cap.vocab[cap.vocab.bos_token] and ids[-1] == cap.vocab[cap.vocab.eos_token]
+    assert cap.get_captions(split=True) == [["the", "player", "serves", "into", "the", "net"]]
