@@ -48,6 +48,20 @@ def test_model(net, dataset, ctx, metrics, batch_size):
     return metrics
 
 
+def save_features(net, dataset, ctx, batch_size):
+    """reference train.py:530-545: backbone features of every sample, one .npy per frame (existing files are kept)."""
+    n = 0
+    for data, _, idxs in batches(dataset, batch_size, False, 0):
+        feat = net.backbone(data.to(ctx)).cpu().numpy()
+        for j, i in enumerate(idxs.tolist()):
+            path = dataset.save_feature_path(i)
+            if not os.path.exists(path):
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                np.save(path, feat[j])
+                n += 1
+    return n
+
+
 def train_model(model, train_set, val_set, trainer, loss_fn, ctx, exp_dir, start_epoch):
     """reference train.py:388-500: epoch loop, LR steps, per-epoch validation, scores.txt, NNNN.params."""
     train_metrics = [Accuracy(), PRF1(label_names=train_set.classes)]
@@ -99,12 +113,25 @@ def main(_argv):
     cli.setup_logging(exp_dir)
     syn = {} if FLAGS.synthetic else None
     common = dict(padding=FLAGS.padding, stride=FLAGS.stride, window=FLAGS.window, model_id=FLAGS.model_id, split_id=FLAGS.split_id,
-                  feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
+                  feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn, save_feats=FLAGS.save_feats)
+    if FLAGS.save_feats:
+        FLAGS.balance = [False, False, False]  # every frame gets a feature (train.py:159-160)
     train_set = TennisSet(split='train', balance=FLAGS.balance[0], every=FLAGS.every[0], **common)
     val_set = TennisSet(split='val', balance=FLAGS.balance[1], every=FLAGS.every[1], **common)
     test_set = TennisSet(split='test', balance=FLAGS.balance[2], every=FLAGS.every[2], **common)
     logging.info('train/val/test: %d / %d / %d samples', len(train_set), len(val_set), len(test_set))
     model = cli.build_detector(ctx, len(train_set.classes))
+    if FLAGS.save_feats:
+        # train.py:266-284: load the best epoch by validation score and dump the backbone features of all three splits
+        best = cli.best_epoch(exp_dir)
+        if best is None:
+            raise SystemExit("--save_feats needs a trained model: %s has no scores.txt" % exp_dir)
+        model(train_set[0][0].unsqueeze(0).to(ctx))  # resolve deferred shapes before loading
+        model.load_parameters(os.path.join(exp_dir, '%04d.params' % best), ctx=ctx)
+        logging.info('Loaded model params: %s', os.path.join(exp_dir, '%04d.params' % best))
+        for sett in (train_set, val_set, test_set):
+            logging.info('saved %d new feature files for the %s split', save_features(model, sett, ctx, FLAGS.batch_size), sett._split)
+        return
     path, start_epoch = cli.latest_params(exp_dir)
     if path is not None:
         x0 = train_set[0][0].unsqueeze(0).to(ctx)
