@@ -91,13 +91,14 @@ def test_train_frozen_backbone_cnn_gru(tmp_path):
 @pytest.mark.parametrize("env_extra", [{"TN_TILE_PAIR_MIN": "1"}, {"TN_NO_PDL": "1", "TN_TILE_PAIR_MIN": "1000000"},
                                        {"TN_RNN_NO_WREG": "1"},
                                        {"TN_CHUNK_B1": "3", "TN_CHUNK_B2": "5", "TN_CHUNK_B3": "3", "TN_CHUNK_B4": "7"},
-                                       {"TN_L2_PREFETCH": "4", "TN_STAGE_CAP": "2"}, {"TN_CLAMP_PROLOGUE": "1"}],
+                                       {"TN_L2_PREFETCH": "4", "TN_STAGE_CAP": "2"}],
                          ids=["paired_tiles_forced", "no_pdl_no_pairing", "rnn_smem_weights", "frame_chunked_blocks",
-                              "l2_prefetch_short_ring", "clamp_prologue"])
+                              "l2_prefetch_short_ring"])
 def test_smoke_parity_under_kernel_variants(env_extra):
     """Every launch-path switch must give the same oracle parity: DenseNet-121 + Bi-GRU logits vs the CPU oracle with
     tile pairing forced on for every streamed-weight 1x1 conv, with PDL and pairing off, with the shared-memory RNN scan, with
-    the dense blocks run in ragged frame chunks, with TMA L2 prefetch on a two-stage ring, and with the clamp prologue."""
+    the dense blocks run in ragged frame chunks, and with TMA L2 prefetch on a two-stage ring (the clamp prologue has its own
+    parity tests in test_gpu_backbone.py)."""
     env = dict(os.environ, PYTHONPATH=ROOT, **env_extra)
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=600)
