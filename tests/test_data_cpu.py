@@ -1,7 +1,9 @@
 """CPU-only: dataset sample assembly (D1), caption batching (8f-3), vocabulary, metrics (8f-4), host pipeline schedule."""
 import math
+import os
 
 import numpy as np
+import pytest
 import torch
 
 from tennis_b200.dataset import TennisSet, feature_path, image_path, window_frames
@@ -224,3 +226,28 @@ def test_real_mode_reads_the_reference_file_layout(tmp_path):
     assert n == 20 and feats.shape == (20, 8) and np.array_equal(feats[0].numpy(), table[105])
     assert ln == 6 and ids[0] == cap.vocab[cap.vocab.bos_token] and ids[-1] == cap.vocab[cap.vocab.eos_token]
     assert cap.get_captions(split=True) == [["the", "player", "serves", "into", "the", "net"]]
+
+
+REF_DATA = "/root/reference/data"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference tree not mounted (GPU box): nothing to compare against")
+def test_host_tables_match_the_reference_fixtures():
+    """The only data artefacts the reference ships: the 11 class names and the 250 x 100 caption-word
+    embeddings.  The class table compiled into dataset.py must equal data/classes.names, and the embedding reader + Vocab glue
+    must reproduce train_gnmt.py:211-218 on the real file (unit-norm rows, specials get zero vectors)."""
+    from tennis_b200.dataset import CLASSES
+    from tennis_b200.vocab import Vocab, count_tokens, load_embedding_file
+    with open(os.path.join(REF_DATA, "classes.names")) as f:
+        assert [line.strip() for line in f if line.strip()] == CLASSES
+    table = load_embedding_file(os.path.join(REF_DATA, "embeddings-ex.txt"))
+    assert len(table) == 250 and all(v.shape == (100,) for v in table.values())
+    norms = np.array([np.linalg.norm(v) for v in table.values()])
+    assert np.abs(norms - 1.0).max() < 1e-3
+    vocab = Vocab(count_tokens(list(table.keys())))
+    assert len(vocab) == 254 and vocab.idx_to_token[:4] == ['<unk>', '<pad>', '<bos>', '<eos>']
+    vocab.set_embedding(table)
+    emb = np.asarray(vocab.embedding.idx_to_vec)
+    assert emb.shape == (254, 100) and not emb[:4].any()
+    some = vocab.idx_to_token[10]
+    assert np.array_equal(emb[10], table[some])
