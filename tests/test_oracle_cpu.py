@@ -142,3 +142,65 @@ def test_training_mode_oracle_matches_torchvision_train_mode():
     # and inference mode is untouched by the switch
     with torch.no_grad():
         assert torch.equal(O.FEATURES["densenet121"](x, p), O.FEATURES["densenet121"](x, p, training=False))
+
+
+@pytest.mark.parametrize("cell", ["lstm", "gru"])
+def test_captioning_unroll_with_valid_length_matches_packed_torch_rnn(cell):
+    """SURVEY.md A.4 (MXNet `unroll(valid_length=...)` + BidirectionalCell with SequenceReverse) restated in
+    oracle/captioning.py, against an independent implementation of the same semantics: torch.nn.LSTM/GRU on a packed
+    sequence (outputs zero past each length, final states taken at the last valid step, reverse direction starting at
+    position len-1)."""
+    from oracle import captioning as C
+    B, T, D, H = 4, 9, 12, 16
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, T, D, generator=g)
+    vl = torch.tensor([9., 3., 6., 1.])
+    G = 4 if cell == "lstm" else 3
+    p = {}
+    for side in ("l_cell", "r_cell"):
+        for n, shape in (("i2h_weight", (G * H, D)), ("h2h_weight", (G * H, H)), ("i2h_bias", (G * H,)), ("h2h_bias", (G * H,))):
+            p["enc.%s.%s" % (side, n)] = torch.randn(shape, generator=g) * 0.3
+    l_out, l_st = C._unroll(cell, p, "enc.l_cell.", x, vl, H)
+    r_out, r_st = C._unroll(cell, p, "enc.r_cell.", C._sequence_reverse(x, vl), vl, H)
+    out = torch.cat([l_out, C._sequence_reverse(r_out, vl)], dim=2)
+    mod = (torch.nn.LSTM if cell == "lstm" else torch.nn.GRU)(D, H, batch_first=True, bidirectional=True)
+    with torch.no_grad():
+        for side, suf in (("l_cell", ""), ("r_cell", "_reverse")):
+            getattr(mod, "weight_ih_l0" + suf).copy_(p["enc.%s.i2h_weight" % side])
+            getattr(mod, "weight_hh_l0" + suf).copy_(p["enc.%s.h2h_weight" % side])
+            getattr(mod, "bias_ih_l0" + suf).copy_(p["enc.%s.i2h_bias" % side])
+            getattr(mod, "bias_hh_l0" + suf).copy_(p["enc.%s.h2h_bias" % side])
+        packed = torch.nn.utils.rnn.pack_padded_sequence(x, vl.long(), batch_first=True, enforce_sorted=False)
+        y, hn = mod(packed)
+        y, _ = torch.nn.utils.rnn.pad_packed_sequence(y, batch_first=True, total_length=T)
+    assert (out - y).abs().max().item() < 1e-5
+    h_n = hn[0] if cell == "lstm" else hn
+    assert (l_st[0] - h_n[0]).abs().max().item() < 1e-5 and (r_st[0] - h_n[1]).abs().max().item() < 1e-5
+    if cell == "lstm":
+        assert (l_st[1] - hn[1][0]).abs().max().item() < 1e-5 and (r_st[1] - hn[1][1]).abs().max().item() < 1e-5
+
+
+def test_captioning_attention_and_masked_ce_match_torch_primitives():
+    """SURVEY.md A.5 / A.8 restated in oracle/captioning.py against torch's own primitives: scaled-Luong attention ==
+    scaled_dot_product_attention of the projected query over the raw memory with a key mask; MaskedSoftmaxCELoss ==
+    per-token cross entropy, masked, averaged over the PADDED length."""
+    import torch.nn.functional as F
+    from oracle import captioning as C
+    g = torch.Generator().manual_seed(1)
+    B, T, H = 3, 7, 16
+    p = {"decoder.attention_cell.proj_query.weight": torch.randn(H, H, generator=g) * 0.3}
+    query, mem = torch.randn(B, H, generator=g), torch.randn(B, T, H, generator=g)
+    vl = torch.tensor([7, 2, 5])
+    masks = (torch.arange(T).reshape(1, T) < vl.reshape(B, 1)).float()
+    ctx, w = C.attention(p, query, mem, masks, H)
+    qp = (query @ p["decoder.attention_cell.proj_query.weight"].t()).unsqueeze(1)
+    ref = F.scaled_dot_product_attention(qp, mem, mem, attn_mask=masks.bool().unsqueeze(1), scale=1.0 / H ** 0.5).squeeze(1)
+    assert (ctx - ref).abs().max().item() < 1e-5
+    assert (w.sum(dim=1) - 1).abs().max().item() < 1e-5 and (w * (1 - masks)).abs().max().item() == 0
+    V, Tt = 11, 6
+    pred = torch.randn(B, Tt, V, generator=g)
+    label = torch.randint(0, V, (B, Tt), generator=g).float()
+    tvl = torch.tensor([6., 1., 4.])
+    ce = F.cross_entropy(pred.reshape(-1, V), label.long().reshape(-1), reduction="none").reshape(B, Tt)
+    keep = (torch.arange(Tt).reshape(1, Tt) < tvl.reshape(B, 1)).float()
+    assert (C.masked_softmax_ce(pred, label, tvl) - (ce * keep).sum(dim=1) / Tt).abs().max().item() < 1e-6
