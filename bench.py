@@ -161,8 +161,8 @@ def build_model(device):
     """CNNRNN(FrameModel(DenseNet121.features, 11), 11, hidden 128, 'gru') with the seeded synthetic weights the
     oracle uses (train.py:204-236 assembly)."""
     import torch
-    from oracle import vision as O  # weights generator only (shared seeds with the parity tests)
     from tennis_b200 import model_zoo
+    from tennis_b200 import synthetic as O  # seeded weights shared with the parity tests (no oracle in this arm)
     from tennis_b200.models.vision.definitions import CNNRNN, FrameModel
     backbone = model_zoo.get_model("DenseNet121", pretrained=False).features
     model = CNNRNN(FrameModel(backbone, CLASSES), CLASSES, hidden_size=HIDDEN, type="gru")
@@ -384,13 +384,13 @@ def bench_captioner(device, steps=3):
     Returns caption tokens/s (best beam, BOS/EOS stripped, train_gnmt.py:289-294) from host features to host token ids,
     next to the CPU oracle port timed on a bounded sample (4 sentences)."""
     import torch
-    from oracle import captioning as C
+    from tennis_b200 import synthetic as S
     from tennis_b200.gluon import Dropout, Embedding, HybridSequential
     from tennis_b200.models.captioning.gnmt import BeamSearchScorer, NMTModel, get_gnmt_encoder_decoder
     from tennis_b200.utils.translation import BeamSearchTranslator
     from tennis_b200.vocab import Vocab, count_tokens
     B, Tsrc, D, H, E, V, beam, max_len = 32, 224, 1024, 128, 100, 254, 5, 150
-    p = C.synthetic_gnmt_params(seed=10000, scale=0.35, cell="lstm", H=H, D_src=D, E=E, V=V)
+    p = S.synthetic_gnmt_params(seed=10000, scale=0.35, cell="lstm", H=H, D_src=D, E=E, V=V)
     vocab = Vocab(count_tokens(["w%03d" % i for i in range(V - 4)]))
     src_embed = HybridSequential()
     src_embed.add(Dropout(0.0))
@@ -401,7 +401,7 @@ def bench_captioner(device, steps=3):
     for k, v in p.items():
         params[k].shape, params[k]._data = tuple(v.shape), v.to(device)
         params[k]._version += 1
-    x, vl = C.synthetic_sources(B, Tsrc, D, seed=100, min_len=64)
+    x, vl = S.synthetic_sources(B, Tsrc, D, seed=100, min_len=64)
     xh, vlh = x.pin_memory(), vl.pin_memory()
     tr = BeamSearchTranslator(model, beam_size=beam, scorer=BeamSearchScorer(alpha=1.0, K=5), max_length=max_len)
 
@@ -417,7 +417,9 @@ def bench_captioner(device, steps=3):
         s, v, n = run()
         toks += n
     dt = time.perf_counter() - t0
-    # CPU port on a bounded sample, checked for token equality on that sample
+    # CPU port on a bounded sample (cpu_baseline leg: the only place this function touches the oracle), checked for token
+    # equality on that sample
+    from oracle import captioning as C
     nb = 4
     t1 = time.perf_counter()
     with torch.no_grad():
@@ -439,9 +441,8 @@ def bench_training(device, steps=4):
       captioner : NMTModel LSTM H=128 on B=128 sources of <=224 x 1024-d features, targets <= 30 tokens, Adam (train_gnmt.py:330-337)
     """
     import torch
-    from oracle import captioning as C
-    from oracle import vision as O
     from tennis_b200 import autograd
+    from tennis_b200 import synthetic as S
     from tennis_b200.gluon import (Dropout, Embedding, HybridSequential, MaskedSoftmaxCELoss, SoftmaxCrossEntropyLoss,
                                    Trainer)
     from tennis_b200.models.captioning.gnmt import NMTModel, get_gnmt_encoder_decoder
@@ -455,7 +456,7 @@ def bench_training(device, steps=4):
     labels = torch.randint(0, CLASSES, (B,), generator=g).to(device)
     head = CNNRNN(None, CLASSES, hidden_size=H, type="gru")
     head.initialize(ctx=device)
-    for k, v in O.synthetic_rnn_params("gru", D, H, seed=4321).items():
+    for k, v in S.synthetic_rnn_params("gru", D, H, seed=4321).items():
         prm = head.rnn._reg_params[k]
         prm.shape, prm._data = tuple(v.shape), v.to(device)
         prm._version += 1
@@ -481,7 +482,7 @@ def bench_training(device, steps=4):
                    "ms_per_step": dt * 1e3, "clips_per_s": B / dt, "frames_per_s": B * Tn / dt, "loss_finite": lh == lh}
     # ---- captioner
     Bc, Ts, Dc, Hc, E, V, Tt = 128, 224, 1024, 128, 100, 254, 30
-    p = C.synthetic_gnmt_params(seed=10000, scale=0.1, cell="lstm", H=Hc, D_src=Dc, E=E, V=V)
+    p = S.synthetic_gnmt_params(seed=10000, scale=0.1, cell="lstm", H=Hc, D_src=Dc, E=E, V=V)
     vocab = Vocab(count_tokens(["w%03d" % i for i in range(V - 4)]))
     src_embed = HybridSequential()
     src_embed.add(Dropout(0.0))
@@ -492,7 +493,7 @@ def bench_training(device, steps=4):
     for k, v in p.items():
         params[k].shape, params[k]._data = tuple(v.shape), v.clone().to(device)
         params[k]._version += 1
-    x, vl = C.synthetic_sources(Bc, Ts, Dc, seed=100, min_len=64)
+    x, vl = S.synthetic_sources(Bc, Ts, Dc, seed=100, min_len=64)
     tgt = torch.randint(4, V, (Bc, Tt), generator=g).float()
     tvl = torch.randint(6, Tt + 1, (Bc,), generator=g).float()
     tvl[0] = Tt
@@ -516,7 +517,8 @@ def bench_training(device, steps=4):
     lc = float(lv.cpu().numpy().mean()) * scale
     dt = (time.perf_counter() - t0) / steps
     words = float(vl.sum() + (tvl - 1).sum())  # the reference's "wps" numerator (train_gnmt.py:339-340)
-    # CPU port: oracle forward + torch.autograd on 8 sentences
+    # CPU port (cpu_baseline leg): oracle forward + torch.autograd on 8 sentences
+    from oracle import captioning as C
     nb = 8
     q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
     t1 = time.perf_counter()

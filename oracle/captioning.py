@@ -14,46 +14,15 @@ import math
 
 import torch
 
+from tennis_b200.synthetic import (cell_param_shapes, gnmt_param_shapes, synthetic_gnmt_params,  # noqa: F401
+                                   synthetic_sources)
+
 from .vision import gru_cell, lstm_cell
 
 NEG = -1e18
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cell_param_shapes(cell, in_dim, H):
-    G = 3 if cell == "gru" else 4
-    return [("i2h_weight", (G * H, in_dim)), ("h2h_weight", (G * H, H)), ("i2h_bias", (G * H,)), ("h2h_bias", (G * H,))]
-
-
-def gnmt_param_shapes(cell="lstm", H=128, D_src=1024, E=100, V=254, num_layers=2, num_bi_layers=1):
-    """Structural names follow Gluon."""
-    shapes = []
-    in_dim = D_src
-    for i in range(num_layers):
-        if i < num_bi_layers:
-            for side in ("l_cell", "r_cell"):
-                shapes += [("encoder.rnn_cells.%d.%s.%s" % (i, side, n), s) for n, s in cell_param_shapes(cell, in_dim, H)]
-            in_dim = 2 * H
-        else:
-            shapes += [("encoder.rnn_cells.%d.%s" % (i, n), s) for n, s in cell_param_shapes(cell, in_dim, H)]
-            in_dim = H
-    for i in range(num_layers):
-        din = E + H if i == 0 else 2 * H
-        shapes += [("decoder.rnn_cells.%d.%s" % (i, n), s) for n, s in cell_param_shapes(cell, din, H)]
-    shapes += [("decoder.attention_cell.proj_query.weight", (H, H))]
-    shapes += [("tgt_embed.weight", (V, E)), ("tgt_proj.weight", (V, H)), ("tgt_proj.bias", (V,))]
-    return shapes
-
-
-def synthetic_gnmt_params(seed=10000, scale=0.1, **kw):
-    """model.initialize(init=Uniform(0.1)) style weights (train_gnmt.py:231), seeded."""
-    g = torch.Generator().manual_seed(seed)
-    out = {}
-    for name, shape in gnmt_param_shapes(**kw):
-        out[name] = (torch.rand(shape, generator=g) * 2 - 1) * scale
-    return out
-
-
 def _cell_step(cell, p, prefix, x, state):
     w = [p[prefix + n] for n in ("i2h_weight", "h2h_weight", "i2h_bias", "h2h_bias")]
     if cell == "gru":
@@ -263,15 +232,3 @@ def best_tokens(samples, vlen):
     for i in range(samples.shape[0]):
         out.append([int(t) for t in samples[i, 0, 1:int(vlen[i, 0]) - 1]])
     return out
-
-
-def synthetic_sources(B, T, D, seed=100, min_len=None):
-    """Config-4 style inputs: non-negative features N(0,1)*0.5 clipped at 0, valid_length ~ U{min_len..T}."""
-    g = torch.Generator().manual_seed(seed)
-    x = (torch.randn(B, T, D, generator=g) * 0.5).clamp(min=0)
-    lo = min_len if min_len is not None else max(1, T // 4)
-    vl = torch.randint(lo, T + 1, (B,), generator=g).float()
-    vl[0] = T
-    for b in range(B):
-        x[b, int(vl[b]):] = 0
-    return x, vl

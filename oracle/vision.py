@@ -18,81 +18,12 @@ import math
 import torch
 import torch.nn.functional as F
 
+from tennis_b200.synthetic import (BOTTLENECK, DENSE_CFG, GROWTH, PARAM_SHAPES, RESNET_CH,  # noqa: F401  (shared seeded
+                                   densenet121_param_shapes, flatten_params, normalize_u8,     # generators: the product-side
+                                   resnet18_v2_param_shapes, rnn_param_shapes, synthetic_frames,  # bench uses the same tensors
+                                   synthetic_params, synthetic_rnn_params)                       # without importing the oracle)
+
 BN_EPS = 1e-5
-DENSE_CFG = (6, 12, 24, 16)
-GROWTH, BOTTLENECK = 32, 128
-RESNET_CH = (64, 128, 256, 512)
-
-
-# ----------------------------------------------------------------------------------------------------------------------
-# parameter inventories (canonical order == Gluon's collect_params() order; see include/tennis_b200.h)
-def _bn_names(prefix):
-    return [prefix + ".gamma", prefix + ".beta", prefix + ".running_mean", prefix + ".running_var"]
-
-
-def densenet121_param_shapes():
-    shapes = [("conv0.weight", (64, 3, 7, 7))] + [(n, (64,)) for n in _bn_names("bn0")]
-    c = 64
-    for b, nl in enumerate(DENSE_CFG):
-        for l in range(nl):
-            p = "block%d.layer%d" % (b + 1, l + 1)
-            shapes += [(n, (c,)) for n in _bn_names(p + ".bn1")]
-            shapes += [(p + ".conv1.weight", (BOTTLENECK, c, 1, 1))]
-            shapes += [(n, (BOTTLENECK,)) for n in _bn_names(p + ".bn2")]
-            shapes += [(p + ".conv2.weight", (GROWTH, BOTTLENECK, 3, 3))]
-            c += GROWTH
-        if b < 3:
-            p = "trans%d" % (b + 1)
-            shapes += [(n, (c,)) for n in _bn_names(p + ".bn")]
-            shapes += [(p + ".conv.weight", (c // 2, c, 1, 1))]
-            c //= 2
-    shapes += [(n, (c,)) for n in _bn_names("bn5")]
-    return shapes
-
-
-def resnet18_v2_param_shapes():
-    shapes = [(n, (3,)) for n in _bn_names("bn_data")]
-    shapes += [("conv0.weight", (64, 3, 7, 7))] + [(n, (64,)) for n in _bn_names("bn0")]
-    cin = 64
-    for s, c in enumerate(RESNET_CH):
-        for b in range(2):
-            p = "stage%d.block%d" % (s + 1, b + 1)
-            shapes += [(n, (cin,)) for n in _bn_names(p + ".bn1")]
-            shapes += [(p + ".conv1.weight", (c, cin, 3, 3))]
-            shapes += [(n, (c,)) for n in _bn_names(p + ".bn2")]
-            shapes += [(p + ".conv2.weight", (c, c, 3, 3))]
-            if b == 0 and cin != c:
-                shapes += [(p + ".downsample.weight", (c, cin, 1, 1))]
-            cin = c
-    shapes += [(n, (512,)) for n in _bn_names("bn_final")]
-    return shapes
-
-
-PARAM_SHAPES = {"densenet121": densenet121_param_shapes, "resnet18_v2": resnet18_v2_param_shapes}
-
-
-def synthetic_params(arch, seed=1234, dtype=torch.float32):
-    """Seeded synthetic weights: He-normal convs, BN gamma~U(.5,1.5), beta~N(0,.1),
-    running_mean~N(0,.1), running_var~U(.5,1.5) so activations stay O(1) through the depth."""
-    g = torch.Generator().manual_seed(seed)
-    out = {}
-    for name, shape in PARAM_SHAPES[arch]():
-        if name.endswith(".weight"):
-            fan_in = shape[1] * shape[2] * shape[3]
-            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
-        elif name.endswith(".gamma") or name.endswith(".running_var"):
-            t = torch.rand(shape, generator=g) + 0.5
-        else:
-            t = torch.randn(shape, generator=g) * 0.1
-        if name.startswith("bn_data") and (name.endswith(".gamma") or name.endswith(".beta")):
-            # BatchNorm(scale=False, center=False): gamma fixed to 1, beta fixed to 0 (A.2)
-            t = torch.ones(shape) if name.endswith(".gamma") else torch.zeros(shape)
-        out[name] = t.to(dtype)
-    return out
-
-
-def flatten_params(arch, params):
-    return torch.cat([params[n].reshape(-1).float() for n, _ in PARAM_SHAPES[arch]()]).contiguous()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -214,24 +145,6 @@ def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
     return o * torch.tanh(c2), c2
 
 
-def rnn_param_shapes(cell, D, H, bidirectional=True):
-    G = 3 if cell == "gru" else 4
-    shapes = []
-    for d in (["l0", "r0"] if bidirectional else ["l0"]):
-        shapes += [(d + "_i2h_weight", (G * H, D)), (d + "_h2h_weight", (G * H, H)), (d + "_i2h_bias", (G * H,)),
-                   (d + "_h2h_bias", (G * H,))]
-    return shapes
-
-
-def synthetic_rnn_params(cell, D, H, seed=4321, bidirectional=True, dtype=torch.float32):
-    g = torch.Generator().manual_seed(seed)
-    out = {}
-    for name, shape in rnn_param_shapes(cell, D, H, bidirectional):
-        fan = shape[1] if len(shape) == 2 else H
-        out[name] = ((torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan)).to(dtype)
-    return out
-
-
 def birnn_layer(x, p, cell="gru", H=128):
     """mx.gluon.rnn.GRU/LSTM(H, layout='NTC', bidirectional=True), zero initial state (A.3):
     out[:, t] = concat(h_fwd[t], h_bwd[t])."""
@@ -275,17 +188,3 @@ def cnnrnn(x, feature_fn, rnn_p, cell, H, classes_w=None, classes_b=None, feats=
     y = birnn_layer(x, rnn_p, cell, H)
     y = y.max(dim=1).values
     return y if classes_w is None else dense(y, classes_w, classes_b)
-
-
-def synthetic_frames(n, size=224, seed=100):
-    """Config-1 style input: u8 pixels ~ U{0..255} -> ToTensor -> Normalize (train.py:142-147)."""
-    g = torch.Generator().manual_seed(seed)
-    u8 = torch.randint(0, 256, (n, size, size, 3), generator=g, dtype=torch.uint8)
-    return u8, normalize_u8(u8)
-
-
-def normalize_u8(u8):
-    mean = torch.tensor([0.485, 0.456, 0.406])
-    std = torch.tensor([0.229, 0.224, 0.225])
-    x = u8.float().div(255.0)
-    return ((x - mean) / std).permute(0, 3, 1, 2).contiguous()

@@ -2,7 +2,7 @@
 import sys
 import torch
 sys.path.insert(0, ".")
-from oracle import vision as O
+from tennis_b200 import synthetic as O
 from tennis_b200 import ops
 B, T, D, H = 256, 32, 1024, 128
 p = O.synthetic_rnn_params("gru", D, H, seed=4321)

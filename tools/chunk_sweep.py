@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from oracle import vision as O  # noqa: E402  (only for synthetic weights)
+from tennis_b200 import synthetic as O  # noqa: E402  (seeded synthetic weights)
 from tennis_b200 import ops  # noqa: E402
 
 n = 2048

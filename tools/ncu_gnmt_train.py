@@ -4,7 +4,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from oracle import captioning as C  # noqa: E402
+from tennis_b200 import synthetic as C  # noqa: E402
 from tennis_b200 import autograd  # noqa: E402
 from tennis_b200.gluon import Dropout, Embedding, HybridSequential, MaskedSoftmaxCELoss, Trainer  # noqa: E402
 from tennis_b200.models.captioning.gnmt import NMTModel, get_gnmt_encoder_decoder  # noqa: E402

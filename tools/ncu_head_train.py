@@ -4,7 +4,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from oracle import vision as O  # noqa: E402
+from tennis_b200 import synthetic as O  # noqa: E402
 from tennis_b200 import autograd  # noqa: E402
 from tennis_b200.gluon import SoftmaxCrossEntropyLoss, Trainer  # noqa: E402
 from tennis_b200.models.vision.definitions import CNNRNN  # noqa: E402

@@ -5,7 +5,7 @@ import time
 import torch
 
 sys.path.insert(0, ".")
-from oracle import vision as O  # noqa: E402  (only for synthetic weights)
+from tennis_b200 import synthetic as O  # noqa: E402  (seeded synthetic weights)
 from tennis_b200 import ops  # noqa: E402
 
 arch = sys.argv[1] if len(sys.argv) > 1 else "densenet121"
