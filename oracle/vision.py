@@ -1,4 +1,5 @@
-"""CPU oracle for the event-detector half of the hot path (TEST INFRASTRUCTURE — never imported by the product).
+"""CPU oracle for the event-detector half of the hot path (TEST INFRASTRUCTURE — never imported by the product;
+the seeded weight / input generators it shares with the benchmark live in tennis_b200/synthetic.py).
 
 PARITY UNPINNED: the reference (HaydenFaulkner/Tennis) ships no golden vectors and executes all arithmetic
 inside MXNet / GluonCV, which are neither vendored in /root/reference nor installable here.
