@@ -400,15 +400,15 @@ class Trainer(object):
         self._lr = float(lr)
 
     def step(self, batch_size, ignore_stale_grad=False):
-        import torch.distributed as dist
         from . import ops
+        from .parallel import sum_gradients_across_ranks
         self._t += 1
-        for p in self._params:
-            if p.grad_req == 'null' or p._grad is None:
-                continue
-            g = p._grad.contiguous()
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(g)
+        live = [p for p in self._params if p.grad_req != 'null' and p._grad is not None]
+        for p in live:
+            p._grad = p._grad.contiguous()
+        sum_gradients_across_ranks([p._grad for p in live])  # no-op in a single process
+        for p in live:
+            g = p._grad
             w = p.data()
             st = self._state.get(id(p))
             if self._opt == "sgd":

@@ -58,6 +58,23 @@ def all_gather_rows(local, world=None, group=None):
     return out
 
 
+def sum_gradients_across_ranks(grads, group=None):
+    """Sum each gradient tensor over the ranks, in place (the reference's Trainer on KVStore('device') sums the per-device
+    gradients before `rescale_grad = 1/batch_size` is applied: train.py:298-299,424).  One flat bucket per call:
+    NVSwitch collectives are latency-, not link-bound, so the ~3 MB of head gradients go out as a single all-reduce."""
+    grads = [g for g in grads if g is not None]
+    if not grads or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return grads
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].reshape(g.shape))
+        off += n
+    return grads
+
+
 class ShardedCNNRNN(object):
     """Frame-sharded forward of a CNNRNN / TemporalPooling-style model: `model.td.model` is the per-frame
     feature extractor, `head(features (B,T,D)) -> logits` the temporal head.

@@ -179,6 +179,38 @@ def test_feature_all_gather_world_size_2_gloo(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
 
 
+_GLOO_GRAD_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from tennis_b200.parallel import sum_gradients_across_ranks
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+g = torch.Generator().manual_seed(7)
+base = [torch.randn(5, 3, generator=g), torch.randn(4, generator=g), torch.randn(2, 2, 2, generator=g)]
+grads = [b * (rank + 1) for b in base] + [None]        # rank r holds (r+1) * base; a parameter without gradient is skipped
+out = sum_gradients_across_ranks(grads)
+assert len(out) == 3
+for o, b in zip(out, base):
+    assert torch.allclose(o, b * sum(range(1, world + 1))), (rank, o, b)
+assert grads[0] is out[0]                               # summed in place
+dist.destroy_process_group()
+"""
+
+
+def test_gradient_sum_world_size_2_gloo(tmp_path):
+    """Trainer.step's cross-rank step: gradients are SUMMED over the ranks before rescale_grad (reference KVStore('device'))."""
+    script = tmp_path / "g.py"
+    script.write_text(_GLOO_GRAD_WORKER % ROOT)
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_PORT="29613", MASTER_ADDR="127.0.0.1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    from tennis_b200.parallel import sum_gradients_across_ranks
+    g = [torch.ones(3)]
+    assert sum_gradients_across_ranks(g)[0] is g[0] and torch.equal(g[0], torch.ones(3))  # single process: untouched
+
+
 def test_sequence_reverse_index_matches_oracle():
     """models/captioning/train_graph.py::_reverse_index is SequenceReverse(use_sequence_length=True) as a gather (A.4)."""
     from oracle.captioning import _sequence_reverse
