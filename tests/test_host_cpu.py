@@ -230,3 +230,18 @@ def test_numa_binding_is_best_effort_without_gpu():
     before = os.sched_getaffinity(0)
     assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)
     assert os.sched_getaffinity(0) <= before
+
+
+def test_checkpoint_directory_conventions(tmp_path):
+    """cli.latest_params / best_epoch: newest NNNN.params wins and valid_best.params is never taken for a resume point
+    (train.py:286-295, train_gnmt.py:236-247); the best epoch is the highest AVG_NB_f1 in scores.txt (train.py:334-346)."""
+    from tennis_b200 import cli
+    d = tmp_path / "exp"
+    assert cli.latest_params(str(d)) == (None, 0) and cli.best_epoch(str(d)) is None
+    d.mkdir()
+    for name in ("0000.params", "0003.params", "0011.params", "valid_best.params", "log.txt"):
+        (d / name).write_bytes(b"x")
+    path, start = cli.latest_params(str(d))
+    assert path.endswith("0011.params") and start == 12
+    (d / "scores.txt").write_text("0000 0.1000\n0003 0.4100\n0011 0.3900\n")
+    assert cli.best_epoch(str(d)) == 3

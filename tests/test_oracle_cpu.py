@@ -204,3 +204,47 @@ def test_captioning_attention_and_masked_ce_match_torch_primitives():
     ce = F.cross_entropy(pred.reshape(-1, V), label.long().reshape(-1), reduction="none").reshape(B, Tt)
     keep = (torch.arange(Tt).reshape(1, Tt) < tvl.reshape(B, 1)).float()
     assert (C.masked_softmax_ce(pred, label, tvl) - (ce * keep).sum(dim=1) / Tt).abs().max().item() < 1e-6
+
+
+def test_beam_search_oracle_invariants_and_scorer_values():
+    """gluonnlp BeamSearchScorer / BeamSearchSampler as restated in oracle/captioning.py: known values of the
+    length penalty, and structural invariants of the sampler output that hold for any model: beam 1 == greedy decoding, scores
+    sorted descending, every hypothesis starts with BOS, ends with EOS at valid_length-1 and is padded with -1 afterwards."""
+    from oracle import captioning as C
+    # scorer: (log_probs + scores * prev_lp) / lp with lp = (K+step)^a / (K+1)^a and prev_lp = 1 at step 1
+    lp = torch.tensor([[[-1.0, -2.0]]])
+    sc = torch.tensor([[-3.0]])
+    assert torch.allclose(C.beam_search_scorer(lp, sc, 1, alpha=1.0, K=5), (lp + sc.unsqueeze(-1)) / 1.0)
+    assert torch.allclose(C.beam_search_scorer(lp, sc, 2, alpha=1.0, K=5), (lp + (sc * 1.0).unsqueeze(-1)) / (7.0 / 6.0))
+    assert torch.allclose(C.beam_search_scorer(lp, sc, 3, alpha=1.0, K=5), (lp + (sc * (7.0 / 6.0)).unsqueeze(-1)) / (8.0 / 6.0))
+    cell, H, D, E, V = "gru", 16, 12, 8, 13
+    p = C.synthetic_gnmt_params(seed=3, scale=0.5, cell=cell, H=H, D_src=D, E=E, V=V)
+    x, vl = C.synthetic_sources(3, 6, D, seed=4)
+    with torch.no_grad():
+        s, scores, vlen = C.translate(p, x, vl, cell=cell, H=H, beam=4, max_length=9, bos=2, eos=3)
+        s1, _, v1 = C.translate(p, x, vl, cell=cell, H=H, beam=1, max_length=9, bos=2, eos=3)
+        # greedy reference: repeatedly take the arg-max token of decode_step
+        mem, st = C.encoder_forward(p, x, vl, cell, H)
+        states = C.init_state_from_encoder(mem, st, vl)
+        tok = torch.full((3,), 2.0)
+        greedy = [tok.clone()]
+        alive = torch.ones(3, dtype=torch.bool)
+        for _ in range(9):
+            logits, states = C.decode_step_logits(p, tok, states, cell=cell, H=H)
+            nxt = logits.argmax(dim=-1).float()
+            greedy.append(torch.where(alive, nxt, torch.full_like(nxt, -1.0)))
+            alive = alive & (nxt != 3)
+            tok = nxt.clamp(min=0)
+            if not alive.any():
+                break
+    assert (scores[:, :-1] >= scores[:, 1:]).all()
+    B, beam, L = s.shape
+    for b in range(B):
+        for k in range(beam):
+            n = int(vlen[b, k])
+            assert s[b, k, 0] == 2 and s[b, k, n - 1] == 3 and (s[b, k, n:] == -1).all() and (s[b, k, 1:n - 1] >= 0).all()
+    g = torch.stack(greedy, dim=1)
+    for b in range(3):
+        n = int(v1[b, 0])
+        m = min(n, g.shape[1])
+        assert torch.equal(s1[b, 0, :m].float(), g[b, :m]), (s1[b, 0], g[b])
