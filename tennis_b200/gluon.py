@@ -237,6 +237,8 @@ class Block(object):
         from . import params_io
         loaded = params_io.load(filename)
         params = self.collect_params()
+        from .gluoncv_names import translate_checkpoint_keys
+        loaded = translate_checkpoint_keys(loaded, params)  # checkpoints written by the reference use GluonCV's child indices
         if not allow_missing:
             missing = [k for k in params if k not in loaded]
             if missing:

@@ -245,3 +245,32 @@ def test_checkpoint_directory_conventions(tmp_path):
     assert path.endswith("0011.params") and start == 12
     (d / "scores.txt").write_text("0000 0.1000\n0003 0.4100\n0011 0.3900\n")
     assert cli.best_epoch(str(d)) == 3
+
+
+@pytest.mark.parametrize("arch,first_bn", [("densenet121", "4.0.1.0.gamma"), ("resnet18_v2", "5.0.bn1.gamma")])
+def test_gluoncv_structural_names_cover_the_inventory_and_load(arch, first_bn, tmp_path):
+    """A checkpoint keyed the way the reference's save_parameters keys it (GluonCV child indices, e.g. the documented
+    `td.model.4.0.1.0.gamma`) loads into our models: the name table is a bijection onto the inventory, in order."""
+    from oracle import vision as O
+    from tennis_b200 import gluoncv_names, model_zoo, params_io
+    from tennis_b200.models.vision.definitions import CNNRNN, FrameModel
+    table = gluoncv_names.NAME_MAPS[arch]()
+    ours = [n for n, _ in O.PARAM_SHAPES[arch]()]
+    assert list(table.values()) == ours and len(set(table)) == len(ours)
+    assert first_bn in table and table[first_bn].endswith("bn1.gamma")
+    p = O.synthetic_params(arch, seed=5)
+    inv = {v: k for k, v in table.items()}
+    for prefix, build in (("backbone.", lambda bb: FrameModel(bb, -1)), ("td.model.", lambda bb: CNNRNN(FrameModel(bb, -1), -1))):
+        model = build(model_zoo.get_model(arch).features)
+        model.initialize(ctx=torch.device("cpu"))
+        ckpt = {prefix + inv[k]: v.numpy() for k, v in p.items()}
+        if prefix == "td.model.":
+            for k, prm in model.rnn._reg_params.items():       # deferred input width: give the checkpoint a concrete one
+                shape = tuple(s if s > 0 else 16 for s in prm.shape)
+                ckpt["rnn." + k] = np.zeros(shape, dtype=np.float32)
+        path = str(tmp_path / ("%s_%s.params" % (arch, prefix.strip("."))))
+        params_io.save(path, ckpt)
+        model.load_parameters(path, ctx=torch.device("cpu"))
+        got = model.collect_params()
+        for k in ("conv0.weight", ours[5], ours[-1]):
+            assert torch.equal(got[prefix + k].data(), p[k]), (prefix, k)
