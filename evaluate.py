@@ -63,7 +63,11 @@ def main(_argv):
     exp_dir = os.path.join('models', 'vision', 'experiments', FLAGS.model_id)
     cli.setup_logging(exp_dir)
     split_i = {'train': 0, 'val': 1, 'test': 2}[FLAGS.split]
-    dataset = TennisSet(split=FLAGS.split, balance=FLAGS.balance[split_i], every=FLAGS.every[split_i], padding=FLAGS.padding,
+    test_tf = None
+    if FLAGS.feats_model is None:
+        from tennis_b200 import transforms  # real frames: Resize(S+32) -> CenterCrop(S) on the host, normalisation on the GPU
+        test_tf = transforms.TestTransform(FLAGS.data_shape)
+    dataset = TennisSet(split=FLAGS.split, transform=test_tf, balance=FLAGS.balance[split_i], every=FLAGS.every[split_i], padding=FLAGS.padding,
                         stride=FLAGS.stride, window=FLAGS.window, model_id=FLAGS.model_id, split_id=FLAGS.split_id,
                         feats_model=FLAGS.feats_model, save_feats=FLAGS.save_feats, data_shape=FLAGS.data_shape,
                         synthetic={} if FLAGS.synthetic else None)

@@ -251,3 +251,33 @@ def test_host_tables_match_the_reference_fixtures():
     assert emb.shape == (254, 100) and not emb[:4].any()
     some = vocab.idx_to_token[10]
     assert np.array_equal(emb[10], table[some])
+
+
+def test_image_transforms_match_the_reference_recipe():
+    """transforms.py: Resize(S+32) is a SQUARE bilinear resize (A.1), CenterCrop takes the middle S x S, output stays uint8 HWC
+    for the device-side ToTensor+Normalize; the training transform is reproducible and clips/feature dumps reuse the test one."""
+    cv2 = pytest.importorskip("cv2")
+    from tennis_b200 import transforms as TF
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, size=(90, 160, 3)).astype(np.uint8)           # a 16:9 frame
+    S = 32
+    out = TF.TestTransform(S)(torch.from_numpy(img))
+    assert out.dtype == torch.uint8 and tuple(out.shape) == (S, S, 3)
+    ref = cv2.resize(img, (S + 32, S + 32), interpolation=cv2.INTER_LINEAR)[16:16 + S, 16:16 + S]
+    assert np.array_equal(out.numpy(), ref)
+    assert TF.center_crop(img, 60).shape == (60, 60, 3) and np.array_equal(TF.center_crop(img, 60), img[15:75, 50:110])
+    a = TF.TrainTransform(S, seed=3)(img)
+    b = TF.TrainTransform(S, seed=3)(img)
+    c = TF.TrainTransform(S, seed=4)(img)
+    assert a.dtype == torch.uint8 and tuple(a.shape) == (S, S, 3) and torch.equal(a, b) and not torch.equal(a, c)
+    train, test = TF.build_transforms(S, window=8)
+    assert train is test
+    train, test = TF.build_transforms(S, window=1)
+    assert isinstance(train, TF.TrainTransform) and isinstance(test, TF.TestTransform)
+    with pytest.raises(ValueError):
+        TF.TestTransform(S)(torch.zeros(3, 8, 8))
+    # host-side ToTensor + Normalize equals the oracle's recipe (train.py:145-146)
+    from oracle.vision import normalize_u8
+    f32 = TF.TestTransform(S, to_tensor=True)(img)
+    assert f32.dtype == torch.float32 and tuple(f32.shape) == (3, S, S)
+    assert (f32 - normalize_u8(out.unsqueeze(0))[0]).abs().max().item() < 1e-6

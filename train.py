@@ -116,9 +116,16 @@ def main(_argv):
                   feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn, save_feats=FLAGS.save_feats)
     if FLAGS.save_feats:
         FLAGS.balance = [False, False, False]  # every frame gets a feature (train.py:159-160)
-    train_set = TennisSet(split='train', balance=FLAGS.balance[0], every=FLAGS.every[0], **common)
-    val_set = TennisSet(split='val', balance=FLAGS.balance[1], every=FLAGS.every[1], **common)
-    test_set = TennisSet(split='test', balance=FLAGS.balance[2], every=FLAGS.every[2], **common)
+    train_tf = test_tf = None
+    if FLAGS.feats_model is None:
+        # decoded JPEGs (real data): Resize/CenterCrop/augmentation on the host (train.py:118-164); a trainable backbone gets
+        # normalised fp32 frames for its fp32 training graph, everything else uint8 frames normalised on the GPU
+        from tennis_b200 import transforms
+        train_tf, test_tf = transforms.build_transforms(FLAGS.data_shape, FLAGS.window, FLAGS.save_feats,
+                                                        to_tensor=not FLAGS.freeze_backbone)
+    train_set = TennisSet(split='train', balance=FLAGS.balance[0], every=FLAGS.every[0], transform=train_tf, **common)
+    val_set = TennisSet(split='val', balance=FLAGS.balance[1], every=FLAGS.every[1], transform=test_tf, **common)
+    test_set = TennisSet(split='test', balance=FLAGS.balance[2], every=FLAGS.every[2], transform=test_tf, **common)
     logging.info('train/val/test: %d / %d / %d samples', len(train_set), len(val_set), len(test_set))
     model = cli.build_detector(ctx, len(train_set.classes))
     if FLAGS.save_feats:
