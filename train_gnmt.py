@@ -111,11 +111,15 @@ def main(_argv):
         raise SystemExit("the captioner's training graph takes its source features as constants (the gradient is not routed into "
                          "the CNN, DESIGN.md section 8): pass --feats_model <id> (the published setting) or --freeze_backbone")
     syn = {} if FLAGS.synthetic else None
-    data_train = TennisSet(split='train', captions=True, max_cap_len=FLAGS.tgt_max_len, every=FLAGS.every,
+    train_tf = test_tf = None
+    if FLAGS.feats_model is None:  # frames through the (frozen) CNN: host-side geometry as in train_gnmt.py:172-188
+        from tennis_b200 import transforms
+        train_tf, test_tf = transforms.build_transforms(FLAGS.data_shape)
+    data_train = TennisSet(split='train', transform=train_tf, captions=True, max_cap_len=FLAGS.tgt_max_len, every=FLAGS.every,
                            feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
-    data_val = TennisSet(split='val', captions=True, vocab=data_train.vocab, every=FLAGS.every, inference=True,
+    data_val = TennisSet(split='val', transform=test_tf, captions=True, vocab=data_train.vocab, every=FLAGS.every, inference=True,
                          feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
-    data_test = TennisSet(split='test', captions=True, vocab=data_train.vocab, every=FLAGS.every, inference=True,
+    data_test = TennisSet(split='test', transform=test_tf, captions=True, vocab=data_train.vocab, every=FLAGS.every, inference=True,
                           feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
     val_tgt_sentences = data_val.get_captions(split=True)
     test_tgt_sentences = data_test.get_captions(split=True)
