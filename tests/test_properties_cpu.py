@@ -1,0 +1,69 @@
+"""Property tests (hypothesis) of the host-side index logic around the hot path: clip windows, frame shards, caption buckets,
+the packed feature store and the chunk planner of the host pipeline."""
+import numpy as np
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from tennis_b200.dataset import window_frames
+from tennis_b200.parallel import plan_chunks, shard_range
+from tennis_b200.utils.captioning import FixedBucketSampler, pad_stack
+
+
+@settings(max_examples=200, deadline=None)
+@given(center=st.integers(0, 5000), window=st.integers(1, 64), stride=st.integers(1, 8), every=st.integers(1, 16),
+       length=st.integers(40, 6000))
+def test_window_frames_properties(center, window, stride, every, length):
+    """dataset.py:190-201: W offsets, clamped into [0, last 'every' frame]; non-decreasing; unclamped entries are center+off*stride."""
+    center = min(center, length - 1)
+    fr = window_frames(center, window, stride, every, length)
+    assert len(fr) == window
+    max_frame = length - every
+    max_frame -= max_frame % every
+    assert all(0 <= f <= max(0, max_frame) for f in fr)
+    assert all(a <= b for a, b in zip(fr, fr[1:]))
+    offs = list(range(int(-window / 2), int(np.ceil(window / 2))))
+    for f, o in zip(fr, offs):
+        raw = center + o * stride
+        if 0 < raw < max_frame:
+            assert f == raw
+
+
+@settings(max_examples=200, deadline=None)
+@given(n=st.integers(0, 100000), world=st.integers(1, 16))
+def test_shard_range_partitions_the_frames(n, world):
+    """split_and_load(even_split=False): contiguous shards, equal size except the last, covering [0, n) exactly once."""
+    spans = [shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert all(s == n // world for s in sizes[:-1]) and sizes[-1] == n - (world - 1) * (n // world)
+
+
+@settings(max_examples=100, deadline=None)
+@given(lengths=st.lists(st.tuples(st.integers(1, 300), st.integers(3, 52)), min_size=1, max_size=200),
+       batch=st.integers(1, 64), buckets=st.integers(1, 8), shuffle=st.booleans())
+def test_bucket_sampler_covers_every_sample_once(lengths, batch, buckets, shuffle):
+    s = FixedBucketSampler(lengths, batch, buckets, shuffle=shuffle)
+    seen = [i for b in s for i in b]
+    assert sorted(seen) == list(range(len(lengths))) and all(1 <= len(b) <= batch for b in s) and len(s) == len(list(s))
+
+
+@settings(max_examples=100, deadline=None)
+@given(lens=st.lists(st.integers(0, 40), min_size=1, max_size=12), width=st.integers(1, 5))
+def test_pad_stack_pads_with_zero_to_the_longest(lens, width):
+    seqs = [torch.full((n, width), float(i + 1)) for i, n in enumerate(lens)]
+    out = pad_stack(seqs)
+    assert tuple(out.shape) == (len(lens), max(lens), width)
+    for i, n in enumerate(lens):
+        assert (out[i, :n] == i + 1).all() and (out[i, n:] == 0).all()
+
+
+@settings(max_examples=100, deadline=None)
+@given(B=st.integers(1, 256), copy_ms=st.floats(0.01, 2.0), fixed_ms=st.floats(0.0, 2.0), compute_ms=st.floats(0.01, 2.0),
+       max_chunks=st.integers(1, 8))
+def test_host_pipeline_chunk_plan_is_a_partition(B, copy_ms, fixed_ms, compute_ms, max_chunks):
+    """HostPipeline's chunk plan: increasing cut points from 0 to B, at most max_chunks chunks, never an empty chunk."""
+    cuts = plan_chunks(B, copy_ms, fixed_ms, compute_ms, max_chunks=max_chunks)
+    assert cuts[0] == 0 and cuts[-1] == B and len(cuts) - 1 <= max_chunks
+    assert all(a < b for a, b in zip(cuts, cuts[1:]))
