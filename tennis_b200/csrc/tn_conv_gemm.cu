@@ -31,6 +31,7 @@
 #include <string.h>
 
 #include "tn_common.h"
+#include "tn_conv1x1_ts.h"
 #include "tn_ptx.cuh"
 
 namespace tn {
@@ -824,6 +825,7 @@ cudaError_t launch_conv_gemm(const ConvGemmParams& p, cudaStream_t stream) {
   if (pp.l2_prefetch < 0) pp.l2_prefetch = 0;
   if (const char* e = getenv("TN_STAGE_CAP")) pp.stage_cap = atoi(e);
   ProfScope prof_scope(kProfConvGemm, stream);
+  if (conv1x1_ts_eligible(pp)) return launch_conv1x1_ts(pp, num_sms, stream);  // bottleneck convs: A operand through TMEM
   switch (conv_gemm_pick_bn(p.Cout)) {
     case 32: return launch_bn<32>(pp, num_sms, stream);
     case 64: return launch_bn<64>(pp, num_sms, stream);
