@@ -23,7 +23,10 @@ FLAGS = flags.FLAGS
 def batches(dataset, batch_size):
     """Default batchify over (img, label, idx) samples, shuffle=False (evaluate.py:112-114)."""
     for lo in range(0, len(dataset), batch_size):
-        items = [dataset[i] for i in range(lo, min(len(dataset), lo + batch_size))]
+        mine = cli.rank_shard(list(range(lo, min(len(dataset), lo + batch_size))))  # --num_gpus N: this process's part
+        if not mine:
+            continue
+        items = [dataset[i] for i in mine]
         yield (torch.stack([it[0] for it in items]), torch.tensor([it[1] for it in items]),
                torch.tensor([it[2] for it in items]))
 
@@ -84,16 +87,20 @@ def main(_argv):
         logging.warning('no checkpoint under %s: evaluating freshly initialised weights', exp_dir)
     if FLAGS.save_feats:
         save_features(model, dataset, ctx, FLAGS.batch_size)
+        cli.shutdown()
         return
     if FLAGS.temp_pool in ('max', 'mean') and FLAGS.window > 1 and FLAGS.feats_model is None:
         model = TemporalPooling(model, pool=FLAGS.temp_pool, num_classes=0, feats=False)
     metrics = [Accuracy(), Accuracy('top5', top_k=5), PRF1(label_names=dataset.classes)]
     evaluate_model(model, dataset, ctx, metrics, FLAGS.batch_size)
-    print(metrics[2].mat.astype(int))
-    for m in metrics[:2]:
-        print('%s: %.4f' % m.get())
-    for k, v in metrics[2].get():
-        print('%s: %.4f' % (k, v))
+    cli.sync_metrics(metrics)
+    if cli.is_main():
+        print(metrics[2].mat.astype(int))
+        for m in metrics[:2]:
+            print('%s: %.4f' % m.get())
+        for k, v in metrics[2].get():
+            print('%s: %.4f' % (k, v))
+    cli.shutdown()
 
 
 if __name__ == '__main__':

@@ -90,23 +90,110 @@ def parse_list_flags():
         FLAGS.lr_steps = [int(s) for s in FLAGS.lr_steps]
 
 
+def world():
+    """(rank, world_size) of this process; (0, 1) outside torch.distributed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def is_main():
+    return world()[0] == 0
+
+
+def _relaunch_under_torchrun(n):
+    """`python train.py --num_gpus N` (reference train.py:103: ctx = [mx.gpu(i) for i in range(num_gpus)]) -> one process per GPU:
+    re-exec the same command line under torch.distributed.run and return its exit code."""
+    import socket
+    import subprocess
+    import sys
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(port)] + sys.argv
+    logging.info("--num_gpus %d: relaunching as %s", n, " ".join(cmd))
+    return subprocess.call(cmd)
+
+
 def context():
+    """Device of this process.  --num_gpus N > 1 means N processes, one per GPU (frames / clips sharded by rank, gradients summed
+    over NCCL in Trainer.step): a plain invocation relaunches itself under torch.distributed.run; under torchrun the process group
+    is initialised here.  Only rank 0 writes checkpoints, scores.txt and log.txt (see is_main())."""
+    import torch.distributed as dist
     if FLAGS.num_gpus <= 0:
         raise SystemExit("--num_gpus 0 selects the reference's MXNet CPU path; tennis_b200 is GPU-only (no CPU fallback)")
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device visible: tennis_b200 has no CPU fallback")
-    if FLAGS.num_gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        logging.warning("--num_gpus %d: launch one process per GPU with torchrun (frames are sharded by rank); running on 1 GPU",
-                        FLAGS.num_gpus)
-    return torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if FLAGS.num_gpus > 1 and "RANK" not in os.environ:
+        if torch.cuda.device_count() < FLAGS.num_gpus:
+            raise SystemExit("--num_gpus %d but only %d CUDA devices are visible" % (FLAGS.num_gpus, torch.cuda.device_count()))
+        raise SystemExit(_relaunch_under_torchrun(FLAGS.num_gpus))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if ws > 1 and not dist.is_initialized():
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return torch.device("cuda", local)
 
 
 def setup_logging(exp_dir):
     os.makedirs(exp_dir, exist_ok=True)
     logger = logging.getLogger()
-    logger.setLevel(logging.INFO)
-    logger.addHandler(logging.FileHandler(os.path.join(exp_dir, 'log.txt')))
+    logger.setLevel(logging.INFO if is_main() else logging.WARNING)
+    if is_main():  # one log.txt per experiment, not one per rank
+        logger.addHandler(logging.FileHandler(os.path.join(exp_dir, 'log.txt')))
     logging.basicConfig()
+
+
+def barrier():
+    import torch.distributed as dist
+    if world()[1] > 1:
+        dist.barrier()
+
+
+def shutdown():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def broadcast_parameters(model):
+    """Every rank continues from rank 0's parameters (initialisation is seeded per process; checkpoints are read by all)."""
+    import torch.distributed as dist
+    if world()[1] == 1:
+        return
+    for _, p in sorted(model.collect_params().items()):
+        if p._data is not None:
+            dist.broadcast(p._data, src=0)
+            p._bump()
+
+
+def rank_shard(items):
+    """This rank's contiguous part of one global batch (list or tensor along dim 0): gluon.utils.split_and_load(batch, ctx_list,
+    even_split=False) semantics (train.py:410-412) with one context per process."""
+    from .parallel import shard_range
+    r, w = world()
+    if w == 1:
+        return items
+    lo, hi = shard_range(len(items), r, w)
+    return items[lo:hi]
+
+
+def sync_metrics(metrics):
+    """Sum the metric accumulators over the ranks (each rank evaluated its shard of every batch)."""
+    import torch.distributed as dist
+    r, w = world()
+    if w == 1:
+        return metrics
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    for m in metrics:
+        state = m.state_tensor().to(dev)
+        dist.all_reduce(state)
+        m.load_state_tensor(state.cpu())
+    return metrics
 
 
 def latest_params(exp_dir):

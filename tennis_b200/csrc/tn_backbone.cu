@@ -290,12 +290,13 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
     // in L2 and never reach HBM).  TN_CHUNK_B<1..4>=<frames> overrides; 0 = whole batch in one pass.
     const int cs = chunk_frames(b, n);
     if (halo) TN_CUDA(launch_zero_border(bott, cs, H + 2, W + 2, kBott, st));
-    // EXPERIMENTAL (off by default): one fused kernel per dense layer, bottleneck kept in shared memory (tn_dense_fused.cu).
-    // Numerically identical to the two-kernel path, but with one tile in flight per SM its phases serialise and it measures
-    // slower (31.8 vs 25.8 ms/2048 frames); enable with TN_DENSE_FUSED_MIN_W=<min map width>, e.g. 28 for blocks 1-2.
+    // Dense blocks 1-2 (maps >= 28 wide): ONE fused kernel per dense layer, the bottleneck stays in shared memory
+    // (tn_dense_fused.cu) -- these layers are DRAM-bound and the bottleneck round trip is 40 % of their bytes.  Blocks 3-4 keep
+    // the two-kernel schedule: their 1x1 weights (K up to 992) would have to be re-streamed for every 84-pixel tile.
+    // TN_DENSE_FUSED_MIN_W=<min map width> overrides (a large value disables the fused path: the A/B and parity tests use it).
     const char* fused_env = getenv("TN_DENSE_FUSED_MIN_W");
-    const int fused_min_w = fused_env ? atoi(fused_env) : (1 << 30);
-    const bool fused = dense_fused_supported(H, W) && W >= fused_min_w;
+    const int fused_min_w = fused_env ? atoi(fused_env) : 28;
+    const bool fused_block = dense_fused_supported(H, W) && W >= fused_min_w;
     // BN1+ReLU as a bf16 clamp (ConvGemmParams::pro_clamp) is opt-in: measured on B200 it is no faster than the fp32
     // scale/shift transform (the 1x1 kernels are bound by the memory system, not by the transformer warps) and its
     // systematic threshold rounding raises the mean feature error by ~16 % (profiles/r1_ab_clamp_prologue.log).
@@ -305,7 +306,7 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
       const int nf = (n - f0 < cs) ? (n - f0) : cs;
       __nv_bfloat16* xb = blk[b] + static_cast<size_t>(f0) * H * W * ct;
       for (const DenseLayer& L : bb->layers[b]) {
-        if (fused) {
+        if (fused_block && L.conv1.num_chunks <= 8) {
           TN_CUDA(launch_dense_layer_fused(xb, ct, nf, H, W, L.cin, L.bn1.scale, L.bn1.shift, L.conv1.wpack, L.conv1.num_chunks,
                                            L.bn2.shift, L.conv2h.wpack, bb->num_sms, st));
           continue;

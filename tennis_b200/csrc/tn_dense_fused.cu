@@ -1,22 +1,24 @@
 // Fused DenseNet layer:  BN1+ReLU -> conv1x1 (C_in -> 128) -> BN2+ReLU -> conv3x3 (128 -> 32) -> in-place concat,
 // ONE persistent kernel per layer; the 128-channel bottleneck never leaves the SM.
 //
-// Unfused, every layer writes the bottleneck (256 B/pixel) to HBM and reads it back (~1.9x with halos); in dense blocks
-// 1-2 those two transfers are ~60 % of the layer's HBM traffic and the 1x1 GEMMs run at 11-15 % tensor utilisation because
-// they wait on memory.  Here a CTA owns TR whole image rows (TR*(W+2) <= 128 padded positions):
-//   1. TMA (4-D tensor map c,x,y,f; box 64 ch x (W+2) x (TR+2) rows, out-of-image pixels zero-filled) streams the raw
-//      concat-buffer rows of the tile PLUS its one-row halo, K-chunk by K-chunk, with the matching 1x1 weight chunk;
-//   2. 8 transformer warps apply BN1+ReLU in place (fp32 math);
-//   3. the MMA warp accumulates the 1x1 conv for all (TR+2)*(W+2) <= 256 halo rows in TMEM (two M=128 tiles, N=128);
-//      the halo rows are recomputed by the neighbouring tile -- free, the tensor pipe was idle;
-//   4. epilogue warps read TMEM, add the folded BN2 shift, ReLU, round to bf16 and write the bottleneck tile straight into
-//      shared memory in the UMMA 128B-swizzled layout (image-border positions are written as zeros = the 3x3's padding);
-//   5. the MMA warp runs the 3x3 conv from that tile exactly like tn_conv3x3.cu (row-shifted descriptors for dy, N = 96 =
-//      3 dx taps stacked), and the epilogue combines the dx taps and stores the 32 new channels at their channel offset.
-// Wide maps (W = 56) are cut into 14-column patches: a 16 x 10 halo tile yields 14 x 8 outputs (1.43x recompute instead of
-// 2.07x for two full rows).  Shared memory (W=56): A/B1 ring 3 x 36 KB, bottleneck tile 40 KB, 3x3 weights 72 KB = 223 KB.
-// TMEM: 2x128 + 96 columns.
+// Why (profiles/r2_k1_launches.md): after the tensor-memory 1x1 kernel the two-kernel schedule of dense blocks 1-2 is DRAM-bound
+// (1x1 convs 5.0-5.9 TB/s of the 6.55 TB/s copy peak) and 36 of its 92 GB per 2048 frames are the bottleneck's round trip (written
+// by the 1x1, read back ~1.4x by the 3x3).  Round 1's fused kernel removed those bytes but ran ONE tile per SM through six
+// serial phases with a 256-row halo tile and was slower.  This version pipelines two tiles:
+//   * tile = 14 x 6 output pixels, halo 16 x 8 = 128 rows = ONE M=128 UMMA tile for the 1x1 (no second, mostly empty M tile);
+//   * the 1x1's A operand goes through TENSOR MEMORY as in tn_conv1x1_ts.cu: TMA (4-D box with zero-filled out-of-image pixels)
+//     -> 4 row-owning transformer warps (LDS.128, packed fp32 FFMA2, BN1 parameters from a shared-memory table) -> tcgen05.st
+//     into two TMEM slots -> tcgen05.mma with A from TMEM; the raw stage is released as soon as it has been read;
+//   * both accumulators are double-buffered in TMEM (2 x 128 + 2 x 96 columns) and the single MMA thread issues the 1x1 of tile
+//     t+1 BEFORE the 3x3 of tile t, so the tensor pipe works on the next tile while epilogue 1 turns tile t's accumulator into
+//     the bf16 bottleneck tile in shared memory (+BN2 shift, ReLU, zeros at image-border positions = the 3x3's padding);
+//   * separate warps for the two epilogues (8 for TMEM -> bottleneck tile, 4 for the 3x3 accumulator -> dx-tap combine ->
+//     256-bit stores into the concat buffer), so neither waits for the other;
+//   * 3x3 exactly as tn_conv3x3.cu: row-shifted descriptors for dy, the three dx taps stacked along N (96).
+// 1x1 weights stay resident in shared memory for K <= 256 and are streamed with the activation chunks above that (block 2).
+// Shared memory: 3x3 weights 72 KB + bottleneck tile 32 KB + [W1 <= 64 KB] + ring.  TMEM: 512 columns.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tn_common.h"
@@ -27,25 +29,33 @@ namespace tn {
 
 namespace {
 
-constexpr int kTransWarps = 8;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (1 + kTransWarps + 1 + kEpiWarps) * 32;  // 576: TMA, 8 transformers, MMA, 8 epilogue
-constexpr int kMmaWarp = 1 + kTransWarps;
-constexpr int kEpiWarp0 = kMmaWarp + 1;
+constexpr int kXfWarps = 4;     // warps 0-3   transformers (TMEM lane quarter = warp)
+constexpr int kEpi1Warp0 = 4;   // warps 4-11  epilogue 1 (quarter = warp & 3, 64-channel half = (warp - 4) >> 2)
+constexpr int kEpi1Warps = 8;
+constexpr int kEpi2Warp0 = 12;  // warps 12-15 epilogue 2 (quarter = warp & 3)
+constexpr int kEpi2Warps = 4;
+constexpr int kMmaWarp = 16;
+constexpr int kTmaWarp = 17;
+constexpr int kThreads = 18 * 32;
 constexpr int kN1 = 128, kN2 = 96;
+constexpr int kABytes = 128 * 128;      // raw A stage: 128 halo rows x 64 bf16
 constexpr int kB1Bytes = kN1 * 128;     // one 64-wide K-chunk of the 1x1 weights
 constexpr int kW2Blob = kN2 * 128;
 constexpr int kW2Bytes = 6 * kW2Blob;   // 72 KB
-constexpr int kMaxNS = 4;               // ring stages: as many as fit (FusedParams::ns)
-constexpr int kTmemCols = 512;          // acc1: 2 x 128, acc2: 96
+constexpr int kHaloHalf = 128 * 128;    // bottleneck tile: 128 rows x 64 ch per half (3x3 reads past row 127 only feed unused rows)
+constexpr int kMaxNS = 6;
+constexpr int kMaxResident = 4;         // K <= 256 resident
+constexpr int kMaxChunks = 8;           // K <= 512
+constexpr int kTmemCols = 512;
+constexpr int kAcc1Col = 0, kAcc2Col = 256, kASlotCol = 448;  // acc1: 2 x 128, acc2: 2 x 96, A slots: 2 x 32
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kTailBytes = kMaxChunks * 512 /*BN1 table*/ + 512 /*BN2 shift*/ + 2048 /*dx exchange*/ + 512 /*barriers*/;
 
 struct FusedParams {
-  int ns;                        // ring stages in use (2..kMaxNS)
-  int F, H, W, Wp, TR, NY;       // tile = TR image rows x PW image columns; Wp = PW + 2 (row pitch of the halo tile); NY = TR + 2
-  int PW, tiles_x;               // PW == W (row bands) or a divisor-sized column patch (W = 56: 14 -> 16 x 10 halo tile)
-  int halo_rows;                 // NY * Wp  (<= 256)
-  int a_bytes;                   // halo_rows * 128 rounded up to 1024
-  int tiles_per_frame, num_tiles;
+  int ns, resident;
+  int F, H, W, Wp, TR, NY, PW;   // tile = TR image rows x PW image columns; halo tile Wp x NY = (PW+2) x (TR+2) <= 128 rows
+  int tiles_x, tiles_y, tiles_per_frame, num_tiles;
+  int halo_rows;
   int Cin, nchunks;
   const float* bn1_scale;        // [Cin]
   const float* bn1_shift;
@@ -56,14 +66,11 @@ struct FusedParams {
   int out_cstride, out_coff;
 };
 
-__device__ __forceinline__ uint32_t cvt_pack(float a, float b, bool relu) {
+__device__ __forceinline__ uint32_t cvt_pack_relu(float a, float b) {
   uint32_t r;
-  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
-__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -72,76 +79,113 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// relu(x * s + b) on a bf16 pair, fp32 math (one packed FFMA2), single rounding back to bf16
+__device__ __forceinline__ uint32_t bn_relu2(uint32_t x, const float4 sb) {
+  float y0 = __uint_as_float(x << 16), y1 = __uint_as_float(x & 0xffff0000u);
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmov.b64 rc, {%4, %5};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(y0), "+f"(y1)
+      : "f"(sb.x), "f"(sb.y), "f"(sb.z), "f"(sb.w));
+  return cvt_pack_relu(y0, y1);
+}
 
 __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = p.a_bytes + kB1Bytes;
-  uint8_t* sRing = smem;                                   // ns x (A | B1)
-  uint8_t* sHalo = sRing + p.ns * stage_bytes;              // 2 halves x a_bytes (bottleneck tile, bf16, swizzled)
-  uint8_t* sW2 = sHalo + 2 * p.a_bytes;                    // 72 KB
-  uint8_t* tail = sW2 + kW2Bytes;
-  float* sShift2 = reinterpret_cast<float*>(tail);         // [128]
-  float* xch = sShift2 + 128;                              // [2 halves][4 quarters][2][16]
-  uint64_t* tma_full = reinterpret_cast<uint64_t*>(xch + 256);  // [kMaxNS]
-  uint64_t* a_ready = tma_full + kMaxNS;                   // [kMaxNS]  transformers done
-  uint64_t* empty_bar = a_ready + kMaxNS;                  // [kMaxNS]  MMA1 done with the stage
-  uint64_t* acc1_full = empty_bar + kMaxNS;
-  uint64_t* acc1_empty = acc1_full + 1;
-  uint64_t* halo_full = acc1_empty + 1;
+  const int nchunks = p.nchunks;
+  const bool resident = p.resident != 0;
+  const int stage_bytes = kABytes + (resident ? 0 : kB1Bytes);
+  uint8_t* sW2 = smem;                                        // 72 KB
+  uint8_t* sHalo = sW2 + kW2Bytes;                            // 2 halves x 16 KB (bottleneck tile, bf16, 128B-swizzled)
+  uint8_t* sW1 = sHalo + 2 * kHaloHalf;                       // resident 1x1 weights (resident mode)
+  uint8_t* sRing = sW1 + (resident ? nchunks * kB1Bytes : 0);  // ns x (A [| B1])
+  uint8_t* tail = sRing + p.ns * stage_bytes;
+  float4* sPar = reinterpret_cast<float4*>(tail);             // [nchunks][32 pairs] (s0, s1, b0, b1)
+  float* sShift2 = reinterpret_cast<float*>(tail + kMaxChunks * 512);  // [128]
+  float* xch = sShift2 + 128;                                 // [2 parity][2 halves][4 quarters][2][16]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(xch + 512);  // [kMaxNS]
+  uint64_t* a_empty = a_full + kMaxNS;                        // [kMaxNS]
+  uint64_t* t_full = a_empty + kMaxNS;                        // [2]
+  uint64_t* t_empty = t_full + 2;                             // [2]
+  uint64_t* acc1_full = t_empty + 2;                          // [2]
+  uint64_t* acc1_empty = acc1_full + 2;                       // [2]
+  uint64_t* acc2_full = acc1_empty + 2;                       // [2]
+  uint64_t* acc2_empty = acc2_full + 2;                       // [2]
+  uint64_t* halo_full = acc2_empty + 2;
   uint64_t* halo_empty = halo_full + 1;
-  uint64_t* acc2_full = halo_empty + 1;
-  uint64_t* acc2_empty = acc2_full + 1;
-  uint64_t* w2_full = acc2_empty + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w2_full + 1);
+  uint64_t* w_full = halo_empty + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  griddep_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < kMaxNS; ++s) {
-      mbar_init(&tma_full[s], 1);
-      mbar_init(&a_ready[s], kTransWarps);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], kXfWarps + (resident ? 0 : 1));
     }
-    mbar_init(acc1_full, 1);
-    mbar_init(acc1_empty, kEpiWarps);
-    mbar_init(halo_full, kEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], kXfWarps);
+      mbar_init(&t_empty[i], 1);
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&acc1_empty[i], kEpi1Warps);
+      mbar_init(&acc2_full[i], 1);
+      mbar_init(&acc2_empty[i], kEpi2Warps);
+    }
+    mbar_init(halo_full, kEpi1Warps);
     mbar_init(halo_empty, 1);
-    mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, kEpiWarps);
-    mbar_init(w2_full, 1);
+    mbar_init(w_full, 1);
     mbar_fence_init();
   }
   if (tid < 128) sShift2[tid] = p.bn2_shift[tid];
+  for (int i = tid; i < nchunks * 32; i += kThreads) {  // BN1 table, one float4 per channel pair
+    const int ch = 2 * i;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch < p.Cin) {
+      v.x = p.bn1_scale[ch];
+      v.z = p.bn1_shift[ch];
+    }
+    if (ch + 1 < p.Cin) {
+      v.y = p.bn1_scale[ch + 1];
+      v.w = p.bn1_shift[ch + 1];
+    }
+    sPar[i] = v;
+  }
   if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_acc1 = tmem_base;          // columns [0,256): two M tiles
-  const uint32_t tm_acc2 = tmem_base + 256;    // columns [256,352)
+  if (tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
+    mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(kW2Bytes + (resident ? nchunks * kB1Bytes : 0)));
+    for (int b = 0; b < 6; ++b) bulk_g2s(sW2 + b * kW2Blob, p.w2pack + b * kW2Blob, kW2Blob, w_full);
+    if (resident)
+      for (int c = 0; c < nchunks; ++c) bulk_g2s(sW1 + c * kB1Bytes, p.w1pack + static_cast<size_t>(c) * kB1Bytes, kB1Bytes, w_full);
+  }
+  griddep_wait();
 
-  if (warp == 0) {
-    // ================================================================ TMA producer
+  if (warp == kTmaWarp) {
+    // ================================================================ TMA producer: raw halo tiles (+ streamed 1x1 weights)
     if (lane == 0) {
-      mbar_arrive_expect_tx(w2_full, kW2Bytes);
-      for (int b = 0; b < 6; ++b) bulk_g2s(sW2 + b * kW2Blob, p.w2pack + b * kW2Blob, kW2Blob, w2_full);
       int stage = 0;
       uint32_t phase = 1;
+      const uint32_t tx = static_cast<uint32_t>(p.halo_rows * 128 + (resident ? 0 : kB1Bytes));
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int f = t / p.tiles_per_frame;
         const int tt = t - f * p.tiles_per_frame;
         const int yt = tt / p.tiles_x, xt = tt - yt * p.tiles_x;
-        const int y0 = yt * p.TR - 1;  // unpadded image row / column of the first halo row / column
+        const int y0 = yt * p.TR - 1;  // image row / column of the first halo row / column (-1 = zero padding)
         const int x0 = xt * p.PW - 1;
-        for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(&empty_bar[stage], phase);
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&a_empty[stage], phase);
           uint8_t* st = sRing + stage * stage_bytes;
-          mbar_arrive_expect_tx(&tma_full[stage], static_cast<uint32_t>(p.halo_rows * 128 + kB1Bytes));
+          mbar_arrive_expect_tx(&a_full[stage], tx);
           asm volatile(
               "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-              ::"r"(smem_u32(st)), "l"(&tmap), "r"(c * 64), "r"(x0), "r"(y0), "r"(f), "r"(smem_u32(&tma_full[stage]))
+              ::"r"(smem_u32(st)), "l"(&tmap), "r"(c * 64), "r"(x0), "r"(y0), "r"(f), "r"(smem_u32(&a_full[stage]))
               : "memory");
-          bulk_g2s(st + p.a_bytes, p.w1pack + static_cast<size_t>(c) * kB1Bytes, kB1Bytes, &tma_full[stage]);
+          if (!resident) bulk_g2s(st + kABytes, p.w1pack + static_cast<size_t>(c) * kB1Bytes, kB1Bytes, &a_full[stage]);
           if (++stage == p.ns) {
             stage = 0;
             phase ^= 1u;
@@ -149,83 +193,96 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
         }
       }
     }
-  } else if (warp >= 1 && warp <= kTransWarps) {
-    // ================================================================ transformers: BN1 + ReLU in place
-    const int ttid = tid - 32;  // 0..255
-    const int j = ttid & 7;     // 16-byte slot within the 128-byte row
-    const int r0 = ttid >> 3;   // first row (0..31), then +32
-    int stage = 0;
-    uint32_t phase = 0;
+  } else if (warp < kXfWarps) {
+    // ================================================================ transformers: smem (raw) -> BN1+ReLU -> TMEM
+    const int r = warp * 32 + lane;  // halo row == TMEM lane
+    const uint32_t row_off = static_cast<uint32_t>(r * 128);
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + kASlotCol;
+    int stage = 0, slot = 0;
+    uint32_t sphase = 0, tphase = 1;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      for (int c = 0; c < p.nchunks; ++c) {
-        mbar_wait(&tma_full[stage], phase);
-        const uint32_t a_stage = smem_u32(sRing + stage * stage_bytes);
-        {
-          // rows r0 + 32*i share (r & 7), so this thread always handles channel group g of the chunk: load BN1 once
-          const int g = j ^ (r0 & 7);
-          const int ch = c * 64 + g * 8;
-          if (ch < p.Cin) {
-            const float4* s4 = reinterpret_cast<const float4*>(p.bn1_scale + ch);
-            const float4* h4 = reinterpret_cast<const float4*>(p.bn1_shift + ch);
-            const float4 s0 = __ldg(s4), s1 = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
-#pragma unroll 4
-            for (int r = r0; r < p.halo_rows; r += 32) {
-              const uint32_t addr = a_stage + r * 128 + (j << 4);
-              const uint4 x = lds128(addr);
-              uint4 o;
-              o.x = cvt_pack(fmaf(bf_lo(x.x), s0.x, h0.x), fmaf(bf_hi(x.x), s0.y, h0.y), true);
-              o.y = cvt_pack(fmaf(bf_lo(x.y), s0.z, h0.z), fmaf(bf_hi(x.y), s0.w, h0.w), true);
-              o.z = cvt_pack(fmaf(bf_lo(x.z), s1.x, h1.x), fmaf(bf_hi(x.z), s1.y, h1.y), true);
-              o.w = cvt_pack(fmaf(bf_lo(x.w), s1.z, h1.z), fmaf(bf_hi(x.w), s1.w, h1.w), true);
-              sts128(addr, o);
-            }
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&a_full[stage], sphase);
+        const uint32_t a_row = smem_u32(sRing + stage * stage_bytes) + row_off;
+        const float4* par = sPar + c * 32;
+        uint32_t o[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // two 32-channel halves (keeps the live register count down)
+          uint4 x[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[i] = lds128(a_row + (((4 * hh + i) ^ sw) << 4));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int b = 16 * hh + 4 * i;
+            o[b + 0] = bn_relu2(x[i].x, par[b + 0]);
+            o[b + 1] = bn_relu2(x[i].y, par[b + 1]);
+            o[b + 2] = bn_relu2(x[i].z, par[b + 2]);
+            o[b + 3] = bn_relu2(x[i].w, par[b + 3]);
           }
         }
-        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[stage]);
+        if (lane == 0) mbar_arrive(&a_empty[stage]);  // raw stage read: the TMA warp may refill it (streamed: once the MMAs retire too)
+        mbar_wait(&t_empty[slot], tphase);            // UMMAs that read this TMEM slot have retired
+        tc_fence_after();
+        tmem_st32(t_lane + slot * 32, o);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_full[slot]);
         if (++stage == p.ns) {
           stage = 0;
-          phase ^= 1u;
+          sphase ^= 1u;
         }
+        slot ^= 1;
+        if (slot == 0) tphase ^= 1u;
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================================================================ MMA issuer
+    // ================================================================ MMA issuer: 1x1 of tile j+1 is issued before the 3x3 of tile j
     if (lane == 0) {
       const uint32_t idesc1 = umma_idesc_bf16_m128(kN1);
       const uint32_t idesc2 = umma_idesc_bf16_m128(kN2);
-      mbar_wait(w2_full, 0);
-      int stage = 0, it = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        // ---- 1x1 conv over the halo rows (two M tiles)
-        mbar_wait(acc1_empty, (it & 1) ^ 1);
+      mbar_wait(w_full, 0);
+      int slot = 0, bstage = 0;
+      uint32_t tphase = 0, bphase = 0;
+      auto issue_mma1 = [&](int j) {
+        const int ab = j & 1;
+        mbar_wait(&acc1_empty[ab], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(&a_ready[stage], phase);
+        const uint32_t d_tmem = tmem_base + kAcc1Col + ab * kN1;
+        for (int c = 0; c < nchunks; ++c) {
+          if (!resident) mbar_wait(&a_full[bstage], bphase);  // the stage's weight chunk has landed
+          mbar_wait(&t_full[slot], tphase);
           tc_fence_after();
           const int kv = min(64, p.Cin - c * 64);
-          const uint32_t a_addr = smem_u32(sRing + stage * stage_bytes);
-          const uint64_t db = umma_desc_sw128(a_addr + p.a_bytes);
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            if (mt * 128 < p.halo_rows) {
-              const uint64_t da = umma_desc_sw128(a_addr + mt * 128 * 128);
-              for (int k = 0; k < kv / 16; ++k) umma_bf16_ss(tm_acc1 + mt * kN1, da + 2 * k, db + 2 * k, idesc1, (c > 0 || k > 0) ? 1u : 0u);
+          const uint32_t a_tmem = tmem_base + kASlotCol + slot * 32;
+          const uint32_t b_addr = resident ? smem_u32(sW1 + c * kB1Bytes) : smem_u32(sRing + bstage * stage_bytes + kABytes);
+          const uint64_t db = umma_desc_sw128(b_addr);
+          for (int k = 0; k < kv / 16; ++k) umma_bf16_ts(d_tmem, a_tmem + 8 * k, db + 2 * k, idesc1, (c > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&t_empty[slot]);
+          if (!resident) {
+            umma_commit(&a_empty[bstage]);
+            if (++bstage == p.ns) {
+              bstage = 0;
+              bphase ^= 1u;
             }
           }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == p.ns) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          slot ^= 1;
+          if (slot == 0) tphase ^= 1u;
         }
-        umma_commit(acc1_full);
-        // ---- 3x3 conv from the bottleneck tile the epilogue warps put in shared memory
+        umma_commit(&acc1_full[ab]);
+      };
+      int it = 0;
+      if (static_cast<int>(blockIdx.x) < p.num_tiles) issue_mma1(0);
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        if (t + static_cast<int>(gridDim.x) < p.num_tiles) issue_mma1(it + 1);
+        // ---- 3x3 conv of tile `it` from the bottleneck tile the epilogue-1 warps put in shared memory
+        const int ab = it & 1;
         mbar_wait(halo_full, it & 1);
-        mbar_wait(acc2_empty, (it & 1) ^ 1);
+        mbar_wait(&acc2_empty[ab], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
+        const uint32_t d2 = tmem_base + kAcc2Col + ab * kN2;
         const uint32_t h_base = smem_u32(sHalo);
         const uint32_t w_base = smem_u32(sW2);
         uint32_t acc = 0;
@@ -233,121 +290,123 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            const uint64_t da = umma_desc_sw128(h_base + half * p.a_bytes + dy * p.Wp * 128);
+            const uint64_t da = umma_desc_sw128(h_base + half * kHaloHalf + dy * p.Wp * 128);
             const uint64_t db = umma_desc_sw128(w_base + (dy * 2 + half) * kW2Blob);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_bf16_ss(tm_acc2, da + 2 * k, db + 2 * k, idesc2, acc);
+              umma_bf16_ss(d2, da + 2 * k, db + 2 * k, idesc2, acc);
               acc = 1;
             }
           }
         }
         umma_commit(halo_empty);
-        umma_commit(acc2_full);
+        umma_commit(&acc2_full[ab]);
       }
     }
-  } else {
-    // ================================================================ epilogue warps
-    const int ew = warp - kEpiWarp0;  // 0..7
-    const int qw = warp & 3;          // TMEM lane quarter
-    // epilogue 1 role: M tile = ew>>2 ... but the quarter is fixed by warp%4, so pair (qw, mt) with mt = ew >> 2
-    const int mt = ew >> 2;
-    // epilogue 2 role: quarter qw, output-channel half hf = ew >> 2
-    const int hf = ew >> 2;
+  } else if (warp >= kEpi1Warp0 && warp < kEpi1Warp0 + kEpi1Warps) {
+    // ================================================================ epilogue 1: TMEM -> (+shift2, ReLU, bf16) -> bottleneck tile
+    const int qw = warp & 3;
+    const int half = (warp - kEpi1Warp0) >> 2;  // channels [64*half, 64*half + 64) == one swizzled half of the tile
+    const int r = qw * 32 + lane;               // halo row of this thread
+    const int yy = r / p.Wp, xx = r - yy * p.Wp;
+    const uint32_t row_addr = smem_u32(sHalo) + half * kHaloHalf + r * 128;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int f = t / p.tiles_per_frame;
       const int tt = t - f * p.tiles_per_frame;
       const int yt = tt / p.tiles_x, xt = tt - yt * p.tiles_x;
-      const int yp0 = yt * p.TR;  // padded row / column index of the first HALO row / column (padded index 0 = border)
-      const int xp0 = xt * p.PW;
-      // ------------------------------------------------ epilogue 1: TMEM -> (+shift2, ReLU, bf16) -> bottleneck tile in smem
-      mbar_wait(acc1_full, it & 1);
+      const int yp = yt * p.TR + yy;  // padded coordinates (0 = border)
+      const int xp = xt * p.PW + xx;
+      const bool interior = r < p.halo_rows && xp >= 1 && xp <= p.W && yp >= 1 && yp <= p.H;
+      const int ab = it & 1;
+      mbar_wait(&acc1_full[ab], (it >> 1) & 1);
+      mbar_wait(halo_empty, (it & 1) ^ 1);  // the previous tile's 3x3 MMAs no longer read the bottleneck tile
       tc_fence_after();
-      mbar_wait(halo_empty, (it & 1) ^ 1);  // previous tile's 3x3 MMAs no longer read the tile
-      {
-        const int r = mt * 128 + qw * 32 + lane;  // halo row of this thread
-        const bool in_tile = r < p.halo_rows;
-        const int yy = r / p.Wp, xx = r - yy * p.Wp;
-        const int yp = yp0 + yy;
-        const int xp = xp0 + xx;
-        const bool interior = in_tile && xp >= 1 && xp <= p.W && yp >= 1 && yp <= p.H;
-        const uint32_t row_addr = smem_u32(sHalo) + r * 128;
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-          uint32_t v[32];
-          tmem_ld32(tm_acc1 + (static_cast<uint32_t>(qw * 32) << 16) + mt * kN1 + cb * 32, v);
-          tmem_ld_wait();
-          if (in_tile) {
-            const uint32_t half_addr = row_addr + (cb >> 1) * p.a_bytes;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o = make_uint4(0, 0, 0, 0);
-              if (interior) {
-                const float4 sa = *reinterpret_cast<const float4*>(sShift2 + cb * 32 + q * 8);
-                const float4 sb = *reinterpret_cast<const float4*>(sShift2 + cb * 32 + q * 8 + 4);
-                o.x = cvt_pack(__uint_as_float(v[q * 8 + 0]) + sa.x, __uint_as_float(v[q * 8 + 1]) + sa.y, true);
-                o.y = cvt_pack(__uint_as_float(v[q * 8 + 2]) + sa.z, __uint_as_float(v[q * 8 + 3]) + sa.w, true);
-                o.z = cvt_pack(__uint_as_float(v[q * 8 + 4]) + sb.x, __uint_as_float(v[q * 8 + 5]) + sb.y, true);
-                o.w = cvt_pack(__uint_as_float(v[q * 8 + 6]) + sb.z, __uint_as_float(v[q * 8 + 7]) + sb.w, true);
-              }
-              const int chunk = (cb & 1) * 4 + q;  // 16-byte chunk within the 64-channel half
-              sts128(half_addr + ((chunk ^ (r & 7)) << 4), o);
-            }
-          }
+      for (int cbl = 0; cbl < 2; ++cbl) {
+        const int cb = half * 2 + cbl;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + kAcc1Col + ab * kN1 + cb * 32, v);
+        tmem_ld_wait();
+        if (cbl == 1) {  // accumulator drained by this warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc1_empty[ab]);
         }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(acc1_empty);
-          mbar_arrive(halo_full);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (interior) {
+            const float4 sa = *reinterpret_cast<const float4*>(sShift2 + cb * 32 + q * 8);
+            const float4 sb = *reinterpret_cast<const float4*>(sShift2 + cb * 32 + q * 8 + 4);
+            o.x = cvt_pack_relu(__uint_as_float(v[q * 8 + 0]) + sa.x, __uint_as_float(v[q * 8 + 1]) + sa.y);
+            o.y = cvt_pack_relu(__uint_as_float(v[q * 8 + 2]) + sa.z, __uint_as_float(v[q * 8 + 3]) + sa.w);
+            o.z = cvt_pack_relu(__uint_as_float(v[q * 8 + 4]) + sb.x, __uint_as_float(v[q * 8 + 5]) + sb.y);
+            o.w = cvt_pack_relu(__uint_as_float(v[q * 8 + 6]) + sb.z, __uint_as_float(v[q * 8 + 7]) + sb.w);
+          }
+          const int chunk = cbl * 4 + q;  // 16-byte chunk within the 64-channel half
+          sts128(row_addr + ((chunk ^ (r & 7)) << 4), o);
         }
       }
-      // ------------------------------------------------ epilogue 2: 3x3 accumulators -> combine dx taps -> concat buffer
-      mbar_wait(acc2_full, it & 1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(halo_full);
+    }
+  } else if (warp >= kEpi2Warp0 && warp < kEpi2Warp0 + kEpi2Warps) {
+    // ================================================================ epilogue 2: 3x3 accumulator -> combine dx taps -> concat buffer
+    const int qw = warp & 3;
+    const int r = qw * 32 + lane;  // accumulator row: output pixel at halo position (yy + 1, xx)
+    const int yy = r / p.Wp, xx = r - yy * p.Wp;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int f = t / p.tiles_per_frame;
+      const int tt = t - f * p.tiles_per_frame;
+      const int yt = tt / p.tiles_x, xt = tt - yt * p.tiles_x;
+      const int y = yt * p.TR + yy;       // output image row
+      const int xo = xt * p.PW + xx - 1;  // output image column
+      const bool valid = yy < p.TR && xx >= 1 && xx <= p.PW && xo < p.W && y < p.H;
+      __nv_bfloat16* dst = p.out + (static_cast<size_t>(f * p.H + y) * p.W + xo) * p.out_cstride + p.out_coff;
+      const int ab = it & 1;
+      mbar_wait(&acc2_full[ab], (it >> 1) & 1);
       tc_fence_after();
-      {
-        const int r = qw * 32 + lane;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
         uint32_t v0[16], v1[16], v2[16];
-        const uint32_t taddr = tm_acc2 + (static_cast<uint32_t>(qw * 32) << 16) + hf * 16;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + kAcc2Col + ab * kN2 + hf * 16;
         tmem_ld16(taddr, v0);
         tmem_ld16(taddr + 32, v1);
         tmem_ld16(taddr + 64, v2);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc2_empty);
-        float* x = xch + (it & 1) * 0 + hf * 128;  // single-buffered: protected by the two named barriers below
+        if (hf == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_empty[ab]);
+        }
+        float* x = xch + (it & 1) * 256 + hf * 128;
         if (lane == 31) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) x[(qw * 2 + 0) * 16 + jj] = __uint_as_float(v0[jj]);
+          for (int j = 0; j < 16; ++j) x[(qw * 2 + 0) * 16 + j] = __uint_as_float(v0[j]);
         }
         if (lane == 0) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) x[(qw * 2 + 1) * 16 + jj] = __uint_as_float(v2[jj]);
+          for (int j = 0; j < 16; ++j) x[(qw * 2 + 1) * 16 + j] = __uint_as_float(v2[j]);
         }
-        if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
-        float o[16];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t o[8];
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[jj]), 1);
-          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[jj]), 1);
-          if (lane == 0 && qw > 0) up = x[((qw - 1) * 2 + 0) * 16 + jj];
-          if (lane == 31 && qw < 3) dn = x[((qw + 1) * 2 + 1) * 16 + jj];
-          o[jj] = up + __uint_as_float(v1[jj]) + dn;
+        for (int j = 0; j < 16; j += 2) {
+          float e[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j + u]), 1);    // D[r-1][dx=-1 block]
+            float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j + u]), 1);  // D[r+1][dx=+1 block]
+            if (lane == 0 && qw > 0) up = x[((qw - 1) * 2 + 0) * 16 + j + u];
+            if (lane == 31 && qw < 3) dn = x[((qw + 1) * 2 + 1) * 16 + j + u];
+            e[u] = up + __uint_as_float(v1[j + u]) + dn;
+          }
+          o[j >> 1] = pack_bf16x2(e[0], e[1]);
         }
-        if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // exchange buffer may be rewritten by the next tile
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
-        const int yy = r / p.Wp, xx = r - yy * p.Wp;
-        const int y = yp0 + yy;  // output image row (unpadded): padded row yp0+1+yy -> image row yp0+yy
-        const int xo = xp0 + xx - 1;  // output image column
-        if (yy < p.TR && xx >= 1 && xx <= p.PW && xo < p.W && y < p.H) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(f * p.H + y) * p.W + xo) * p.out_cstride + p.out_coff + hf * 16);
-          dst[0] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          dst[1] = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
-        }
+        if (valid) stg256(dst + hf * 16, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
       }
     }
   }
@@ -369,39 +428,27 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-constexpr int kSmemLimit = 227 * 1024;
-
-// Ring depth: as many stages as fit beside the bottleneck tile and the 3x3 weights (2..4).
-int ring_stages(int a_bytes) {
-  const int fixed = 1024 + 2 * a_bytes + kW2Bytes + 512 + 1024 + 256;
-  int ns = (kSmemLimit - fixed) / (a_bytes + kB1Bytes);
-  return ns > kMaxNS ? kMaxNS : ns;
-}
-
-bool geometry(int H, int W, int* TR, int* PW, int* halo_rows, int* a_bytes, int* smem) {
-  // Wide maps are cut into column patches so that the one-pixel halo costs less: W = 56 -> 14 x 8 outputs from a 16 x 10
-  // halo tile (1.43x recompute of the 1x1 conv instead of 2.07x for two full rows), and the smaller tile buys a deeper ring.
-  *PW = W;
-  if (W + 2 > 32 && W % 14 == 0) *PW = 14;
-  const int Wp = *PW + 2;
-  if (Wp > 128) return false;
-  *TR = 128 / Wp;
-  if (*TR > H) *TR = H;
-  if (*TR < 1) return false;
-  *halo_rows = (*TR + 2) * Wp;
-  if (*halo_rows > 256) return false;
-  *a_bytes = static_cast<int>(align_up(static_cast<size_t>(*halo_rows) * 128, 1024));
-  const int ns = ring_stages(*a_bytes);
-  if (ns < 2) return false;
-  *smem = 1024 + ns * (*a_bytes + kB1Bytes) + 2 * *a_bytes + kW2Bytes + 512 + 1024 + 256;
-  return *smem <= kSmemLimit;
+// Tile geometry: PW output columns x TR output rows from a (PW+2) x (TR+2) halo tile of at most 128 rows (one M=128 UMMA).
+bool geometry(int H, int W, int* TR, int* PW) {
+  if (H < 1 || W < 1) return false;
+  int pw = W;
+  if (W > 14) pw = 14;            // 16-wide halo rows: 16 x 8 = 128 -> 14 x 6 outputs
+  const int wp = pw + 2;
+  int tr = 128 / wp - 2;
+  if (tr > H) tr = H;
+  if (tr < 1) return false;
+  // the last valid accumulator row (TR-1)*Wp + PW must stay below 128 - 1 (its dx=+1 neighbour row is read)
+  if ((tr - 1) * wp + pw + 1 > 127) return false;
+  *TR = tr;
+  *PW = pw;
+  return true;
 }
 
 }  // namespace
 
 bool dense_fused_supported(int H, int W) {
-  int TR, PW, hr, ab, sm;
-  return geometry(H, W, &TR, &PW, &hr, &ab, &sm) && (PW + 2) <= 256 && (TR + 2) <= 256;
+  int TR, PW;
+  return geometry(H, W, &TR, &PW);
 }
 
 cudaError_t launch_dense_layer_fused(const __nv_bfloat16* blk, int blk_cstride, int F, int H, int W, int Cin, const float* bn1_scale,
@@ -410,19 +457,34 @@ cudaError_t launch_dense_layer_fused(const __nv_bfloat16* blk, int blk_cstride, 
   EncodeTiledFn encode = get_encode();
   if (!encode) return cudaErrorNotSupported;
   FusedParams p;
-  int smem;
-  if (!geometry(H, W, &p.TR, &p.PW, &p.halo_rows, &p.a_bytes, &smem)) return cudaErrorInvalidValue;
+  memset(&p, 0, sizeof(p));
+  if (!geometry(H, W, &p.TR, &p.PW)) return cudaErrorInvalidValue;
+  if (w1_chunks < 1 || w1_chunks > kMaxChunks || (Cin % 16) != 0 || (blk_cstride % 16) != 0 || (Cin % 16) != 0 ||
+      (reinterpret_cast<uintptr_t>(blk) & 31) != 0)
+    return cudaErrorInvalidValue;
   p.F = F;
   p.H = H;
   p.W = W;
   p.Wp = p.PW + 2;
   p.NY = p.TR + 2;
-  p.ns = ring_stages(p.a_bytes);
+  p.halo_rows = p.Wp * p.NY;
   p.tiles_x = (W + p.PW - 1) / p.PW;
-  p.tiles_per_frame = ((H + p.TR - 1) / p.TR) * p.tiles_x;
-  p.num_tiles = F * p.tiles_per_frame;
+  p.tiles_y = (H + p.TR - 1) / p.TR;
+  p.tiles_per_frame = p.tiles_x * p.tiles_y;
+  const long long nt = static_cast<long long>(F) * p.tiles_per_frame;
+  if (nt <= 0) return cudaSuccess;
+  if (nt >= (1ll << 31)) return cudaErrorInvalidValue;
+  p.num_tiles = static_cast<int>(nt);
   p.Cin = Cin;
   p.nchunks = w1_chunks;
+  static const int force_stream = getenv("TN_FUSED_STREAM_W1") ? atoi(getenv("TN_FUSED_STREAM_W1")) : 0;
+  p.resident = (w1_chunks <= kMaxResident && !force_stream) ? 1 : 0;
+  const int fixed = 1024 + kW2Bytes + 2 * kHaloHalf + kTailBytes + (p.resident ? w1_chunks * kB1Bytes : 0);
+  const int stage_bytes = kABytes + (p.resident ? 0 : kB1Bytes);
+  p.ns = (kSmemLimit - fixed) / stage_bytes;
+  if (p.ns > kMaxNS) p.ns = kMaxNS;
+  if (p.ns < 2) return cudaErrorInvalidValue;
+  const int smem = fixed + p.ns * stage_bytes;
   p.bn1_scale = bn1_scale;
   p.bn1_shift = bn1_shift;
   p.bn2_shift = bn2_shift;
@@ -449,8 +511,7 @@ cudaError_t launch_dense_layer_fused(const __nv_bfloat16* blk, int blk_cstride, 
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ProfScope prof_scope(kProfConvGemm, st);
-  dense_layer_fused_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
-  return cudaGetLastError();
+  return launch_pdl(dense_layer_fused_kernel, dim3(grid), dim3(kThreads), smem, st, tmap, p);
 }
 
 }  // namespace tn

@@ -405,7 +405,16 @@ class Trainer(object):
         from . import ops
         from .parallel import sum_gradients_across_ranks
         self._t += 1
-        live = [p for p in self._params if p.grad_req != 'null' and p._grad is not None]
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # every rank must enter the same all-reduce: a rank whose shard of the batch was empty (or that did not touch a
+            # parameter) contributes zeros, like an idle context in the reference's split_and_load(even_split=False) loop
+            live = [p for p in self._params if p.grad_req != 'null' and p._data is not None]
+            for p in live:
+                if p._grad is None:
+                    p._grad = torch.zeros_like(p.data())
+        else:
+            live = [p for p in self._params if p.grad_req != 'null' and p._grad is not None]
         for p in live:
             p._grad = p._grad.contiguous()
         sum_gradients_across_ranks([p._grad for p in live])  # no-op in a single process

@@ -29,6 +29,17 @@ class PRF1(object):
                 self.scores[1, i] += positives.sum()
                 self.scores[2, i] += predictions.sum()
 
+    def state_tensor(self):
+        """Accumulators as one float64 tensor (summed across ranks by cli.sync_metrics)."""
+        import torch
+        return torch.from_numpy(np.concatenate([self.scores.reshape(-1), self.mat.reshape(-1)]).astype(np.float64))
+
+    def load_state_tensor(self, t):
+        n = len(self.label_names)
+        a = t.numpy()
+        self.scores = a[:3 * n].reshape(3, n).copy()
+        self.mat = a[3 * n:].reshape(n, n).copy()
+
     def get(self):
         eps = np.finfo(float).eps
         out, ps, rs, fs = [], [], [], []
@@ -61,6 +72,13 @@ class Accuracy(object):
             top = np.argsort(-pred, axis=1, kind='stable')[:, : self.top_k]
             self.hit += int((top == label.reshape(-1, 1)).any(axis=1).sum())
             self.n += label.shape[0]
+
+    def state_tensor(self):
+        import torch
+        return torch.tensor([self.hit, self.n], dtype=torch.float64)
+
+    def load_state_tensor(self, t):
+        self.hit, self.n = int(t[0].item()), int(t[1].item())
 
     def get(self):
         return self.name, self.hit / max(1, self.n)

@@ -28,11 +28,18 @@ FLAGS = flags.FLAGS
 
 
 def batches(dataset, batch_size, shuffle, seed):
+    """Global batches in a rank-independent order; with --num_gpus N each process loads only ITS contiguous shard of every
+    batch (reference train.py:410-412 split_and_load over the context list -> one context per process here).  A rank whose shard
+    is empty (last, short batch) yields None and still takes part in the gradient all-reduce of Trainer.step."""
     order = list(range(len(dataset)))
     if shuffle:
         np.random.RandomState(seed).shuffle(order)
     for lo in range(0, len(order), batch_size):
-        items = [dataset[i] for i in order[lo:lo + batch_size]]
+        mine = cli.rank_shard(order[lo:lo + batch_size])
+        if not mine:
+            yield None
+            continue
+        items = [dataset[i] for i in mine]
         yield (torch.stack([it[0] for it in items]), torch.tensor([it[1] for it in items]),
                torch.tensor([it[2] for it in items]))
 
@@ -41,17 +48,23 @@ def test_model(net, dataset, ctx, metrics, batch_size):
     """reference train.py:503-527."""
     for m in metrics:
         m.reset()
-    for data, labels, _ in batches(dataset, batch_size, False, 0):
+    for batch in batches(dataset, batch_size, False, 0):
+        if batch is None:
+            continue
+        data, labels, _ = batch
         out = net(data.to(ctx, non_blocking=True)).cpu()
         for m in metrics:
             m.update([labels], [out])
-    return metrics
+    return cli.sync_metrics(metrics)
 
 
 def save_features(net, dataset, ctx, batch_size):
     """reference train.py:530-545: backbone features of every sample, one .npy per frame (existing files are kept)."""
     n = 0
-    for data, _, idxs in batches(dataset, batch_size, False, 0):
+    for batch in batches(dataset, batch_size, False, 0):
+        if batch is None:
+            continue
+        data, _, idxs = batch
         feat = net.backbone(data.to(ctx)).cpu().numpy()
         for j, i in enumerate(idxs.tolist()):
             path = dataset.save_feature_path(i)
@@ -75,16 +88,21 @@ def train_model(model, train_set, val_set, trainer, loss_fn, ctx, exp_dir, start
             lr_counter += 1
         for m in train_metrics:
             m.reset()
-        tic, btic, train_loss = time.time(), time.time(), 0.0
-        for i, (data, labels, _) in enumerate(batches(train_set, FLAGS.batch_size, True, epoch)):
+        tic, btic, train_loss, nb = time.time(), time.time(), 0.0, 0
+        for i, batch in enumerate(batches(train_set, FLAGS.batch_size, True, epoch)):
             if FLAGS.max_batches > 0 and i >= FLAGS.max_batches:
                 break
-            data, dl = data.to(ctx, non_blocking=True), labels.to(ctx)
-            with ag.record():
-                out = model(data)
-                loss = loss_fn(out, dl)
-            ag.backward([loss])
-            trainer.step(FLAGS.batch_size)
+            if batch is not None:
+                data, labels, _ = batch
+                data, dl = data.to(ctx, non_blocking=True), labels.to(ctx)
+                with ag.record():
+                    out = model(data)
+                    loss = loss_fn(out, dl)
+                ag.backward([loss])
+            trainer.step(FLAGS.batch_size)  # sums the per-rank gradients (NCCL), rescales by 1/global batch (train.py:424)
+            if batch is None:
+                continue
+            nb += 1
             train_loss += loss.mean().item()  # device -> host sync point, as in the reference (train.py:427)
             for m in train_metrics:
                 m.update([labels], [out.cpu()])
@@ -93,17 +111,19 @@ def train_model(model, train_set, val_set, trainer, loss_fn, ctx, exp_dir, start
                 logging.info('[Epoch %d] [Batch %d] Speed: %.3f samples/sec, %s=%.4f, lr=%.6f', epoch, i + 1,
                              FLAGS.batch_size * FLAGS.log_interval / max(1e-9, time.time() - btic), name, acc, trainer.learning_rate)
                 btic = time.time()
-        nb = max(1, i + 1)
-        logging.info('[Epoch %d] training: loss=%.4f %s=%.4f time: %.1fs', epoch, train_loss / nb, *train_metrics[0].get(),
+        cli.sync_metrics(train_metrics)
+        logging.info('[Epoch %d] training: loss=%.4f %s=%.4f time: %.1fs', epoch, train_loss / max(1, nb), *train_metrics[0].get(),
                      time.time() - tic)
         tic = time.time()
         test_model(model, val_set, ctx, val_metrics, FLAGS.batch_size)
         scores = dict(val_metrics[2].get())
         logging.info('[Epoch %d] validation: acc=%.4f AVG_NB_f1=%.4f time: %.1fs', epoch, val_metrics[0].get()[1], scores['AVG_NB_f1'],
                      time.time() - tic)
-        with open(os.path.join(exp_dir, 'scores.txt'), 'a') as f:
-            f.write('%04d %.4f\n' % (epoch, scores['AVG_NB_f1']))
-        model.save_parameters(os.path.join(exp_dir, '%04d.params' % epoch))
+        if cli.is_main():  # one writer: ranks hold identical parameters after the summed-gradient update
+            with open(os.path.join(exp_dir, 'scores.txt'), 'a') as f:
+                f.write('%04d %.4f\n' % (epoch, scores['AVG_NB_f1']))
+            model.save_parameters(os.path.join(exp_dir, '%04d.params' % epoch))
+        cli.barrier()
 
 
 def main(_argv):
@@ -145,21 +165,32 @@ def main(_argv):
         model(x0)  # resolve deferred shapes before loading
         model.load_parameters(path, ctx=ctx)
         logging.info('Loaded model params: %s', path)
+    cli.broadcast_parameters(model)  # ranks start from rank 0's initialisation / checkpoint
     trainer = Trainer(model.collect_params(), 'sgd', {'learning_rate': FLAGS.lr, 'momentum': FLAGS.momentum, 'wd': FLAGS.wd})
-    train_model(model, train_set, val_set, trainer, SoftmaxCrossEntropyLoss(), ctx, exp_dir, start_epoch)
+    pooled_at_test = FLAGS.temp_pool in ('max', 'mean') and FLAGS.window > 1 and FLAGS.feats_model is None
+    if pooled_at_test:
+        # reference train.py:326,349-351: a max/mean-pooled model over a CNN is NOT trained here -- the frame-wise CNN comes from
+        # --backbone_from_id and is only wrapped in TemporalPooling for the test below (its windows are 5-D clips the frame model
+        # cannot train on)
+        logging.info('--temp_pool %s --window %d without --feats_model: no training, pooled evaluation only (train.py:326)',
+                     FLAGS.temp_pool, FLAGS.window)
+    else:
+        train_model(model, train_set, val_set, trainer, SoftmaxCrossEntropyLoss(), ctx, exp_dir, start_epoch)
     best = cli.best_epoch(exp_dir)
     if best is not None:
         model.load_parameters(os.path.join(exp_dir, '%04d.params' % best), ctx=ctx)
         logging.info('Testing best epoch %d', best)
     net = model
-    if FLAGS.temp_pool in ('max', 'mean') and FLAGS.window > 1 and FLAGS.feats_model is None:
+    if pooled_at_test:
         net = TemporalPooling(model, pool=FLAGS.temp_pool, num_classes=0, feats=False)  # train.py:349-351
     metrics = test_model(net, test_set, ctx, [Accuracy(), Accuracy('top5', top_k=5), PRF1(label_names=test_set.classes)],
                          FLAGS.batch_size)
-    print(metrics[2].mat.astype(int))
-    print('test %s: %.4f' % metrics[0].get())
-    for k, v in metrics[2].get()[-6:]:
-        print('test %s: %.4f' % (k, v))
+    if cli.is_main():
+        print(metrics[2].mat.astype(int))
+        print('test %s: %.4f' % metrics[0].get())
+        for k, v in metrics[2].get()[-6:]:
+            print('test %s: %.4f' % (k, v))
+    cli.shutdown()
 
 
 if __name__ == '__main__':

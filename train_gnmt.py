@@ -44,14 +44,22 @@ def train(data_train, data_val, data_test, model, loss_function, val_tgt_sentenc
         log_avg_loss, log_wc, nlog = 0.0, 0.0, 0
         log_start_time = time.time()
         for batch_id, (src_seq, tgt_seq, src_valid_length, tgt_valid_length) in enumerate(train_data_loader):
+            # loss = loss_function(...).mean() * (T - 1) / (tgt_valid_length - 1).mean(); loss.backward()   (:330-334)
+            # the normalisers are those of the GLOBAL batch; with --num_gpus N every process takes its contiguous shard of the
+            # sentences (split_and_load, train_gnmt.py:322-327) and Trainer.step sums the gradients over the ranks
+            n_global = tgt_seq.shape[0]
+            scale = float((tgt_seq.shape[1] - 1) / (tgt_valid_length - 1).cpu().numpy().mean())
+            src_seq, tgt_seq = cli.rank_shard(src_seq), cli.rank_shard(tgt_seq)
+            src_valid_length, tgt_valid_length = cli.rank_shard(src_valid_length), cli.rank_shard(tgt_valid_length)
+            if src_seq.shape[0] == 0:  # empty shard of a short batch: contribute zero gradients
+                trainer.step(1)
+                continue
             src_seq, tgt_seq = src_seq.to(ctx).float(), tgt_seq.to(ctx).float()
             src_valid_length, tgt_valid_length = src_valid_length.to(ctx), tgt_valid_length.to(ctx)
-            # loss = loss_function(...).mean() * (T - 1) / (tgt_valid_length - 1).mean(); loss.backward()   (:330-334)
-            scale = float((tgt_seq.shape[1] - 1) / (tgt_valid_length - 1).cpu().numpy().mean())
             with autograd.record():
                 out, _ = model(src_seq, tgt_seq[:, :-1], src_valid_length, tgt_valid_length - 1)
                 loss_vec = loss_function(out, tgt_seq[:, 1:], tgt_valid_length - 1)
-            autograd.backward([loss_vec], [torch.full_like(loss_vec, scale / loss_vec.shape[0])])
+            autograd.backward([loss_vec], [torch.full_like(loss_vec, scale / n_global)])
             trainer.step(1)
             step_loss = float(loss_vec.cpu().numpy().mean()) * scale
             log_avg_loss += step_loss
@@ -73,19 +81,24 @@ def train(data_train, data_val, data_test, model, loss_function, val_tgt_sentenc
         test_bleu_score, _, _, _, _ = compute_bleu([[r] for r in test_tgt_sentences], test_translation_out)
         logging.info('[Epoch %d] test Loss=%.4f, test ppl=%.4f, test bleu=%.2f', epoch_id, test_loss, np.exp(min(test_loss, 50)),
                      test_bleu_score * 100)
-        write_sentences(valid_translation_out, os.path.join(exp_dir, 'epoch%d_valid_out.txt' % epoch_id))
-        write_sentences(test_translation_out, os.path.join(exp_dir, 'epoch%d_test_out.txt' % epoch_id))
+        if cli.is_main():
+            write_sentences(valid_translation_out, os.path.join(exp_dir, 'epoch%d_valid_out.txt' % epoch_id))
+            write_sentences(test_translation_out, os.path.join(exp_dir, 'epoch%d_test_out.txt' % epoch_id))
 
         if valid_bleu_score > best_valid_bleu or not os.path.exists(os.path.join(exp_dir, 'valid_best.params')):
             best_valid_bleu = max(best_valid_bleu, valid_bleu_score)
             save_path = os.path.join(exp_dir, 'valid_best.params')
             logging.info('Save best parameters to %s', save_path)
-            model.save_parameters(save_path)
+            if cli.is_main():
+                model.save_parameters(save_path)
+        cli.barrier()
         if epoch_id + 1 >= (FLAGS.epochs * 2) // 3:
             new_lr = trainer.learning_rate * FLAGS.lr_update_factor
             logging.info('Learning rate change to %s', new_lr)
             trainer.set_learning_rate(new_lr)
-        model.save_parameters(os.path.join(exp_dir, '%04d.params' % epoch_id))
+        if cli.is_main():
+            model.save_parameters(os.path.join(exp_dir, '%04d.params' % epoch_id))
+        cli.barrier()
 
     # load and evaluate the best model
     if os.path.exists(os.path.join(exp_dir, 'valid_best.params')):
@@ -98,9 +111,11 @@ def train(data_train, data_val, data_test, model, loss_function, val_tgt_sentenc
     test_bleu_score, _, _, _, _ = compute_bleu([[r] for r in test_tgt_sentences], test_translation_out)
     logging.info('Best model test Loss=%.4f, test ppl=%.4f, test bleu=%.2f', test_loss, np.exp(min(test_loss, 50)),
                  test_bleu_score * 100)
-    write_sentences(valid_translation_out, os.path.join(exp_dir, 'best_valid_out.txt'))
-    write_sentences(test_translation_out, os.path.join(exp_dir, 'best_test_out.txt'))
-    print(get_comp_str(test_tgt_sentences[:2], test_translation_out[:2]))
+    if cli.is_main():
+        write_sentences(valid_translation_out, os.path.join(exp_dir, 'best_valid_out.txt'))
+        write_sentences(test_translation_out, os.path.join(exp_dir, 'best_test_out.txt'))
+        print(get_comp_str(test_tgt_sentences[:2], test_translation_out[:2]))
+    cli.shutdown()
 
 
 def main(_argv):
@@ -123,8 +138,9 @@ def main(_argv):
                           feats_model=FLAGS.feats_model, data_shape=FLAGS.data_shape, synthetic=syn)
     val_tgt_sentences = data_val.get_captions(split=True)
     test_tgt_sentences = data_test.get_captions(split=True)
-    write_sentences(val_tgt_sentences, os.path.join(exp_dir, 'val_gt.txt'))
-    write_sentences(test_tgt_sentences, os.path.join(exp_dir, 'test_gt.txt'))
+    if cli.is_main():
+        write_sentences(val_tgt_sentences, os.path.join(exp_dir, 'val_gt.txt'))
+        write_sentences(test_tgt_sentences, os.path.join(exp_dir, 'test_gt.txt'))
 
     embedding = None
     emb_path = os.path.join('data', FLAGS.emb_file) if FLAGS.emb_file else None
@@ -137,6 +153,7 @@ def main(_argv):
     if path is not None:
         model.load_parameters(path, ctx=ctx)
         logging.info('Loaded model params: %s', path)
+    cli.broadcast_parameters(model)
     translator = BeamSearchTranslator(model=model, beam_size=FLAGS.beam_size,
                                       scorer=BeamSearchScorer(alpha=FLAGS.lp_alpha, K=FLAGS.lp_k),
                                       max_length=FLAGS.tgt_max_len + 100)
