@@ -7,16 +7,22 @@
 // serial phases with a 256-row halo tile and was slower.  This version pipelines two tiles:
 //   * tile = 14 x 6 output pixels, halo 16 x 8 = 128 rows = ONE M=128 UMMA tile for the 1x1 (no second, mostly empty M tile);
 //   * the 1x1's A operand goes through TENSOR MEMORY as in tn_conv1x1_ts.cu: TMA (4-D box with zero-filled out-of-image pixels)
-//     -> 4 row-owning transformer warps (LDS.128, packed fp32 FFMA2, BN1 parameters from a shared-memory table) -> tcgen05.st
-//     into two TMEM slots -> tcgen05.mma with A from TMEM; the raw stage is released as soon as it has been read;
-//   * both accumulators are double-buffered in TMEM (2 x 128 + 2 x 96 columns) and the single MMA thread issues the 1x1 of tile
-//     t+1 BEFORE the 3x3 of tile t, so the tensor pipe works on the next tile while epilogue 1 turns tile t's accumulator into
-//     the bf16 bottleneck tile in shared memory (+BN2 shift, ReLU, zeros at image-border positions = the 3x3's padding);
+//     -> 8 row-owning transformer warps (LDS.128, packed fp32 FFMA2, BN1 parameters from a shared-memory table) -> tcgen05.st
+//     into four TMEM slots -> tcgen05.mma with A from TMEM; the raw stage is released as soon as it has been read;
+//   * the 1x1 accumulator is double-buffered in TMEM and the single MMA thread is a small SCHEDULER: it polls two in-order queues
+//     (1x1 K-chunks whose operand slot is full; 3x3 halves whose bottleneck half-tile is written) with non-blocking mbarrier
+//     tests and issues whatever is ready, so the 1x1 of tiles t+1, t+2 fills the tensor pipe while epilogue 1 turns tile t's
+//     accumulator into the bf16 bottleneck tile in shared memory (+BN2 shift, ReLU, zeros at image-border positions = the 3x3's
+//     padding) -- round 2's first version issued in a fixed order and measured 1.3x SLOWER than the two-kernel path because
+//     the 3x3 of tile t waited behind the transformers of tile t+1 (profiles/r2_fused_v1_launches.md);
+//   * the bottleneck tile is handed over per 64-channel HALF (own full/empty barriers): the 3x3 runs half 0 (12 UMMAs) then half 1,
+//     so epilogue 1 of the next tile rewrites half 0 while the tensor core still reads half 1;
 //   * separate warps for the two epilogues (8 for TMEM -> bottleneck tile, 4 for the 3x3 accumulator -> dx-tap combine ->
 //     256-bit stores into the concat buffer), so neither waits for the other;
-//   * 3x3 exactly as tn_conv3x3.cu: row-shifted descriptors for dy, the three dx taps stacked along N (96).
+//   * 3x3 as in tn_conv3x3.cu: row-shifted descriptors for dy, the three dx taps stacked along N (96).
 // 1x1 weights stay resident in shared memory for K <= 256 and are streamed with the activation chunks above that (block 2).
-// Shared memory: 3x3 weights 72 KB + bottleneck tile 32 KB + [W1 <= 64 KB] + ring.  TMEM: 512 columns.
+// Shared memory: 3x3 weights 72 KB + bottleneck tile 32 KB + [W1 <= 64 KB] + ring.
+// TMEM (512 columns): 1x1 accumulators 2 x 128, 3x3 accumulator 96, four 32-column operand slots.  22 warps.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,14 +35,14 @@ namespace tn {
 
 namespace {
 
-constexpr int kXfWarps = 4;     // warps 0-3   transformers (TMEM lane quarter = warp)
-constexpr int kEpi1Warp0 = 4;   // warps 4-11  epilogue 1 (quarter = warp & 3, 64-channel half = (warp - 4) >> 2)
+constexpr int kXfWarps = 8;     // warps 0-7   transformers (TMEM lane quarter = warp & 3, channel half = warp >> 2)
+constexpr int kEpi1Warp0 = 8;   // warps 8-15  epilogue 1 (quarter = warp & 3, 64-channel half = (warp - 8) >> 2)
 constexpr int kEpi1Warps = 8;
-constexpr int kEpi2Warp0 = 12;  // warps 12-15 epilogue 2 (quarter = warp & 3)
+constexpr int kEpi2Warp0 = 16;  // warps 16-19 epilogue 2 (quarter = warp & 3)
 constexpr int kEpi2Warps = 4;
-constexpr int kMmaWarp = 16;
-constexpr int kTmaWarp = 17;
-constexpr int kThreads = 18 * 32;
+constexpr int kMmaWarp = 20;
+constexpr int kTmaWarp = 21;
+constexpr int kThreads = 22 * 32;
 constexpr int kN1 = 128, kN2 = 96;
 constexpr int kABytes = 128 * 128;      // raw A stage: 128 halo rows x 64 bf16
 constexpr int kB1Bytes = kN1 * 128;     // one 64-wide K-chunk of the 1x1 weights
@@ -47,7 +53,8 @@ constexpr int kMaxNS = 6;
 constexpr int kMaxResident = 4;         // K <= 256 resident
 constexpr int kMaxChunks = 8;           // K <= 512
 constexpr int kTmemCols = 512;
-constexpr int kAcc1Col = 0, kAcc2Col = 256, kASlotCol = 448;  // acc1: 2 x 128, acc2: 2 x 96, A slots: 2 x 32
+constexpr int kAcc1Col = 0, kAcc2Col = 256, kASlotCol = 352;  // acc1: 2 x 128, acc2: 96, A slots: 4 x 32
+constexpr int kASlots = 4;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kTailBytes = kMaxChunks * 512 /*BN1 table*/ + 512 /*BN2 shift*/ + 2048 /*dx exchange*/ + 512 /*barriers*/;
 
@@ -107,15 +114,15 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
   float* xch = sShift2 + 128;                                 // [2 parity][2 halves][4 quarters][2][16]
   uint64_t* a_full = reinterpret_cast<uint64_t*>(xch + 512);  // [kMaxNS]
   uint64_t* a_empty = a_full + kMaxNS;                        // [kMaxNS]
-  uint64_t* t_full = a_empty + kMaxNS;                        // [2]
-  uint64_t* t_empty = t_full + 2;                             // [2]
-  uint64_t* acc1_full = t_empty + 2;                          // [2]
+  uint64_t* t_full = a_empty + kMaxNS;                        // [kASlots]
+  uint64_t* t_empty = t_full + kASlots;                       // [kASlots]
+  uint64_t* acc1_full = t_empty + kASlots;                    // [2]
   uint64_t* acc1_empty = acc1_full + 2;                       // [2]
-  uint64_t* acc2_full = acc1_empty + 2;                       // [2]
-  uint64_t* acc2_empty = acc2_full + 2;                       // [2]
-  uint64_t* halo_full = acc2_empty + 2;
-  uint64_t* halo_empty = halo_full + 1;
-  uint64_t* w_full = halo_empty + 1;
+  uint64_t* halo_full = acc1_empty + 2;                       // [2] per 64-channel half
+  uint64_t* halo_empty = halo_full + 2;                       // [2]
+  uint64_t* acc2_full = halo_empty + 2;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint64_t* w_full = acc2_empty + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -125,16 +132,18 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], kXfWarps + (resident ? 0 : 1));
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kASlots; ++i) {
       mbar_init(&t_full[i], kXfWarps);
       mbar_init(&t_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1);
       mbar_init(&acc1_empty[i], kEpi1Warps);
-      mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], kEpi2Warps);
+      mbar_init(&halo_full[i], kEpi1Warps / 2);
+      mbar_init(&halo_empty[i], 1);
     }
-    mbar_init(halo_full, kEpi1Warps);
-    mbar_init(halo_empty, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, kEpi2Warps);
     mbar_init(w_full, 1);
     mbar_fence_init();
   }
@@ -195,37 +204,35 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
     }
   } else if (warp < kXfWarps) {
     // ================================================================ transformers: smem (raw) -> BN1+ReLU -> TMEM
-    const int r = warp * 32 + lane;  // halo row == TMEM lane
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int hh = warp >> 2;  // channels [32hh, 32hh+32) of every 64-channel chunk
+    const int r = q * 32 + lane;  // halo row == TMEM lane
     const uint32_t row_off = static_cast<uint32_t>(r * 128);
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + kASlotCol;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kASlotCol + hh * 16;
     int stage = 0, slot = 0;
     uint32_t sphase = 0, tphase = 1;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&a_full[stage], sphase);
         const uint32_t a_row = smem_u32(sRing + stage * stage_bytes) + row_off;
-        const float4* par = sPar + c * 32;
-        uint32_t o[32];
+        const float4* par = sPar + c * 32 + hh * 16;
+        uint4 x[4];
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {  // two 32-channel halves (keeps the live register count down)
-          uint4 x[4];
+        for (int i = 0; i < 4; ++i) x[i] = lds128(a_row + (((4 * hh + i) ^ sw) << 4));
+        uint32_t o[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[i] = lds128(a_row + (((4 * hh + i) ^ sw) << 4));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int b = 16 * hh + 4 * i;
-            o[b + 0] = bn_relu2(x[i].x, par[b + 0]);
-            o[b + 1] = bn_relu2(x[i].y, par[b + 1]);
-            o[b + 2] = bn_relu2(x[i].z, par[b + 2]);
-            o[b + 3] = bn_relu2(x[i].w, par[b + 3]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          o[4 * i + 0] = bn_relu2(x[i].x, par[4 * i + 0]);
+          o[4 * i + 1] = bn_relu2(x[i].y, par[4 * i + 1]);
+          o[4 * i + 2] = bn_relu2(x[i].z, par[4 * i + 2]);
+          o[4 * i + 3] = bn_relu2(x[i].w, par[4 * i + 3]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_empty[stage]);  // raw stage read: the TMA warp may refill it (streamed: once the MMAs retire too)
         mbar_wait(&t_empty[slot], tphase);            // UMMAs that read this TMEM slot have retired
         tc_fence_after();
-        tmem_st32(t_lane + slot * 32, o);
+        tmem_st16(t_lane + slot * 32, o);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -234,32 +241,55 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
           stage = 0;
           sphase ^= 1u;
         }
-        slot ^= 1;
-        if (slot == 0) tphase ^= 1u;
+        if (++slot == kASlots) {
+          slot = 0;
+          tphase ^= 1u;
+        }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================================================================ MMA issuer: 1x1 of tile j+1 is issued before the 3x3 of tile j
+    // ================================================================ MMA issuer = scheduler over two in-order queues
     if (lane == 0) {
       const uint32_t idesc1 = umma_idesc_bf16_m128(kN1);
       const uint32_t idesc2 = umma_idesc_bf16_m128(kN2);
       mbar_wait(w_full, 0);
-      int slot = 0, bstage = 0;
+      const int n_my = (static_cast<int>(blockIdx.x) < p.num_tiles) ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      // queue 1: 1x1 K-chunks (tile j1, chunk c1);  queue 2: 3x3 halves (tile j2, half h2)
+      int j1 = 0, c1 = 0, slot = 0, bstage = 0, j2 = 0, h2 = 0;
       uint32_t tphase = 0, bphase = 0;
-      auto issue_mma1 = [&](int j) {
-        const int ab = j & 1;
-        mbar_wait(&acc1_empty[ab], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + kAcc1Col + ab * kN1;
-        for (int c = 0; c < nchunks; ++c) {
-          if (!resident) mbar_wait(&a_full[bstage], bphase);  // the stage's weight chunk has landed
-          mbar_wait(&t_full[slot], tphase);
+      const uint32_t h_base = smem_u32(sHalo);
+      const uint32_t w_base = smem_u32(sW2);
+      uint32_t idle = 0;
+      while (j2 < n_my) {
+        bool did = false;
+        // ---- 3x3 half (priority: it releases the bottleneck half-tile and the epilogues)
+        if (mbar_test(&halo_full[h2], j2 & 1) && (h2 == 1 || mbar_test(acc2_empty, (j2 & 1) ^ 1))) {
           tc_fence_after();
-          const int kv = min(64, p.Cin - c * 64);
+          const uint32_t d2 = tmem_base + kAcc2Col;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t da = umma_desc_sw128(h_base + h2 * kHaloHalf + dy * p.Wp * 128);
+            const uint64_t db = umma_desc_sw128(w_base + (dy * 2 + h2) * kW2Blob);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ss(d2, da + 2 * k, db + 2 * k, idesc2, (h2 | dy | k) ? 1u : 0u);
+          }
+          umma_commit(&halo_empty[h2]);
+          if (h2 == 1) {
+            umma_commit(acc2_full);
+            ++j2;
+          }
+          h2 ^= 1;
+          did = true;
+        } else if (j1 < n_my && (c1 > 0 || mbar_test(&acc1_empty[j1 & 1], ((j1 >> 1) & 1) ^ 1)) && mbar_test(&t_full[slot], tphase) &&
+                   (resident || mbar_test(&a_full[bstage], bphase))) {
+          // ---- one K-chunk of the 1x1 conv of tile j1
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + kAcc1Col + (j1 & 1) * kN1;
+          const int kv = min(64, p.Cin - c1 * 64);
           const uint32_t a_tmem = tmem_base + kASlotCol + slot * 32;
-          const uint32_t b_addr = resident ? smem_u32(sW1 + c * kB1Bytes) : smem_u32(sRing + bstage * stage_bytes + kABytes);
+          const uint32_t b_addr = resident ? smem_u32(sW1 + c1 * kB1Bytes) : smem_u32(sRing + bstage * stage_bytes + kABytes);
           const uint64_t db = umma_desc_sw128(b_addr);
-          for (int k = 0; k < kv / 16; ++k) umma_bf16_ts(d_tmem, a_tmem + 8 * k, db + 2 * k, idesc1, (c > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kv / 16; ++k) umma_bf16_ts(d_tmem, a_tmem + 8 * k, db + 2 * k, idesc1, (c1 > 0 || k > 0) ? 1u : 0u);
           umma_commit(&t_empty[slot]);
           if (!resident) {
             umma_commit(&a_empty[bstage]);
@@ -268,39 +298,23 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
               bphase ^= 1u;
             }
           }
-          slot ^= 1;
-          if (slot == 0) tphase ^= 1u;
-        }
-        umma_commit(&acc1_full[ab]);
-      };
-      int it = 0;
-      if (static_cast<int>(blockIdx.x) < p.num_tiles) issue_mma1(0);
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        if (t + static_cast<int>(gridDim.x) < p.num_tiles) issue_mma1(it + 1);
-        // ---- 3x3 conv of tile `it` from the bottleneck tile the epilogue-1 warps put in shared memory
-        const int ab = it & 1;
-        mbar_wait(halo_full, it & 1);
-        mbar_wait(&acc2_empty[ab], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d2 = tmem_base + kAcc2Col + ab * kN2;
-        const uint32_t h_base = smem_u32(sHalo);
-        const uint32_t w_base = smem_u32(sW2);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint64_t da = umma_desc_sw128(h_base + half * kHaloHalf + dy * p.Wp * 128);
-            const uint64_t db = umma_desc_sw128(w_base + (dy * 2 + half) * kW2Blob);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16_ss(d2, da + 2 * k, db + 2 * k, idesc2, acc);
-              acc = 1;
-            }
+          if (++slot == kASlots) {
+            slot = 0;
+            tphase ^= 1u;
           }
+          if (++c1 == nchunks) {
+            umma_commit(&acc1_full[j1 & 1]);
+            c1 = 0;
+            ++j1;
+          }
+          did = true;
         }
-        umma_commit(halo_empty);
-        umma_commit(&acc2_full[ab]);
+        if (did) {
+          idle = 0;
+        } else if (++idle > (1u << 26)) {
+          printf("tn: fused dense layer: MMA scheduler stalled (block %d, j1=%d c1=%d j2=%d h2=%d)\n", blockIdx.x, j1, c1, j2, h2);
+          __trap();
+        }
       }
     }
   } else if (warp >= kEpi1Warp0 && warp < kEpi1Warp0 + kEpi1Warps) {
@@ -320,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
       const bool interior = r < p.halo_rows && xp >= 1 && xp <= p.W && yp >= 1 && yp <= p.H;
       const int ab = it & 1;
       mbar_wait(&acc1_full[ab], (it >> 1) & 1);
-      mbar_wait(halo_empty, (it & 1) ^ 1);  // the previous tile's 3x3 MMAs no longer read the bottleneck tile
+      mbar_wait(&halo_empty[half], (it & 1) ^ 1);  // the previous tile's 3x3 MMAs no longer read this half of the bottleneck tile
       tc_fence_after();
 #pragma unroll
       for (int cbl = 0; cbl < 2; ++cbl) {
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(halo_full);
+      if (lane == 0) mbar_arrive(&halo_full[half]);
     }
   } else if (warp >= kEpi2Warp0 && warp < kEpi2Warp0 + kEpi2Warps) {
     // ================================================================ epilogue 2: 3x3 accumulator -> combine dx taps -> concat buffer
@@ -366,13 +380,12 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
       const int xo = xt * p.PW + xx - 1;  // output image column
       const bool valid = yy < p.TR && xx >= 1 && xx <= p.PW && xo < p.W && y < p.H;
       __nv_bfloat16* dst = p.out + (static_cast<size_t>(f * p.H + y) * p.W + xo) * p.out_cstride + p.out_coff;
-      const int ab = it & 1;
-      mbar_wait(&acc2_full[ab], (it >> 1) & 1);
+      mbar_wait(acc2_full, it & 1);
       tc_fence_after();
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t v0[16], v1[16], v2[16];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + kAcc2Col + ab * kN2 + hf * 16;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + kAcc2Col + hf * 16;
         tmem_ld16(taddr, v0);
         tmem_ld16(taddr + 32, v1);
         tmem_ld16(taddr + 64, v2);
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
         if (hf == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc2_empty[ab]);
+          if (lane == 0) mbar_arrive(acc2_empty);
         }
         float* x = xch + (it & 1) * 256 + hf * 128;
         if (lane == 31) {

@@ -47,6 +47,37 @@ def shard_range(n_items, rank, world):
     return lo, hi
 
 
+def balanced_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) whose sizes differ by at most one item (first n % world ranks get the extra one): the split used
+    for FRAME sharding, where any frame count must work (odd B*T, world sizes that do not divide it)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_ragged(local, n_total, world=None, group=None):
+    """All-gather row blocks of UNEQUAL size: rank r holds rows balanced_range(n_total, r, world) of a (n_total, ...) tensor.  Blocks
+    are padded to the largest one so that ONE all_gather_into_tensor moves them (NVSwitch collectives are latency-bound: one
+    padded exchange beats `world` broadcasts), then the padding rows are dropped.  Returns (n_total, ...) on every rank."""
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    per = -(-n_total // world)
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == per and n_total % world == 0:
+        return all_gather_rows(local, world, group)
+    padded = local.new_zeros((per,) + tail)
+    padded[:local.shape[0]].copy_(local)
+    out = local.new_empty((world * per,) + tail)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = balanced_range(n_total, r, world)
+        parts.append(out[r * per:r * per + (hi - lo)])
+    return torch.cat(parts, 0)
+
+
 def all_gather_rows(local, world=None, group=None):
     """All-gather equal-sized row blocks (n_local, D) -> (world*n_local, D) on every rank."""
     if world is None:
@@ -79,14 +110,19 @@ class ShardedCNNRNN(object):
     """Frame-sharded forward of a CNNRNN / TemporalPooling-style model: `model.td.model` is the per-frame
     feature extractor, `head(features (B,T,D)) -> logits` the temporal head.
 
-    forward(local_clips): local_clips is this rank's (B_local, T, 3, H, W) slice of the global batch; returns the
-    logits of the GLOBAL batch (B_local*world, C) on every rank.
+    forward(local_clips): local_clips is this rank's (B_local, T, 3, H, W) slice of the global batch -> logits of the GLOBAL
+    batch (B_local*world, C) on every rank.  forward_frames(frames_local, B, T): the general form -- this rank holds frames
+    balanced_range(B*T, rank, world) of the flattened (B*T, ...) batch, so shards may cut through clips and B need not divide.
+
+    Collectives per step: ONE all-gather of the bf16 per-frame features (the exchange north_star names), then every rank runs the
+    temporal head on ITS OWN clips only and the (B, C) logits are all-gathered (a few KB) -- the head is not recomputed W times.
     """
 
     def __init__(self, model, group=None):
         self.model = model
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
     def features_local(self, clips):
         B, T = clips.shape[:2]
@@ -104,23 +140,36 @@ class ShardedCNNRNN(object):
             y = ops.temporal_pool(feats_bt, 'mean' if m.pool == 'mean' else 'max')
         return m.classes(y) if m.classes else y
 
+    def head_sharded(self, gathered, B, T):
+        """gathered: (B*T, D) features of the global batch (bf16 twin or fp32) on every rank -> (B, C) global logits: each rank
+        runs the head on clips balanced_range(B, rank, world) and the logits are exchanged."""
+        D = gathered.shape[1]
+        lo, hi = balanced_range(B, self.rank, self.world)
+        mine = gathered[lo * T:hi * T].reshape(hi - lo, T, D)
+        if hi > lo:
+            logits = self.head(mine, None)
+        else:  # more ranks than clips: nothing to do here, but the exchange below needs the logit width
+            logits = self.head(gathered[:T].reshape(1, T, D), None)[:0]
+        return all_gather_ragged(logits.contiguous(), B, self.world, self.group)
+
+    def forward_frames(self, frames_local, B, T):
+        feats = self.model.td.model(frames_local)
+        twin = getattr(feats, "_tn_bf16", None)
+        src = twin if twin is not None else feats
+        if self.world == 1:
+            D = feats.shape[1]
+            return self.head(feats.reshape(B, T, D), None if twin is None else twin.reshape(B, T, D))
+        return self.head_sharded(all_gather_ragged(src, B * T, self.world, self.group), B, T)
+
     def forward(self, clips):
         B, T = clips.shape[:2]
         feats, twin = self.features_local(clips)
-        if self.world > 1:
-            # the only forward collective: per-frame features, exchanged in the dtype the head consumes
-            if twin is not None:
-                twin = all_gather_rows(twin, self.world, self.group)
-                feats = twin  # fp32 copy is not needed by the head
-            else:
-                feats = all_gather_rows(feats, self.world, self.group)
-        Bg = B * self.world
-        D = feats.shape[1]
-        f_bt = feats.reshape(Bg, T, D)
-        t_bt = None if twin is None else twin.reshape(Bg, T, D)
-        if twin is not None and self.world > 1:
-            return self.head(t_bt, None)
-        return self.head(f_bt, t_bt)
+        if self.world == 1:
+            D = feats.shape[1]
+            return self.head(feats.reshape(B, T, D), None if twin is None else twin.reshape(B, T, D))
+        # the only large forward collective: per-frame features, exchanged in the dtype the head consumes
+        src = twin if twin is not None else feats
+        return self.head_sharded(all_gather_rows(src, self.world, self.group), B * self.world, T)
 
     __call__ = forward
 
@@ -197,6 +246,7 @@ class HostPipeline(object):
         self._dev_bufs = None
         self._consumed = [None, None]   # per device buffer: event recorded after its last consumer kernel
         self._turn = 0
+        self._host_out = [None, None]   # pinned (B*world, C) result buffers, one per in-flight step
         self._model = {}                # (shape, dtype) -> (copy_ms, fixed_ms, compute_ms) per clip, measured once
 
     def _bufs(self, shape, dtype, device):
@@ -278,11 +328,12 @@ class HostPipeline(object):
         if self.sh.world > 1:
             src = twin if twin is not None else feats
             g = all_gather_rows(src, self.sh.world, self.sh.group)
-            Bg = B * self.sh.world
-            logits = self.sh.head(g.reshape(Bg, T, -1), None)
+            logits = self.sh.head_sharded(g, B * self.sh.world, T)
         else:
             logits = self.sh.head(feats.reshape(B, T, -1), None if twin is None else twin.reshape(B, T, -1))
-        host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+        host = self._host_out[slot]  # pinned result buffers are allocated once per slot, not per step (cudaHostAlloc is slow)
+        if host is None or host.shape != logits.shape or host.dtype != logits.dtype:
+            host = self._host_out[slot] = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
         host.copy_(logits, non_blocking=True)  # device -> host read of the step's result, queued behind the head
         fin = torch.cuda.Event()
         fin.record(main)

@@ -211,6 +211,66 @@ def test_gradient_sum_world_size_2_gloo(tmp_path):
     assert sum_gradients_across_ranks(g)[0] is g[0] and torch.equal(g[0], torch.ones(3))  # single process: untouched
 
 
+_GLOO_RAGGED_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from tennis_b200.parallel import all_gather_ragged, balanced_range, ShardedCNNRNN
+from tennis_b200 import cli
+from tennis_b200.metrics.vision import PRF1, Accuracy
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# (1) frame shards that do not divide: 7 clips x 5 frames = 35 rows over 3 ranks (12/12/11), and fewer rows than ranks
+for F in (35, 2, 3, 0 + world):
+    full = torch.arange(F * 4, dtype=torch.float32).reshape(F, 4)
+    lo, hi = balanced_range(F, rank, world)
+    got = all_gather_ragged(full[lo:hi].clone(), F, world)
+    assert torch.equal(got, full), (F, rank, got)
+# (2) the sharded head: every rank runs the head on its own clips only, logits are exchanged -> identical to one process
+class _Head(object):
+    classes = None
+    pool = 'max'
+class _Sh(ShardedCNNRNN):
+    def head(self, f_bt, twin=None):
+        return f_bt.max(dim=1).values[:, :3] * 2.0      # stand-in temporal head (B,T,D)->(B,3)
+sh = _Sh(_Head())
+B, T, D = 7, 5, 4
+g = torch.Generator().manual_seed(3)
+feats = torch.randn(B * T, D, generator=g)
+want = feats.reshape(B, T, D).max(dim=1).values[:, :3] * 2.0
+got = sh.head_sharded(feats, B, T)
+assert torch.equal(got, want), (rank, got, want)
+# (3) script plumbing: contiguous batch shards (last rank takes the remainder) and metric accumulators summed over ranks
+items = list(range(10))
+mine = cli.rank_shard(items)
+assert sum(dist_len for dist_len in [len(mine)]) >= 10 // world
+labels = torch.tensor(items) %% 3
+preds = torch.nn.functional.one_hot((torch.tensor(items) * 2) %% 3, 3).float()
+acc, prf = Accuracy(), PRF1(label_names=['a', 'b', 'c'])
+lo = items.index(mine[0]) if mine else 0
+sl = slice(lo, lo + len(mine))
+if mine:
+    acc.update([labels[sl]], [preds[sl]]); prf.update([labels[sl]], [preds[sl]])
+cli.sync_metrics([acc, prf])
+acc1, prf1 = Accuracy(), PRF1(label_names=['a', 'b', 'c'])
+acc1.update([labels], [preds]); prf1.update([labels], [preds])
+assert acc.get() == acc1.get() and (prf.mat == prf1.mat).all() and (prf.scores == prf1.scores).all()
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ragged_gather_sharded_head_and_metric_sync_gloo(tmp_path, world):
+    """Frame sharding for frame counts the world size does not divide, the head on the rank's own clips +
+    logits exchange, and the scripts' rank sharding / metric reduction, on gloo."""
+    script = tmp_path / "r.py"
+    script.write_text(_GLOO_RAGGED_WORKER % ROOT)
+    env = dict(os.environ, WORLD_SIZE=str(world), MASTER_PORT=str(29620 + world), MASTER_ADDR="127.0.0.1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+
+
 def test_sequence_reverse_index_matches_oracle():
     """models/captioning/train_graph.py::_reverse_index is SequenceReverse(use_sequence_length=True) as a gather (A.4)."""
     from oracle.captioning import _sequence_reverse
