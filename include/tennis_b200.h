@@ -171,6 +171,11 @@ int tn_gnmt_decode_step(tn_gnmt_t* g, const float* step_ids, const float* h_in, 
                         const float* mem, const int32_t* src_len, int rows_per_mem, int R, int T, float* logits,
                         float* h_out, float* c_out, float* att_out, void* workspace, size_t workspace_bytes,
                         tn_stream_t stream);
+/* GNMTDecoder.__call__(step_input, states) (gnmt.py:306-404): the decoder BLOCK's step.  step_emb device (R,E) already
+ * embedded inputs; out (R,H) = rnn_out of the last layer (no target projection); states as in tn_gnmt_decode_step. */
+int tn_gnmt_decoder_step(tn_gnmt_t* g, const float* step_emb, const float* h_in, const float* c_in, const float* att_in,
+                         const float* mem, const int32_t* src_len, int rows_per_mem, int R, int T, float* out, float* h_out,
+                         float* c_out, float* att_out, void* workspace, size_t workspace_bytes, tn_stream_t stream);
 /* Teacher-forced decode (model.decode_seq, gnmt.py:254-304; train_gnmt.py:280,331): tgt_ids device float (B,T_tgt),
  * tgt_valid_len device int32 (B) or NULL, h0/c0 (L,B,H), logits (B,T_tgt,V). */
 int tn_gnmt_decode_seq(tn_gnmt_t* g, const float* tgt_ids, const int32_t* tgt_valid_len, const float* h0,
@@ -260,6 +265,13 @@ int tn_avgpool_nhwc_forward(const float* x, long long ldx, int N, int H, int W, 
                             tn_stream_t stream); /* window = stride = (kh,kw), floor */
 int tn_avgpool_nhwc_backward(const float* dy, long long lddy, int N, int H, int W, int C, int kh, int kw, float* dx, long long lddx,
                              int accumulate, tn_stream_t stream);
+
+/* ------------------------------------------------------------------ device-side metrics (metrics/vision.py:27-58, train.py:427-431)
+ * logits device fp32 (N,C), labels device int32 (N).  conf device uint64 (C,C) indexed [label][argmax prediction] (first maximal
+ * class, like numpy argmax); hits device uint64 [3] = {top-1 hits, top-k hits (stable descending order: ties -> lower class
+ * index first), samples seen}.  Counters accumulate across calls; the host zeroes them to reset and reads them once per epoch. */
+int tn_metrics_update(const float* logits, const int32_t* labels, int N, int C, int top_k, unsigned long long* conf,
+                      unsigned long long* hits, tn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -290,12 +290,12 @@ int densenet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, in
     // in L2 and never reach HBM).  TN_CHUNK_B<1..4>=<frames> overrides; 0 = whole batch in one pass.
     const int cs = chunk_frames(b, n);
     if (halo) TN_CUDA(launch_zero_border(bott, cs, H + 2, W + 2, kBott, st));
-    // Dense blocks 1-2 (maps >= 28 wide): ONE fused kernel per dense layer, the bottleneck stays in shared memory
-    // (tn_dense_fused.cu) -- these layers are DRAM-bound and the bottleneck round trip is 40 % of their bytes.  Blocks 3-4 keep
-    // the two-kernel schedule: their 1x1 weights (K up to 992) would have to be re-streamed for every 84-pixel tile.
-    // TN_DENSE_FUSED_MIN_W=<min map width> overrides (a large value disables the fused path: the A/B and parity tests use it).
+    // OPT-IN (TN_DENSE_FUSED_MIN_W=<min map width>, e.g. 28 = dense blocks 1-2): ONE fused kernel per dense layer, the bottleneck
+    // stays in shared memory (tn_dense_fused.cu).  It removes a third of the step's DRAM bytes (92 -> 62 GB per 2048 frames) but
+    // measures slower than the two-kernel schedule: with 14 x 6-pixel tiles the 3x3's tensor-core operand reads (84 useful of 128
+    // accumulator rows) saturate the L1TEX data pipe (profiles/r2_fused_dense_layer.md).  The parity test keeps it honest.
     const char* fused_env = getenv("TN_DENSE_FUSED_MIN_W");
-    const int fused_min_w = fused_env ? atoi(fused_env) : 28;
+    const int fused_min_w = fused_env ? atoi(fused_env) : (1 << 30);
     const bool fused_block = dense_fused_supported(H, W) && W >= fused_min_w;
     // BN1+ReLU as a bf16 clamp (ConvGemmParams::pro_clamp) is opt-in: measured on B200 it is no faster than the fp32
     // scale/shift transform (the 1x1 kernels are bound by the memory system, not by the transformer warps) and its

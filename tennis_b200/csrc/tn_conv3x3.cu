@@ -170,25 +170,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ab]);  // accumulator drained: MMA warp may overwrite it
 
+      // dx-tap exchange across the four lane quarters: quarter qw publishes its last row's dx=-1 block (lane 31) and its first
+      // row's dx=+1 block (lane 0) with 4 x STS.128 by two active lanes, and reads its neighbours' rows the same way -- 8 + 4
+      // shared-memory wavefronts per warp and tile.  (Round 1 moved these 16 floats with scalar, lane-predicated LDS/STS inside the
+      // channel loop: 64 wavefronts per warp, 512 per tile = 22 % of the kernel's L1TEX data-pipe time, profiles/r2_smem_pipe.md.)
       float* x = xch + (it & 1) * 256 + hf * 128;
-      // publish the rows the neighbouring quarters need: my last row's dx=-1 part, my first row's dx=+1 part
-      if (lane == 31) {
+      if (lane == 0 || lane == 31) {
+        uint4* dst = reinterpret_cast<uint4*>(x + (qw * 2 + (lane == 0 ? 1 : 0)) * 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[(qw * 2 + 0) * 16 + j] = __uint_as_float(v0[j]);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[(qw * 2 + 1) * 16 + j] = __uint_as_float(v2[j]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 w;
+          w.x = (lane == 0) ? v2[4 * j4 + 0] : v0[4 * j4 + 0];
+          w.y = (lane == 0) ? v2[4 * j4 + 1] : v0[4 * j4 + 1];
+          w.z = (lane == 0) ? v2[4 * j4 + 2] : v0[4 * j4 + 2];
+          w.w = (lane == 0) ? v2[4 * j4 + 3] : v0[4 * j4 + 3];
+          dst[j4] = w;
+        }
       }
       if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       else asm volatile("bar.sync 2, 128;" ::: "memory");
+      float nb[16];  // lane 0: row above my quarter (dx=-1 block of quarter qw-1's last row); lane 31: row below (dx=+1 block)
+      const bool need_up = lane == 0 && qw > 0, need_dn = lane == 31 && qw < 3;
+      if (need_up || need_dn) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + (need_up ? ((qw - 1) * 2 + 0) : ((qw + 1) * 2 + 1)) * 16);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const uint4 w = src[j4];
+          nb[4 * j4 + 0] = __uint_as_float(w.x);
+          nb[4 * j4 + 1] = __uint_as_float(w.y);
+          nb[4 * j4 + 2] = __uint_as_float(w.z);
+          nb[4 * j4 + 3] = __uint_as_float(w.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) nb[j] = 0.f;
+      }
       float o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);      // D[r-1][j]
         float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);    // D[r+1][64+j]
-        if (lane == 0 && qw > 0) up = x[((qw - 1) * 2 + 0) * 16 + j];
-        if (lane == 31 && qw < 3) dn = x[((qw + 1) * 2 + 1) * 16 + j];
+        if (need_up) up = nb[j];
+        if (need_dn) dn = nb[j];
         o[j] = up + __uint_as_float(v1[j]) + dn;
       }
       const int q = t * kTileRows - 1 + r;

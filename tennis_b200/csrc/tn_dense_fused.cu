@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
         }
         if (did) {
           idle = 0;
-        } else if (++idle > (1u << 26)) {
+        } else if (__nanosleep(40), ++idle > (1u << 22)) {  // back off: every failed poll is a shared-memory access on the data pipe
           printf("tn: fused dense layer: MMA scheduler stalled (block %d, j1=%d c1=%d j2=%d h2=%d)\n", blockIdx.x, j1, c1, j2, h2);
           __trap();
         }
@@ -395,16 +395,37 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
           __syncwarp();
           if (lane == 0) mbar_arrive(acc2_empty);
         }
+        // dx-tap exchange across the lane quarters with vector stores/loads by the two boundary lanes (see tn_conv3x3.cu)
         float* x = xch + (it & 1) * 256 + hf * 128;
-        if (lane == 31) {
+        if (lane == 0 || lane == 31) {
+          uint4* xd = reinterpret_cast<uint4*>(x + (qw * 2 + (lane == 0 ? 1 : 0)) * 16);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[(qw * 2 + 0) * 16 + j] = __uint_as_float(v0[j]);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[(qw * 2 + 1) * 16 + j] = __uint_as_float(v2[j]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 w;
+            w.x = (lane == 0) ? v2[4 * j4 + 0] : v0[4 * j4 + 0];
+            w.y = (lane == 0) ? v2[4 * j4 + 1] : v0[4 * j4 + 1];
+            w.z = (lane == 0) ? v2[4 * j4 + 2] : v0[4 * j4 + 2];
+            w.w = (lane == 0) ? v2[4 * j4 + 3] : v0[4 * j4 + 3];
+            xd[j4] = w;
+          }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        float nb[16];
+        const bool need_up = lane == 0 && qw > 0, need_dn = lane == 31 && qw < 3;
+        if (need_up || need_dn) {
+          const uint4* src = reinterpret_cast<const uint4*>(x + (need_up ? ((qw - 1) * 2 + 0) : ((qw + 1) * 2 + 1)) * 16);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 w = src[j4];
+            nb[4 * j4 + 0] = __uint_as_float(w.x);
+            nb[4 * j4 + 1] = __uint_as_float(w.y);
+            nb[4 * j4 + 2] = __uint_as_float(w.z);
+            nb[4 * j4 + 3] = __uint_as_float(w.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) nb[j] = 0.f;
+        }
         uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
@@ -413,8 +434,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_layer_fused_kernel(const __
           for (int u = 0; u < 2; ++u) {
             float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j + u]), 1);    // D[r-1][dx=-1 block]
             float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j + u]), 1);  // D[r+1][dx=+1 block]
-            if (lane == 0 && qw > 0) up = x[((qw - 1) * 2 + 0) * 16 + j + u];
-            if (lane == 31 && qw < 3) dn = x[((qw + 1) * 2 + 1) * 16 + j + u];
+            if (need_up) up = nb[j + u];
+            if (need_dn) dn = nb[j + u];
             e[u] = up + __uint_as_float(v1[j + u]) + dn;
           }
           o[j >> 1] = pack_bf16x2(e[0], e[1]);

@@ -396,7 +396,8 @@ void carve_step(const tn_gnmt* g, int R, float* base, StepBufs* sb) {
 // One decoder step (gnmt.py:345-404) for R rows: reads state set `cur` through src_row, writes state set 1-cur.
 // Returns the device pointer of the last layer's output (R,H).
 const float* run_step(const tn_gnmt* g, const StepBufs& sb, int cur, const int* ids, const int* src_row, const float* mem,
-                      const int* src_len, int use_mask, int beam, int T, int R, cudaStream_t st, cudaError_t* err) {
+                      const int* src_len, int use_mask, int beam, int T, int R, cudaStream_t st, cudaError_t* err,
+                      const float* step_emb = nullptr) {
   const int H = g->H, nxt = 1 - cur;
   dim3 grid((R + 15) / 16, (H + 15) / 16);
   auto launch_cell = [&](int l, const float* xa, int Da, const int* xa_index, const float* xb, int Db, const int* xb_src,
@@ -411,7 +412,9 @@ const float* run_step(const tn_gnmt* g, const StepBufs& sb, int cur, const int* 
                                               g->WhhT[l], g->bih[l], g->bhh[l], sb.h[nxt][l], sb.c[nxt][l], out_res, R, H);
   };
   // layer 0: [embedding(step_input) ; previous attention vector]
-  launch_cell(0, g->embed, g->E, ids, sb.att[cur], H, src_row, nullptr);
+  // (step_emb: rows are the already embedded inputs -- the decoder BLOCK's own call, gnmt.py:306-404)
+  if (step_emb) launch_cell(0, step_emb, g->E, nullptr, sb.att[cur], H, src_row, nullptr);
+  else launch_cell(0, g->embed, g->E, ids, sb.att[cur], H, src_row, nullptr);
   {
     ProfScope ps(kProfOther, st);
     attn_kernel<<<R, 128, (2 * H + T) * sizeof(float), st>>>(sb.h[nxt][0], g->WqT, mem, src_len, beam, T, H, sb.att[nxt], use_mask);
@@ -510,6 +513,37 @@ int tn_gnmt_decode_step(tn_gnmt_t* g, const float* step_ids, const float* h_in, 
     proj_kernel<<<R, 128, (g->H + g->V) * sizeof(float), st>>>(outp, g->WpT, g->bp, logits, g->H, g->V, 0, nullptr, g->V);
   }
   TN_CUDA(cudaGetLastError());
+  for (int l = 0; l < g->L; ++l) {
+    TN_CUDA(cudaMemcpyAsync(h_out + l * n, sb.h[1][l], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (g->G == 4) TN_CUDA(cudaMemcpyAsync(c_out + l * n, sb.c[1][l], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  TN_CUDA(cudaMemcpyAsync(att_out, sb.att[1], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return TN_OK;
+}
+
+// GNMTDecoder.__call__(step_input, states) (gnmt.py:306-404): the decoder BLOCK's step -- inputs are already embedded
+// (R,E) rows, the output is the last layer's rnn_out (R,H) (no target projection).  States as in tn_gnmt_decode_step.
+int tn_gnmt_decoder_step(tn_gnmt_t* g, const float* step_emb, const float* h_in, const float* c_in, const float* att_in,
+                         const float* mem, const int32_t* src_len, int rows_per_mem, int R, int T, float* out, float* h_out,
+                         float* c_out, float* att_out, void* workspace, size_t workspace_bytes, tn_stream_t stream) {
+  if (!g || R < 0 || T <= 0 || rows_per_mem <= 0) return set_error(TN_ERR_INVALID, "bad decoder_step arguments");
+  if (R == 0) return TN_OK;
+  if (!step_emb || !h_in || !att_in || !mem || !out || !h_out || !att_out || !workspace || (g->G == 4 && (!c_in || !c_out)))
+    return set_error(TN_ERR_INVALID, "null device pointer");
+  if (workspace_bytes < tn_gnmt_workspace_bytes(g, R, 1)) return set_error(TN_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(R) * g->H;
+  StepBufs sb;
+  carve_step(g, R, static_cast<float*>(workspace), &sb);
+  for (int l = 0; l < g->L; ++l) {
+    TN_CUDA(cudaMemcpyAsync(sb.h[0][l], h_in + l * n, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (g->G == 4) TN_CUDA(cudaMemcpyAsync(sb.c[0][l], c_in + l * n, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  TN_CUDA(cudaMemcpyAsync(sb.att[0], att_in, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  cudaError_t e;
+  const float* outp = run_step(g, sb, 0, nullptr, nullptr, mem, src_len, src_len != nullptr, rows_per_mem, T, R, st, &e, step_emb);
+  TN_CUDA(e);
+  TN_CUDA(cudaMemcpyAsync(out, outp, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   for (int l = 0; l < g->L; ++l) {
     TN_CUDA(cudaMemcpyAsync(h_out + l * n, sb.h[1][l], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (g->G == 4) TN_CUDA(cudaMemcpyAsync(c_out + l * n, sb.c[1][l], n * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -166,6 +166,60 @@ class GNMTDecoder(Block):
             decoder_states.append(mem_masks)
         return decoder_states
 
+    # ---- the decoder block's own step API (reference gnmt.py:254-343); the scripts reach it through NMTModel, which fuses the
+    # target embedding and projection around the same device step
+    def _block_engine(self, E, device):
+        H = self._hidden_size
+        for i, c in enumerate(self.rnn_cells):
+            c.ensure(E + H if i == 0 else 2 * H, device)
+        plist = list(self.collect_params().values())
+        key = (device.index or 0, E) + tuple(p._version for p in plist)
+        if getattr(self, "_blk_engine", None) is None or self._blk_key != key:
+            z = torch.zeros  # embedding / projection are outside the block: one-row placeholders, never read by decoder_step
+            self._blk_engine = ops.GNMTDecoderEngine(
+                self._cell_type, H, E, 1, [c.weights() for c in self.rnn_cells], self.attention_cell.proj_query.weight.data(),
+                z(1, E), z(1, H), z(1), use_residual=self._use_residual, device=device.index or 0)
+            self._blk_key = key
+        return self._blk_engine
+
+    def __call__(self, step_input, states):
+        """One-step-ahead decoding (gnmt.py:306-404): step_input (B, C_in) embedded target -> (rnn_out (B,H),
+        [rnn_states, attention_vec, mem_value(, mem_masks)], [])."""
+        ops._require_cuda(step_input, states[2])
+        if self._dropout and getattr(self, "_training", False):
+            raise NotImplementedError("dropout > 0 is a training-time feature (training runs through GNMTTrainGraph)")
+        eng = self._block_engine(step_input.shape[1], states[2].device)
+        h, c = NMTModel._pack_states(states[0])
+        rows_per_mem = step_input.shape[0] // states[2].shape[0]
+        out, h2, c2, att2 = eng.decoder_step(step_input, h, c, states[1], states[2], NMTModel._mask_to_len(states), rows_per_mem)
+        return out, [NMTModel._unpack_states(h2, c2), att2] + list(states[2:]), []
+
+    forward = __call__
+
+    def decode_seq(self, inputs, states, valid_length=None):
+        """Decode the (embedded) decoder inputs step by step (gnmt.py:254-304): inputs (B, T, C_in) -> output (B, T, H) masked past
+        valid_length, states taken at each row's last valid step (_nested_sequence_last), []."""
+        B, T = inputs.shape[:2]
+        fixed = list(states[2:])
+        outs, rnn_l, att_l = [], [], []
+        for i in range(T):
+            o, states, _ = self(inputs[:, i].contiguous(), states)
+            outs.append(o)
+            rnn_l.append(states[0])
+            att_l.append(states[1])
+        output = torch.stack(outs, dim=1)
+        if valid_length is not None:
+            last = (valid_length.to(torch.int64) - 1).clamp(min=0)
+            rows = torch.arange(B, device=output.device)
+
+            def seq_last(per_step):
+                return torch.stack(per_step, dim=0)[last, rows]
+            rnn_states = [[seq_last([st[l][k] for st in rnn_l]) for k in range(len(rnn_l[0][l]))] for l in range(len(rnn_l[0]))]
+            states = [rnn_states, seq_last(att_l)] + fixed
+            keep = torch.arange(T, device=output.device).reshape(1, T, 1) < valid_length.reshape(B, 1, 1)
+            output = torch.where(keep, output, torch.zeros_like(output))  # SequenceMask
+        return output, states, []
+
 
 def get_gnmt_encoder_decoder(cell_type='lstm', attention_cell='scaled_luong', num_layers=2, num_bi_layers=1,
                              hidden_size=128, dropout=0.0, use_residual=False, i2h_weight_initializer=None,

@@ -350,6 +350,21 @@ class GNMTDecoderEngine:
                                         dptr(att2), ws, wsb, stream_ptr()))
         return logits, h2, c2, att2
 
+    def decoder_step(self, step_emb, h, c, att, mem, src_len, rows_per_mem=1):
+        """The decoder BLOCK's step (gnmt.py:306-404): step_emb (R,E) embedded inputs -> rnn_out (R,H), h', c', att'."""
+        _require_cuda(step_emb, h, c, att, mem, src_len)
+        R, T = step_emb.shape[0], mem.shape[1]
+        out = torch.empty((R, self.H), dtype=torch.float32, device=mem.device)
+        h2, att2 = torch.empty_like(h), torch.empty_like(att)
+        c2 = torch.empty_like(c) if c is not None else None
+        ws, wsb = self._workspace(R, 1, mem.device)
+        sl = self._i32(src_len)
+        check(lib().tn_gnmt_decoder_step(self._h, dptr(step_emb.float().contiguous()), dptr(h.contiguous()),
+                                         dptr(None if c is None else c.contiguous()), dptr(att.contiguous()),
+                                         dptr(mem.contiguous()), dptr(sl), rows_per_mem, R, T, dptr(out), dptr(h2), dptr(c2),
+                                         dptr(att2), ws, wsb, stream_ptr()))
+        return out, h2, c2, att2
+
     def decode_seq(self, tgt_ids, tgt_valid_len, h0, c0, mem, src_len):
         """tgt_ids (B,T_tgt) float; h0/c0 (L,B,H) -> logits (B,T_tgt,V)."""
         _require_cuda(tgt_ids, h0, c0, mem, src_len, tgt_valid_len)

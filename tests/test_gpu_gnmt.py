@@ -138,3 +138,97 @@ def test_masked_softmax_ce_matches_oracle():
     ref = C.masked_softmax_ce(pred, label, vl)
     out = MaskedSoftmaxCELoss()(pred.cuda(), label.cuda(), vl.cuda())
     assert (out.cpu() - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("cell", ["lstm", "gru"])
+def test_decoder_block_call_and_decode_seq(cell):
+    """GNMTDecoder.__call__(step_input, states) / decode_seq(inputs, states, valid_length) on the decoder BLOCK (reference
+    gnmt.py:254-404): embedded inputs in, rnn_out (B,T,H) out.  Projecting that output with tgt_proj must reproduce the oracle's
+    teacher-forced logits, and the returned states are the per-row last valid ones."""
+    from oracle import captioning as C
+    H, D, E, V = 128, 64, 100, 254
+    model, p, _ = _build(cell, H, D, E, V, 0.1)
+    B, T, Tt = 5, 11, 7
+    x, vl = C.synthetic_sources(B, T, D, seed=3)
+    g = torch.Generator().manual_seed(5)
+    tgt = torch.randint(0, V, (B, Tt), generator=g).float()
+    tvl = torch.tensor([7., 6., 4., 2., 7.])
+    with torch.no_grad():
+        ref = C.nmt_forward(p, x, tgt, vl, tvl, cell=cell, H=H)
+    enc_out, _ = model.encode(x.cuda(), valid_length=vl.cuda())
+    dstates = model.decoder.init_state_from_encoder(enc_out, vl.cuda())
+    emb = p["tgt_embed.weight"][tgt.long()].cuda()  # (B,Tt,E): the block takes embedded inputs
+    out, states, add = model.decoder.decode_seq(emb, dstates, tvl.cuda())
+    torch.cuda.synchronize()
+    assert out.shape == (B, Tt, H) and add == []
+    logits = out.cpu() @ p["tgt_proj.weight"].t() + p["tgt_proj.bias"]
+    assert (logits - ref).abs().max().item() < 1e-3
+    # one step through __call__ equals the first step of the fused model-level decode_step
+    o1, st1, _ = model.decoder(emb[:, 0].contiguous(), dstates)
+    lg, st_ref, _ = model.decode_step(tgt[:, 0].cuda(), dstates)
+    assert (o1.cpu() @ p["tgt_proj.weight"].t() + p["tgt_proj.bias"] - lg.cpu()).abs().max().item() < 1e-4
+    assert torch.equal(st1[1], st_ref[1]) and len(st1) == len(dstates)
+    # states after decode_seq: row b carries the state of ITS last valid step (gnmt.py:294-296)
+    s = dstates
+    per_step = []
+    for i in range(Tt):
+        _, s, _ = model.decoder(emb[:, i].contiguous(), s)
+        per_step.append(s[1])
+    for b in range(B):
+        assert torch.equal(states[1][b], per_step[int(tvl[b]) - 1][b])
+
+
+def test_beam_search_at_config4_shapes_matches_oracle():
+    """BASELINE configs[3]: B=32 sources x T_src<=224 x 1024-d features, LSTM H=128, V=254, beam 5 -- token ids and valid lengths
+    bit-exact against the oracle, scores within 1e-3 (VERDICT r1 weak #1e: this shape was only checked inside bench.py)."""
+    from oracle import captioning as C
+    from tennis_b200.models.captioning.gnmt import BeamSearchScorer
+    from tennis_b200.utils.translation import BeamSearchTranslator
+    cell, H, D, E, V, beam = "lstm", 128, 1024, 100, 254, 5
+    model, p, _ = _build(cell, H, D, E, V, 0.35, seed=4242)
+    B, T = 32, 224
+    x, vl = C.synthetic_sources(B, T, D, seed=77)
+    assert int(vl.max()) <= T and int(vl.min()) >= 1
+    with torch.no_grad():
+        s_ref, sc_ref, v_ref = C.translate(p, x, vl, cell=cell, H=H, beam=beam, max_length=150, bos=2, eos=3, alpha=1.0, K=5)
+    s, sc, v = BeamSearchTranslator(model, beam_size=beam, scorer=BeamSearchScorer(alpha=1.0, K=5), max_length=150).translate(
+        x.cuda(), vl.cuda())
+    torch.cuda.synchronize()
+    assert s.shape == s_ref.shape, (s.shape, s_ref.shape)
+    assert torch.equal(v.cpu(), v_ref)
+    assert torch.equal(s.cpu(), s_ref)
+    assert (sc.cpu() - sc_ref).abs().max().item() < 1e-3
+
+
+def test_beam_search_forced_ties_lowest_index_wins():
+    """Exact ties in the candidate scores: vocabulary entries 10 and 11 share their projection row and bias, so at every step the
+    two candidates of a beam have bit-identical log-probabilities.  The sampler's top-k must keep the LOWER flattened index
+    first (stable descending order) -- token 11 may only appear where 10 already took a slot -- and the result
+    must equal the oracle's."""
+    from oracle import captioning as C
+    from tennis_b200.models.captioning.gnmt import BeamSearchScorer
+    from tennis_b200.utils.translation import BeamSearchTranslator
+    cell, H, D, E, V, beam = "gru", 128, 64, 100, 30, 4
+    model, p, _ = _build(cell, H, D, E, V, 0.35, seed=99)
+    p = dict(p)
+    w, b = p["tgt_proj.weight"].clone(), p["tgt_proj.bias"].clone()
+    w[11], b[11] = w[10], b[10]
+    b[10] += 6.0  # make the tied pair the most likely continuation so that the tie decides the beams
+    b[11] += 6.0
+    emb = p["tgt_embed.weight"].clone()
+    emb[11] = emb[10]  # identical continuations as well: the tie persists down the beams
+    p["tgt_proj.weight"], p["tgt_proj.bias"], p["tgt_embed.weight"] = w, b, emb
+    for name, t in (("tgt_proj.weight", w), ("tgt_proj.bias", b), ("tgt_embed.weight", emb)):
+        prm = model.collect_params()[name]
+        prm._data = t.cuda()
+        prm._version += 1
+    x, vl = C.synthetic_sources(4, 9, D, seed=5)
+    with torch.no_grad():
+        s_ref, sc_ref, v_ref = C.translate(p, x, vl, cell=cell, H=H, beam=beam, max_length=12, bos=2, eos=3, alpha=1.0, K=5)
+    s, sc, v = BeamSearchTranslator(model, beam, BeamSearchScorer(1.0, 5), 12).translate(x.cuda(), vl.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(s.cpu(), s_ref) and torch.equal(v.cpu(), v_ref)
+    # the tie is real and is resolved towards the lower index: the best beam's first generated token is 10, never 11
+    assert (s_ref[:, 0, 1] == 10).all(), s_ref[:, 0, :4]
+    assert ((s_ref == 11).sum() > 0) and ((s_ref == 10).sum() >= (s_ref == 11).sum())
+    assert (sc.cpu() - sc_ref).abs().max().item() < 1e-3

@@ -20,6 +20,7 @@ from tennis_b200 import autograd as ag
 from tennis_b200 import cli
 from tennis_b200.dataset import TennisSet
 from tennis_b200.gluon import SoftmaxCrossEntropyLoss, Trainer
+from tennis_b200.metrics.device import DeviceMetrics
 from tennis_b200.metrics.vision import PRF1, Accuracy
 from tennis_b200.models.vision.definitions import TemporalPooling
 
@@ -45,17 +46,18 @@ def batches(dataset, batch_size, shuffle, seed):
 
 
 def test_model(net, dataset, ctx, metrics, batch_size):
-    """reference train.py:503-527."""
-    for m in metrics:
-        m.reset()
+    """reference train.py:503-527.  The metric counters are accumulated on the device (tennis_b200/metrics/device.py): no logits
+    leave the GPU and nothing synchronises per batch; `metrics` = [Accuracy, Accuracy(top5), PRF1] is filled at the end."""
+    dm = DeviceMetrics(dataset.classes, top_k=5, device=ctx)
     for batch in batches(dataset, batch_size, False, 0):
         if batch is None:
             continue
         data, labels, _ = batch
-        out = net(data.to(ctx, non_blocking=True)).cpu()
-        for m in metrics:
-            m.update([labels], [out])
-    return cli.sync_metrics(metrics)
+        dm.update(labels.to(ctx, non_blocking=True), net(data.to(ctx, non_blocking=True)))
+    got = dm.finish()  # one D2H read; summed over ranks
+    for m, g in zip(metrics, got):
+        m.__dict__.update(g.__dict__)
+    return metrics
 
 
 def save_features(net, dataset, ctx, batch_size):
