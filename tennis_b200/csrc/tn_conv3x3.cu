@@ -21,6 +21,7 @@
 // are double-buffered (2 x 96 columns) so the epilogue of tile i overlaps the MMAs of tile i+1; the halo tile is
 // double-buffered when it fits.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tn_common.h"
@@ -44,6 +45,7 @@ struct Conv3x3Params {
   int nbox, box_rows;         // TMA boxes per 64-channel half and their height (multiple of 8 when nbox == 2)
   int a_half_bytes;           // nbox*box_rows*128 rounded up to 1024
   int nbuf;                   // 1 or 2 halo buffers
+  int l2_ahead;               // TMA L2 prefetch distance in tiles (0 = off)
   int num_tiles;
   const uint8_t* wpack;       // 6 blobs [dy][half]
   __nv_bfloat16* out;
@@ -102,10 +104,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      // The two halo buffers (all that fits beside the 72 KB of weights) give one tile of look-ahead: ~61 KB in flight per SM is
+      // too little to cover the loaded DRAM latency (the MMA thread waited on a_full a third of the time, profiles/r1_ncu_summary.md).
+      // An L2 prefetch of the tiles p.l2_ahead iterations ahead costs no shared memory and turns the later TMA load into an L2 hit.
+      auto prefetch_tile = [&](int t) {
+        if (t >= p.num_tiles) return;
+        const int row0 = t * kTileRows - 1 - p.Wp;
+        for (int half = 0; half < 2; ++half)
+          for (int b = 0; b < p.nbox; ++b)
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap), "r"(half * 64),
+                         "r"(row0 + b * p.box_rows)
+                         : "memory");
+      };
+      for (int a = 1; a < p.l2_ahead; ++a) prefetch_tile(blockIdx.x + a * gridDim.x);
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int buf = it % p.nbuf;
         const int use = it / p.nbuf;
+        if (p.l2_ahead > 0) prefetch_tile(t + p.l2_ahead * gridDim.x);
         mbar_wait(&a_empty[buf], (use & 1) ^ 1);
         mbar_arrive_expect_tx(&a_full[buf], static_cast<uint32_t>(2 * p.nbox * p.box_rows * 128));
         const int row0 = t * kTileRows - 1 - p.Wp;
@@ -328,6 +344,11 @@ cudaError_t launch_conv3x3_halo(const Conv3x3Dev& cv, const __nv_bfloat16* in_pa
   const int fixed = kWBytes + 4096;
   p.nbuf = (fixed + 4 * p.a_half_bytes <= kMaxSmem) ? 2 : 1;
   p.num_tiles = (p.NR + kTileRows - 1) / kTileRows;
+  {
+    const char* e = getenv("TN_3X3_L2_AHEAD");  // read per call: tools/ab_bench.py sweeps it in-process
+    p.l2_ahead = e ? atoi(e) : 3;
+    if (p.l2_ahead < 0) p.l2_ahead = 0;
+  }
   p.wpack = cv.wpack;
   p.out = out;
   p.out_cstride = out_cstride;

@@ -204,13 +204,27 @@ struct StemPoolParams {
   int out_cstride;
 };
 constexpr int kPoolABuf = 6 * kStripBytes;
-constexpr int kPoolSmem = 1024 + kWBytes + 2 * kPoolABuf + 4096 /*exchange*/ + 256 + 256;
+// Weights of the fused-pool kernel, stacked along N: pixel strip s (0..5 = s2d rows 2py-1+s) feeds stem row j (0..2) with filter
+// row a = s - j, so for a fixed (s, b) ONE UMMA with B = [W[s-j][b] for every valid j] (N = 64, 128 or 192) updates all the
+// accumulators the strip contributes to.  24 UMMAs per tile instead of 48 of N = 64: the A operand (4 KB per UMMA) is read from
+// shared memory half as often -- 192 KB instead of 288 KB of operand reads per tile, at the same tensor time.
+//   s:        0    1     2      3      4    5
+//   j range:  0   0-1   0-2    0-2    1-2   2
+__host__ __device__ constexpr int pool_jmin(int s) { return s <= 3 ? 0 : s - 3; }
+__host__ __device__ constexpr int pool_jmax(int s) { return s <= 2 ? s : 2; }
+__host__ __device__ constexpr int pool_blob_off(int s) {  // byte offset of strip s's four (b) blobs
+  int rows = 0;
+  for (int i = 0; i < s; ++i) rows += 4 * 64 * (pool_jmax(i) - pool_jmin(i) + 1);
+  return rows * 32;
+}
+constexpr int kPoolWBytes = pool_blob_off(6);  // 96 KB
+constexpr int kPoolSmem = 1024 + kPoolWBytes + 2 * kPoolABuf + 4096 /*exchange*/ + 256 + 256;
 
 __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_constant__ CUtensorMap tmap, const StemPoolParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;
-  uint8_t* sA = sW + kWBytes;
+  uint8_t* sA = sW + kPoolWBytes;
   float* xch = reinterpret_cast<float*>(sA + 2 * kPoolABuf);  // [2 parity][2 halves][4 quarters][32]
   float* sShift = xch + 1024;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sShift + 64);
@@ -238,8 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
-    mbar_arrive_expect_tx(w_full, kWBytes);
-    bulk_g2s(sW, p.wpack, kWBytes, w_full);
+    mbar_arrive_expect_tx(w_full, kPoolWBytes);
+    for (int off = 0; off < kPoolWBytes; off += 32768) bulk_g2s(sW + off, p.wpack + off, 32768, w_full);
   }
   griddep_wait();
 
@@ -262,7 +276,6 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_m128(kN);
       mbar_wait(w_full, 0);
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -272,17 +285,21 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_con
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + buf * kPoolABuf);
         const uint32_t w_base = smem_u32(sW);
+        const uint32_t d_base = tmem_base + ab * 192;
+        // strip 2 first: its N = 192 UMMA touches all three accumulators, so it can initialise them (accumulate = 0)
+        constexpr int kOrder[6] = {2, 3, 1, 4, 0, 5};
+        uint32_t acc = 0;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {  // stem row 2py-1+j
-          const uint32_t d_tmem = tmem_base + ab * 192 + j * kN;
-          uint32_t acc = 0;
+        for (int i = 0; i < 6; ++i) {
+          const int s_ = kOrder[i];
+          const int nj = pool_jmax(s_) - pool_jmin(s_) + 1;
+          const uint32_t idesc = umma_idesc_bf16_m128(64 * nj);
+          const uint32_t d_tmem = d_base + pool_jmin(s_) * kN;
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              umma_bf16_ss(d_tmem, desc_sw32(a_base + (j + a) * kStripBytes + b * 32), desc_sw32(w_base + (a * 4 + b) * kTapBytes), idesc, acc);
-              acc = 1;
-            }
+          for (int b = 0; b < 4; ++b) {
+            umma_bf16_ss(d_tmem, desc_sw32(a_base + s_ * kStripBytes + b * 32), desc_sw32(w_base + pool_blob_off(s_) + b * nj * kTapBytes),
+                         idesc, acc);
+            acc = 1;
           }
         }
         umma_commit(&a_empty[buf]);
@@ -321,19 +338,34 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const __grid_con
 #pragma unroll
         for (int c = 0; c < 32; ++c) m[c] = -INFINITY;  // columns past the image edge never win the max
       }
+      // column 32*qw-1 (lane 31 of the previous lane quarter) through shared memory: 8 x STS.128 by one lane, 8 x LDS.128 by
+      // lane 0 (scalar, lane-predicated accesses inside the channel loop cost 64 wavefronts per warp and tile)
       float* xq = xch + (it & 1) * 256 + hf * 128;
       if (lane == 31) {
+        float4* dstq = reinterpret_cast<float4*>(xq + qw * 32);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) xq[qw * 32 + c] = m[c];
+        for (int c4 = 0; c4 < 8; ++c4) dstq[c4] = make_float4(m[4 * c4], m[4 * c4 + 1], m[4 * c4 + 2], m[4 * c4 + 3]);
       }
       if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       else asm volatile("bar.sync 2, 128;" ::: "memory");
+      float lq[32];
+      if (lane == 0 && qw > 0) {
+        const float4* srcq = reinterpret_cast<const float4*>(xq + (qw - 1) * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 w4 = srcq[c4];
+          lq[4 * c4] = w4.x; lq[4 * c4 + 1] = w4.y; lq[4 * c4 + 2] = w4.z; lq[4 * c4 + 3] = w4.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) lq[c] = -INFINITY;
+      }
       float o[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         float left = __shfl_up_sync(0xffffffffu, m[c], 1);
         const float right = __shfl_down_sync(0xffffffffu, m[c], 1);
-        if (lane == 0) left = (qw > 0) ? xq[(qw - 1) * 32 + c] : -INFINITY;
+        if (lane == 0) left = lq[c];
         o[c] = fmaxf(fmaxf(left, m[c]), right);  // lane 31 is an odd column: never a pooling centre
       }
       if ((x & 1) == 0 && x < p.Ws && (x >> 1) < p.Wp) {
@@ -387,7 +419,19 @@ bool make_stem(DeviceArena& arena, const float* w /* (64,3,7,7) */, const float*
             }
           }
   out->wpack = static_cast<const uint8_t*>(arena.upload(blob.data(), blob.size()));
-  return out->wpack != nullptr;
+  // stacked image for the fused-pool kernel: blob (s, b) = rows [(j - jmin) * 64 + n] = tap (a = s - j, b) of output channel n
+  std::vector<uint8_t> pool(kPoolWBytes, 0);
+  for (int s_ = 0; s_ < 6; ++s_) {
+    const int jmin = pool_jmin(s_), nj = pool_jmax(s_) - jmin + 1;
+    for (int b = 0; b < 4; ++b)
+      for (int j = jmin; j < jmin + nj; ++j) {
+        const int a = s_ - j;
+        memcpy(&pool[static_cast<size_t>(pool_blob_off(s_)) + static_cast<size_t>(b) * nj * kTapBytes + static_cast<size_t>(j - jmin) * kTapBytes],
+               &blob[static_cast<size_t>(a * 4 + b) * kTapBytes], kTapBytes);
+      }
+  }
+  out->wpack_pool = static_cast<const uint8_t*>(arena.upload(pool.data(), pool.size()));
+  return out->wpack != nullptr && out->wpack_pool != nullptr;
 }
 
 cudaError_t launch_stem_s2d(const StemDev& sd, const __nv_bfloat16* z, int n, int Hz, int Wz, int Ho, int Wo, const float* shift,
@@ -437,7 +481,7 @@ cudaError_t launch_stem_pool(const StemDev& sd, const __nv_bfloat16* z, int n, i
   StemPoolParams p;
   p.Hz = Hz; p.Wz = Wz; p.Hs = Hs; p.Ws = Ws; p.Hp = Hp; p.Wp = Wp;
   p.num_tiles = n * Hp;
-  p.wpack = sd.wpack;
+  p.wpack = sd.wpack_pool;
   p.shift = shift;
   p.out = out;
   p.out_cstride = out_cstride;

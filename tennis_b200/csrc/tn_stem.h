@@ -10,6 +10,7 @@ namespace tn {
 
 struct StemDev {
   const uint8_t* wpack = nullptr;  // 16 taps x (64 rows x 16 bf16), SWIZZLE_32B image, BN scale folded in
+  const uint8_t* wpack_pool = nullptr;  // the same taps stacked along N per pixel strip for the fused conv+pool kernel (96 KB)
 };
 
 bool make_stem(DeviceArena& arena, const float* w_64x3x7x7, const float* fold_scale, StemDev* out);
