@@ -32,6 +32,10 @@ typedef enum {
 
 enum { TN_ARCH_DENSENET121 = 0, TN_ARCH_RESNET18_V2 = 1 };
 enum { TN_FRAMES_F32_NCHW = 0, TN_FRAMES_U8_NHWC = 1 };
+/* arithmetic of the CNN forward: TN_PRECISION_BF16 = bf16 operands and activations, fp32 accumulation (speed path, logits within
+ * ~2e-2 of the fp32 reference); TN_PRECISION_SPLIT_BF16 = every tensor a (hi, lo) bf16 pair and every contraction three
+ * tensor-core products hi*Wh + hi*Wl + lo*Wh accumulated in fp32 (fp32-grade: logits within 1e-3, DenseNet-121 only) */
+enum { TN_PRECISION_BF16 = 0, TN_PRECISION_SPLIT_BF16 = 1 };
 enum { TN_CELL_GRU = 0, TN_CELL_LSTM = 1 };
 enum { TN_POOL_MAX = 0, TN_POOL_MEAN = 1 };
 
@@ -69,6 +73,9 @@ size_t tn_backbone_param_count(int arch);
 int tn_backbone_feature_dim(int arch, int h, int w); /* 1024 @224 / 4096 @512 (DenseNet), 512 (ResNet) */
 int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* params, size_t n_params);
 void tn_backbone_destroy(tn_backbone_t* bb);
+/* Select the arithmetic of subsequent tn_backbone_forward calls (and of tn_backbone_workspace_bytes, which grows in the split
+ * mode).  The reference computes in fp32 (train.py:204, evaluate.py:125); default TN_PRECISION_BF16. */
+int tn_backbone_set_precision(tn_backbone_t* bb, int mode);
 size_t tn_backbone_workspace_bytes(const tn_backbone_t* bb, int n_frames, int h, int w);
 /* frames: device, (n,3,h,w) fp32 NCHW already normalised (dataset.py:214-217 / train.py:142-147), or
  *         (n,h,w,3) uint8 NHWC raw pixels (ToTensor+Normalize is then applied on the device);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "tn_backbone_feature_dim": (c_int, [c_int, c_int, c_int]),
     "tn_backbone_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_size_t]),
     "tn_backbone_destroy": (None, [c_void_p]),
+    "tn_backbone_set_precision": (c_int, [c_void_p, c_int]),
     "tn_backbone_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "tn_backbone_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),

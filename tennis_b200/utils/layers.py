@@ -23,6 +23,8 @@ class TimeDistributed(Block):
         twin = getattr(y, "_tn_bf16", None)
         if twin is not None:
             out._tn_bf16 = twin.reshape((B, T) + tuple(twin.shape[1:]))
+        if getattr(y, "_tn_precise", False):  # fp32-grade features: downstream layers keep the split-bf16 arithmetic
+            out._tn_precise = True
         if getattr(y, "_tn_node", None) is not None:  # recorded (trainable model): the unfold is a view, pass the gradient through
             from .. import autograd
             autograd.tag(out, lambda g, shp=tuple(y.shape): g.reshape(shp), y)

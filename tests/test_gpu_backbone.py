@@ -4,8 +4,10 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-# bf16 activations + fp32 accumulation through 120 conv layers: tolerance on O(1) features, stated per test.
-FEAT_TOL = {"densenet121": 6e-2, "resnet18_v2": 6e-2}
+# bf16 activations + fp32 accumulation through 120 conv layers (speed path).  Measured on B200 (gpurun, round 2): max |cuda - oracle|
+# = 0.42 % of max|ref| for DenseNet-121 at 224 (0.28 on 67.9), 0.46 % at 512, 0.48 % / 0.43 % for ResNet-18 v2 at 224 / 512.  The
+# gate is ~2x the measured error.  The fp32-grade mode (tests/test_gpu_precise.py) is held to 1e-3 on the logits.
+FEAT_TOL = {"densenet121": 1e-2, "resnet18_v2": 1e-2}
 
 
 # 512 is the reference's default --data_shape (train.py:48; 4096-d DenseNet features, train.py:259); 231 gives odd feature maps
