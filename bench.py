@@ -28,10 +28,34 @@ sys.path.insert(0, ROOT)
 CLIPS_PER_GPU, T, SIZE, CLASSES, HIDDEN = 64, 32, 224, 11, 128
 ARCH = "densenet121"
 FLOP_PER_FRAME = 5.666e9  # conv layers of DenseNet-121 @224^2, SURVEY.md §8d / BASELINE.md §3
-# DRAM bytes (read + write) of the conv-kernel family (1x1 GEMMs, 3x3 halo kernel, stem, transition GEMMs) for ONE 2048-frame
-# step, summed from the ncu launch list of the same forward (profiles/r1_launches_final2.csv, summarised by
-# tools/launch_summary.py: dram__bytes_read.sum + dram__bytes_write.sum per launch).
-CONV_DRAM_BYTES_PER_STEP = 83.1e9
+RESNET_FLOP_PER_FRAME = 3.627e9  # ResNet-18 v2 @224^2
+TRAIN_GLOBAL_CLIPS = 256  # BASELINE.json configs[2]: 256 clips sharded over the GPUs of the run (strong scaling)
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources: profiles/conv_traffic.json is only valid for the kernels it was measured on."""
+    import hashlib
+    d = os.path.join(ROOT, "tennis_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def conv_traffic_per_frame():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per frame of the conv-kernel family, measured by
+    `python tools/measure_traffic.py` (an ncu launch list of one 2048-frame forward) and committed as profiles/conv_traffic.json
+    together with the hash of the kernel sources it was taken on.  A stale file (sources changed since) yields None."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if not os.path.exists(path):
+        return None, "profiles/conv_traffic.json missing: run tools/measure_traffic.py under ncu"
+    with open(path) as f:
+        d = json.load(f)
+    if d.get("kernel_source_hash") != kernel_source_hash():
+        return None, "profiles/conv_traffic.json is stale (kernel sources changed since it was measured): re-run tools/measure_traffic.py"
+    return float(d["conv_dram_bytes_per_frame"]), "measured by ncu on %d frames (%s), tools/measure_traffic.py" % (d["frames"], d["when"])
 WORKLOAD = "configs[1]: CNN+GRU event detector fwd, %d clips x %d frames @%dx%d per GPU" % (CLIPS_PER_GPU, T, SIZE, SIZE)
 
 
@@ -246,59 +270,111 @@ def run_ours(args, rank, world, local_rank):
     value = frames_total / (ms_total * 1e-3)
     finite = bool(torch.isfinite(logits).all().item())
 
-    # ---- end to end from pinned host memory (e2e)
+    # ---- end to end from pinned host memory (e2e): the call a user of the scripts makes -- decoded uint8 NHWC frames in pinned
+    # host memory -> HostPipeline.submit()/result() -> logits on the host.  Every step's H2D copy, the forward and the D2H read
+    # of the logits are inside the timed region; one step is kept in flight (the copy of step s+1 runs under the kernels of s).
+    def pipelined(pipe_, host):
+        pipe_.result(pipe_.submit(host))
+        pipe_.result(pipe_.submit(host))
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        pending = pipe_.submit(host)
+        out_ = None
+        for s_i in range(args.steps):
+            nxt = pipe_.submit(host) if s_i + 1 < args.steps else None
+            out_ = pipe_.result(pending)
+            pending = nxt
+        p1.record()
+        barrier()
+        tt = torch.tensor([p0.elapsed_time(p1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return frames_total / (tt.item() * 1e-3), out_
+
+    clips_u8 = torch.empty((B, T, SIZE, SIZE, 3), dtype=torch.uint8).pin_memory()
+    clips_u8.random_(0, 256, generator=g)
+    pipe_u8 = HostPipeline(sharded, chunks=3)  # with a step in flight the copy is already hidden: few, large chunks
+    e2e_u8_value, out8 = pipelined(pipe_u8, clips_u8)
+    d2h = out8.numel() * out8.element_size()
+    # the same frames as normalised fp32 NCHW tensors (the reference's in-memory format after its transforms): 4x the bytes over
+    # the host link, which then bounds the step (~55 GB/s per GPU, less when eight ranks share one host)
+    pipe_f32 = HostPipeline(sharded, chunks=3)
+    e2e_f32_value, _ = pipelined(pipe_f32, clips_host)
+    h2d = clips_host.numel() * clips_host.element_size()
+    # one blocking call per step (chunked H2D/compute overlap inside the call only)
     for _ in range(2):
-        out = pipe(clips_host)
+        pipe(clips_u8)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        out = pipe(clips_host)
+        pipe(clips_u8)
     f1.record()
     barrier()
     t2 = torch.tensor([f0.elapsed_time(f1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = frames_total / (t2.item() * 1e-3)
-    h2d = clips_host.numel() * clips_host.element_size()
-    d2h = out.numel() * out.element_size()
-    plan_f32 = dict(pipe.last_plan)
+    e2e_serial_value = frames_total / (t2.item() * 1e-3)
+    plan_u8 = dict(pipe.last_plan)
 
-    pipe2 = HostPipeline(sharded, chunks=3)  # with a step in flight the copy is already hidden: few, large chunks
-    pipe2.result(pipe2.submit(clips_host))
-    pipe2.result(pipe2.submit(clips_host))
-    # ---- same call split into submit()/result() with ONE step kept in flight (H2D of step s+1 under the kernels of s)
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    pending = pipe2.submit(clips_host)
-    for s_i in range(args.steps):
-        nxt = pipe2.submit(clips_host) if s_i + 1 < args.steps else None
-        out_p = pipe2.result(pending)
-        pending = nxt
-    p1.record()
-    barrier()
-    t2p = torch.tensor([p0.elapsed_time(p1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2p, op=dist.ReduceOp.MAX)
-    e2e_pipelined_value = frames_total / (t2p.item() * 1e-3)
+    extra = {}
+    # ---- fp32-grade mode (split-bf16, |logit - fp32 oracle| <= 1e-3: tests/test_gpu_precise.py), same workload, device-resident
+    try:
+        model.td.model.precision = "split_bf16"
+        for _ in range(2):
+            lp = sharded(clips_dev)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        psteps = max(2, min(args.steps, 5))
+        q0.record()
+        for _ in range(psteps):
+            lp = sharded(clips_dev)
+        q1.record()
+        barrier()
+        tp = torch.tensor([q0.elapsed_time(q1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        extra["precise"] = {
+            "mode": "split_bf16: every tensor a (hi, lo) bf16 pair, three tcgen05 products per contraction, fp32 accumulation",
+            "value": B * T * world * psteps / (tp.item() * 1e-3), "unit": "frames/s", "ms_per_step": tp.item() / psteps,
+            "tolerance": "max |logit - fp32 oracle| 2.7e-4 on 64 x 32 clips (<= 1e-3), argmax bit-exact (tests/test_gpu_precise.py)",
+            "max_abs_diff_vs_bf16_mode_logits": float((lp - logits).abs().max().item())}
+    except Exception as exc:  # the headline metric must still be reported
+        extra["precise"] = {"error": repr(exc)}
+    finally:
+        model.td.model.precision = "bf16"
 
-    # ---- same, with the frames as the decoder delivers them: uint8 NHWC on the host, ToTensor+Normalize on the device (K13)
-    clips_u8 = torch.empty((B, T, SIZE, SIZE, 3), dtype=torch.uint8).pin_memory()
-    clips_u8.random_(0, 256, generator=g)
-    for _ in range(2):
-        out8 = pipe(clips_u8)
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(args.steps):
-        out8 = pipe(clips_u8)
-    g1.record()
-    barrier()
-    t3 = torch.tensor([g0.elapsed_time(g1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-    e2e_u8_value = frames_total / (t3.item() * 1e-3)
+    # ---- strong scaling: BASELINE.json configs[2]/[4] shape the work as 256 clips in total over the GPUs of the run
+    try:
+        per = TRAIN_GLOBAL_CLIPS // world
+        strong_dev = clips_dev[:per] if per <= B else torch.cat([clips_dev] * (per // B), 0)
+        for _ in range(2):
+            sharded(strong_dev)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ssteps = max(2, min(args.steps, 5))
+        s0.record()
+        for _ in range(ssteps):
+            sharded(strong_dev)
+        s1.record()
+        barrier()
+        ts_ = torch.tensor([s0.elapsed_time(s1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        extra["strong_scaling"] = {"workload": "%d clips x %d frames in total, %d per GPU, forward" % (per * world, T, per),
+                                   "value": per * world * T * ssteps / (ts_.item() * 1e-3), "unit": "frames/s",
+                                   "ms_per_step": ts_.item() / ssteps, "scaling": "strong"}
+        del strong_dev
+    except Exception as exc:
+        extra["strong_scaling"] = {"error": repr(exc)}
+
+    # ---- configs[2]: CNN+GRU training step (fwd + bwd + SGD), 256 clips sharded over the GPUs, frozen backbone (the published
+    # 0042 setting: tensor-core forward, fused BPTT head, gradient all-reduce over NCCL in Trainer.step)
+    try:
+        extra["train_step"] = bench_train_step(model, clips_dev, device, world, barrier, args)
+    except Exception as exc:
+        extra["train_step"] = {"error": repr(exc)}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -307,6 +383,8 @@ def run_ours(args, rank, world, local_rank):
         flops = FLOP_PER_FRAME * B * T * args.steps  # algorithmic conv FLOPs executed by this rank's conv-GEMM launches
         achieved = flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        traffic_pf, traffic_note = conv_traffic_per_frame()
+        traffic_step = traffic_pf * B * T if traffic_pf is not None else None
         os.sched_setaffinity(0, full_affinity)  # the CPU baseline gets every host core again
         cpu = time_cpu_port(budget_s=12.0, clips_per_step=1, warmup=1)
         line = {
@@ -315,36 +393,43 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "arch": ARCH, "head": "BiGRU(128)+max+Dense(11)",
                        "global_clips": B * world, "frames_per_step": B * T * world,
-                       "parallelism": "frame-sharded dp%d, NCCL all-gather of features" % world,
+                       "parallelism": "frame-sharded dp%d: NCCL all-gather of bf16 features, temporal head on each rank's own clips, "
+                                      "logits all-gather" % world,
+                       "precision": "value/e2e: bf16 operands + fp32 accumulation (stated tolerance: logits within 2e-2 x max|logit| "
+                                    "of the fp32 reference arithmetic); the fp32-grade mode (<= 1e-3) is the `precise` object",
                        "l2": "inputs %.2f GB per GPU per step > 126 MB L2, no flush needed" % (h2d / 1e9),
                        "outputs_finite": finite, "numa_node_of_rank0": numa_node},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": CONV_DRAM_BYTES_PER_STEP,
-                         "traffic_note": "bytes per step (all conv-kernel launches of one step, like `achieved`), ncu capture "
-                                         "profiles/r1_launches_final2.csv; algorithmic minimum with dense-layer fusion 24.3 MB/frame "
-                                         "= 49.8 GB/step, so the unfused layer-by-layer schedule moves 1.7x that",
-                         "hbm_view": {"achieved_gbs": CONV_DRAM_BYTES_PER_STEP * args.steps / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0,
+                         "frac": achieved / peak, "traffic": traffic_step,
+                         "traffic_note": "DRAM bytes per step of all conv-kernel launches (like `achieved`): " + traffic_note +
+                                         "; algorithmic minimum with the bottleneck kept on chip 24.3 MB/frame = 49.8 GB/step",
+                         "hbm_view": {"achieved_gbs": (traffic_step * args.steps / (conv_ms * 1e-3) / 1e9) if (traffic_step and conv_ms > 0) else None,
                                       "peak_gbs": peaks.get("hbm_gbs")},
-                         "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), %d launches/step, %.2f ms/step summed over "
+                         "kernel": "conv kernel family (conv1x1_ts / conv3x3_halo / conv_gemm / stem_pool, all tcgen05), %d launches/step, %.2f ms/step summed over "
                                    "CUDA events on the launch stream" % (conv_launches // max(1, args.steps),
                                                                          conv_ms / max(1, args.steps)),
                          "peak_source": "bf16_tflops_sustained, " + peak_src,
                          "algorithmic": "5.666 GFLOP/frame x %d frames/step" % (B * T)},
             "cpu_baseline": {"value": cpu["frames_per_s"], "unit": "frames/s", "cores": cpu["cores"], "kind": "port",
                              "sample": "%d x 1 clip (32 frames) through the torch-fp32 CPU oracle of the same model" % cpu["steps"]},
-            "e2e": {"value": e2e_pipelined_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "pinned host fp32 clips (the reference's tensor format) -> HostPipeline.submit()/result(): every step's "
-                            "H2D copy, forward and logits D2H are inside the timed region, one step is kept in flight (the copy "
-                            "of step s+1 runs under the kernels of step s)"},
-            "e2e_serial": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                           "path": "same clips, one blocking call per step (chunked H2D/compute overlap inside the call only)",
-                           "chunk_plan": plan_f32},
-            "e2e_u8": {"value": e2e_u8_value, "unit": "frames/s", "h2d_bytes_per_step": clips_u8.numel(), "d2h_bytes_per_step": d2h,
-                       "path": "pinned host uint8 NHWC frames (decoder output), ToTensor+Normalize on the device"},
+            "e2e": {"value": e2e_u8_value, "unit": "frames/s", "h2d_bytes_per_step": clips_u8.numel(), "d2h_bytes_per_step": d2h,
+                    "path": "pinned host uint8 NHWC frames (what the decoder / dataset delivers) -> HostPipeline.submit()/result(): "
+                            "H2D copy, ToTensor+Normalize on the device, forward and logits D2H of every step are inside the timed "
+                            "region; one step is kept in flight (the copy of step s+1 runs under the kernels of step s)"},
+            "e2e_serial": {"value": e2e_serial_value, "unit": "frames/s", "h2d_bytes_per_step": clips_u8.numel(),
+                           "d2h_bytes_per_step": d2h, "path": "same uint8 frames, one blocking call per step", "chunk_plan": plan_u8},
+            "e2e_f32_host": {"value": e2e_f32_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                             "path": "normalised fp32 NCHW clips on the host (the reference's tensor format), submit()/result(); "
+                                     "host-link-bandwidth-bound: 602 KB per frame"},
             "gpu_launches": int(prof["conv_launches"] + prof["other_launches"]),
             "clocks": clocks,
         }
+        line.update(extra)
         if world == 1:
+            try:
+                line["resnet18_v2"] = bench_resnet18(clips_dev, device)
+            except Exception as exc:
+                line["resnet18_v2"] = {"error": repr(exc)}
             try:
                 line["gru_head"] = bench_gru_head(model, device)
             except Exception as exc:
@@ -533,6 +618,83 @@ def bench_training(device, steps=4):
     return out
 
 
+def bench_train_step(model, clips_dev, device, world, barrier, args, steps=3):
+    """BASELINE.json configs[2]: CNN+GRU event-detector TRAINING step (forward + backward + SGD) on 256 clips x 32 frames in total,
+    sharded over the GPUs of the run (reference train.py:410-424: split_and_load, per-device forward/backward, trainer.step sums
+    the gradients).  Frozen DenseNet-121 backbone -- the published CNN-RNN 0042 setting: tensor-core CNN forward, bi-GRU with saved
+    activations, softmax-CE, fused BPTT, SGD with momentum; Trainer.step all-reduces the head gradients over NCCL."""
+    import torch
+    import torch.distributed as dist
+    from tennis_b200 import autograd
+    from tennis_b200.gluon import SoftmaxCrossEntropyLoss, Trainer
+    per = TRAIN_GLOBAL_CLIPS // world
+    B0 = clips_dev.shape[0]
+    x = clips_dev[:per] if per <= B0 else torch.cat([clips_dev] * (per // B0), 0)
+    for prm in model.td.model.collect_params().values():
+        prm.grad_req = 'null'
+    labels = torch.arange(per, device=device) % CLASSES
+    loss_fn = SoftmaxCrossEntropyLoss()
+    tr = Trainer(model.collect_params(), 'sgd', {'learning_rate': 1e-3, 'momentum': 0.9, 'wd': 1e-4})
+
+    def step():
+        with autograd.record():
+            loss = loss_fn(model(x), labels)
+        autograd.backward([loss])
+        tr.step(TRAIN_GLOBAL_CLIPS)
+        return loss
+    for _ in range(2):
+        loss = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    lv = float(loss.float().mean().item())
+    return {"workload": "configs[2]: CNN+GRU training step (fwd+bwd+SGD), %d clips x %d frames in total, %d per GPU, frozen "
+                        "DenseNet-121 backbone, NCCL gradient all-reduce" % (per * world, T, per),
+            "ms_per_step": ms, "clips_per_s": per * world / (ms * 1e-3), "frames_per_s": per * world * T / (ms * 1e-3),
+            "scaling": "strong", "loss_finite": lv == lv}
+
+
+def bench_resnet18(clips_dev, device, steps=5):
+    """ResNet-18 v2 `features` (the reference's --backbone default, train.py:32) on the same 2048 frames: frames/s and the fraction of
+    the bf16 tensor roofline (3.627 GFLOP/frame)."""
+    import torch
+    from tennis_b200 import _lib, ops
+    from tennis_b200 import synthetic as O
+    p = O.synthetic_params("resnet18_v2", seed=1234)
+    bb = ops.Backbone("resnet18_v2", O.flatten_params("resnet18_v2", p), device=device.index or 0)
+    x = clips_dev.reshape((-1,) + tuple(clips_dev.shape[2:]))
+    for _ in range(2):
+        bb(x)
+    torch.cuda.synchronize()
+    _lib.profile_read(reset=True)
+    _lib.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = bb(x)
+    e1.record()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read(reset=True)
+    _lib.profile_enable(False)
+    ms = e0.elapsed_time(e1) / steps
+    peaks, peak_src = measured_peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    ach = RESNET_FLOP_PER_FRAME * x.shape[0] * steps / (prof["conv_ms"] * 1e-3) / 1e12 if prof["conv_ms"] > 0 else 0.0
+    return {"workload": "ResNet-18 v2 features, %d frames @%dx%d, forward, device-resident" % (x.shape[0], SIZE, SIZE),
+            "value": x.shape[0] / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "algorithmic": "3.627 GFLOP/frame", "peak_source": "bf16_tflops_sustained, " + peak_src},
+            "outputs_finite": bool(torch.isfinite(out).all().item())}
+
+
 def bench_gru_head(model, device, iters=20):
     """north_star secondary target: the Bi-GRU(128)+max+Dense head at 256 clips x 32 frames against the HBM roofline.
     Algorithmic bytes: features B*T*D*2 (bf16 as exchanged) + 3.56 MB weights + logits."""
@@ -562,7 +724,7 @@ def bench_gru_head(model, device, iters=20):
     return {"workload": "BiGRU(128)+max+Dense(11) on (256,32,1024) bf16 features", "us_per_call": us,
             "algorithmic_bytes": bytes_alg, "achieved_gbs": gbs, "hbm_peak_gbs": peaks["hbm_gbs"],
             "frac_of_hbm_roofline": gbs / peaks["hbm_gbs"],
-            "note": "32 serial recurrence steps: latency-bound (SURVEY.md 7.2-5), target 0.5 not met"}
+            "note": "32 serial recurrence steps: latency-bound (per-step breakdown: profiles/r2_gru_head.md)"}
 
 
 def main():

@@ -122,23 +122,28 @@ __global__ void __launch_bounds__(WREG ? G * kHReg / CL : 1024, 1) rnn_scan_kern
   if (CL > 1) cg::this_cluster().sync(); else __syncthreads();
 
   const int gx_row = p.ndir * GH;  // floats per (b,t) row of gx
-  for (int s = 0; s < maxlen; ++s) {
-    const float* hcur = hbuf + (s & 1) * H * kRB;
-    float* hnext_local = hbuf + ((s + 1) & 1) * H * kRB;
-
-    // prefetch this step's input-projection gates (latency hidden behind the matvec)
-    float gxv[IPT][G];
+  // input-projection gates of step s are loaded ONE STEP AHEAD (during step s-1): the ~1 us L2/HBM latency of these loads was
+  // on the critical path of every step when they were issued at the top of the step that consumes them
+  float gxv[IPT][G];
+  auto load_gx = [&](int s, float (&dst)[IPT][G]) {
 #pragma unroll
     for (int n = 0; n < IPT; ++n) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) gxv[n][g] = 0.f;
+      for (int g = 0; g < G; ++g) dst[n][g] = 0.f;
       if (it_b[n] >= 0 && s < it_len[n]) {
         const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : it_len[n] - 1 - s;
         const float* gp = p.gx + (static_cast<size_t>(b0 + it_b[n]) * p.T + pos) * gx_row + dir * GH + q * HS + it_u[n];
 #pragma unroll
-        for (int g = 0; g < G; ++g) gxv[n][g] = __ldg(gp + g * H);
+        for (int g = 0; g < G; ++g) dst[n][g] = __ldg(gp + g * H);
       }
     }
+  };
+  load_gx(0, gxv);
+  for (int s = 0; s < maxlen; ++s) {
+    const float* hcur = hbuf + (s & 1) * H * kRB;
+    float* hnext_local = hbuf + ((s + 1) & 1) * H * kRB;
+    float gxn[IPT][G];
+    load_gx(s + 1, gxn);  // s + 1 >= it_len -> zeros, no load
 
     // phase 1: hh[b][j] = sum_k Wt[k][j] * h[k][b] + bhh[j]
     float acc[kRB];
@@ -216,6 +221,11 @@ __global__ void __launch_bounds__(WREG ? G * kHReg / CL : 1024, 1) rnn_scan_kern
       } else {
         hnext_local[hidx] = hnew;
       }
+    }
+#pragma unroll
+    for (int n = 0; n < IPT; ++n) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) gxv[n][g] = gxn[n][g];
     }
     if (CL > 1) cg::this_cluster().sync(); else __syncthreads();
   }
