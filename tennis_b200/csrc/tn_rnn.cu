@@ -150,22 +150,35 @@ __global__ void __launch_bounds__(WREG ? G * kHReg / CL : 1024, 1) rnn_scan_kern
 #pragma unroll
     for (int b = 0; b < kRB; ++b) acc[b] = 0.f;
     if (WREG) {
-      float2 acc2[kRB];
+      // Two rows per pass, eight k per block: the four LDS.128 of a block are issued together and feed eight packed FFMA2 on
+      // four independent accumulator chains.  (With all four rows live next to the 128 weight registers ptxas had no room to
+      // hoist the loads: every FFMA2 waited ~30 cycles on its own LDS through one reused register -- 256 serial load->fma
+      // round trips = the whole 3.8 us step, profiles/r2_gru_head.md.)
 #pragma unroll
-      for (int b = 0; b < kRB; ++b) acc2[b] = make_float2(0.f, 0.f);
+      for (int bp = 0; bp < kRB; bp += 2) {
+        float2 a0 = make_float2(0.f, 0.f), a0b = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f), a1b = make_float2(0.f, 0.f);
+        const float* h0 = hcur + bp * kHReg;
+        const float* h1 = h0 + kHReg;
 #pragma unroll
-      for (int k = 0; k < kHReg; k += 4) {
-        const float2 w01 = make_float2(wreg[k], wreg[k + 1]);
-        const float2 w23 = make_float2(wreg[k + 2], wreg[k + 3]);
-#pragma unroll
-        for (int b = 0; b < kRB; ++b) {
-          const float4 hv = *reinterpret_cast<const float4*>(hcur + b * kHReg + k);
-          ffma2(acc2[b], w01, make_float2(hv.x, hv.y));
-          ffma2(acc2[b], w23, make_float2(hv.z, hv.w));
+        for (int k = 0; k < kHReg; k += 8) {
+          const float4 p0 = *reinterpret_cast<const float4*>(h0 + k);
+          const float4 p1 = *reinterpret_cast<const float4*>(h0 + k + 4);
+          const float4 q0 = *reinterpret_cast<const float4*>(h1 + k);
+          const float4 q1 = *reinterpret_cast<const float4*>(h1 + k + 4);
+          const float2 w01 = make_float2(wreg[k], wreg[k + 1]), w23 = make_float2(wreg[k + 2], wreg[k + 3]);
+          const float2 w45 = make_float2(wreg[k + 4], wreg[k + 5]), w67 = make_float2(wreg[k + 6], wreg[k + 7]);
+          ffma2(a0, w01, make_float2(p0.x, p0.y));
+          ffma2(a1, w01, make_float2(q0.x, q0.y));
+          ffma2(a0b, w23, make_float2(p0.z, p0.w));
+          ffma2(a1b, w23, make_float2(q0.z, q0.w));
+          ffma2(a0, w45, make_float2(p1.x, p1.y));
+          ffma2(a1, w45, make_float2(q1.x, q1.y));
+          ffma2(a0b, w67, make_float2(p1.z, p1.w));
+          ffma2(a1b, w67, make_float2(q1.z, q1.w));
         }
+        acc[bp] = (a0.x + a0.y) + (a0b.x + a0b.y);
+        acc[bp + 1] = (a1.x + a1.y) + (a1b.x + a1b.y);
       }
-#pragma unroll
-      for (int b = 0; b < kRB; ++b) acc[b] = acc2[b].x + acc2[b].y;
     } else {
 #pragma unroll 8
       for (int k = 0; k < H; ++k) {
@@ -242,6 +255,126 @@ __global__ void __launch_bounds__(WREG ? G * kHReg / CL : 1024, 1) rnn_scan_kern
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GRU, H = 128 (the event detector's head, definitions.py:94-96): K-split scan.
+// The 384-thread register-resident kernel above keeps 128 recurrent weights per thread; with 168 registers per thread ptxas has no
+// room left to software-pipeline the hidden-state loads, every FFMA2 waits ~30 cycles on its own LDS and a step takes ~7400
+// cycles at 25 % issue utilisation (ncu: stall_short_scoreboard 5.9 warps per issue, profiles/r2_gru_head.md).  Here a PAIR of
+// threads shares one gate column: 768 threads, 64 weights each (k in [64*half, 64*half+64)), the two partial dot products are
+// combined with one shuffle.  Twice the warps hide the shared-memory latency and the loads of a block are issued together.
+constexpr int kKS = 64;  // weights per thread
+__global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanParams p) {
+  constexpr int H = 128, G = 3, NJ = G * H, GH = G * H;
+  __shared__ __align__(16) float hbuf[2][kRB][H];
+  __shared__ __align__(16) float hh[kRB][NJ];
+  const int tid = threadIdx.x;
+  const int j = tid >> 1;        // gate column (g, u)
+  const int kh = tid & 1;        // which half of k
+  const int tile = blockIdx.x, dir = blockIdx.y;
+  const int b0 = tile * kRB;
+
+  float wreg[kKS];
+  {
+    const float* src = p.WhhT + static_cast<size_t>(dir) * H * GH + j + static_cast<size_t>(kh * kKS) * GH;
+#pragma unroll
+    for (int k = 0; k < kKS; ++k) wreg[k] = __ldg(src + static_cast<size_t>(k) * GH);
+  }
+  const float bhh = __ldg(p.bhh + static_cast<size_t>(dir) * GH + j);
+  for (int idx = tid; idx < kRB * H; idx += 768) {
+    const int b = idx / H, k = idx - b * H;
+    float v = 0.f;
+    if (p.h0 && b0 + b < p.B) v = p.h0[(static_cast<size_t>(dir) * p.B + b0 + b) * H + k];
+    hbuf[0][b][k] = v;
+    hbuf[1][b][k] = v;
+  }
+  // phase-2 item of this thread: (row b, unit u) for tid < kRB * H
+  const bool has_item = tid < kRB * H && b0 + tid / H < p.B;
+  const int ib = tid / H, iu = tid - ib * H;
+  int ilen = 0;
+  float ih = 0.f, imax = -INFINITY;
+  if (has_item) {
+    ilen = p.valid_len ? min(max(p.valid_len[b0 + ib], 0), p.T) : p.T;
+    if (p.h0) ih = p.h0[(static_cast<size_t>(dir) * p.B + b0 + ib) * H + iu];
+  }
+  int maxlen = 0;
+  for (int b = 0; b < kRB; ++b)
+    if (b0 + b < p.B) maxlen = max(maxlen, p.valid_len ? min(max(p.valid_len[b0 + b], 0), p.T) : p.T);
+  const int gx_row = p.ndir * GH;
+  auto load_gx = [&](int s, float (&dst)[G]) {
+    dst[0] = dst[1] = dst[2] = 0.f;
+    if (has_item && s < ilen) {
+      const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : ilen - 1 - s;
+      const float* gp = p.gx + (static_cast<size_t>(b0 + ib) * p.T + pos) * gx_row + dir * GH + iu;
+#pragma unroll
+      for (int g = 0; g < G; ++g) dst[g] = __ldg(gp + g * H);
+    }
+  };
+  float gxv[G];
+  load_gx(0, gxv);
+  __syncthreads();
+
+  for (int s = 0; s < maxlen; ++s) {
+    const float* hcur = &hbuf[s & 1][0][0] + kh * kKS;
+    float gxn[G];
+    load_gx(s + 1, gxn);  // next step's gates: their L2/HBM latency hides behind this step
+    float part[kRB];
+#pragma unroll
+    for (int bp = 0; bp < kRB; bp += 2) {
+      float2 a0 = make_float2(0.f, 0.f), a0b = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f), a1b = make_float2(0.f, 0.f);
+      const float* h0 = hcur + bp * H;
+      const float* h1 = h0 + H;
+#pragma unroll
+      for (int k = 0; k < kKS; k += 8) {
+        const float4 p0 = *reinterpret_cast<const float4*>(h0 + k);
+        const float4 p1 = *reinterpret_cast<const float4*>(h0 + k + 4);
+        const float4 q0 = *reinterpret_cast<const float4*>(h1 + k);
+        const float4 q1 = *reinterpret_cast<const float4*>(h1 + k + 4);
+        const float2 w01 = make_float2(wreg[k], wreg[k + 1]), w23 = make_float2(wreg[k + 2], wreg[k + 3]);
+        const float2 w45 = make_float2(wreg[k + 4], wreg[k + 5]), w67 = make_float2(wreg[k + 6], wreg[k + 7]);
+        ffma2(a0, w01, make_float2(p0.x, p0.y));
+        ffma2(a1, w01, make_float2(q0.x, q0.y));
+        ffma2(a0b, w23, make_float2(p0.z, p0.w));
+        ffma2(a1b, w23, make_float2(q0.z, q0.w));
+        ffma2(a0, w45, make_float2(p1.x, p1.y));
+        ffma2(a1, w45, make_float2(q1.x, q1.y));
+        ffma2(a0b, w67, make_float2(p1.z, p1.w));
+        ffma2(a1b, w67, make_float2(q1.z, q1.w));
+      }
+      part[bp] = (a0.x + a0.y) + (a0b.x + a0b.y);
+      part[bp + 1] = (a1.x + a1.y) + (a1b.x + a1b.y);
+    }
+#pragma unroll
+    for (int b = 0; b < kRB; ++b) part[b] += __shfl_xor_sync(0xffffffffu, part[b], 1);  // + the other half of k
+    // each thread of the pair publishes two of the four rows
+    hh[2 * kh][j] = part[2 * kh] + bhh;
+    hh[2 * kh + 1][j] = part[2 * kh + 1] + bhh;
+    __syncthreads();
+
+    float hnew = ih;
+    if (has_item && s < ilen) {
+      const float r = sigmoidf_(gxv[0] + hh[ib][iu]);
+      const float z = sigmoidf_(gxv[1] + hh[ib][H + iu]);
+      const float nn = tanhf(gxv[2] + r * hh[ib][2 * H + iu]);
+      hnew = (1.f - z) * nn + z * ih;
+      ih = hnew;
+      imax = fmaxf(imax, hnew);
+      if (p.y) {
+        const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : ilen - 1 - s;
+        p.y[(static_cast<size_t>(b0 + ib) * p.T + pos) * (p.ndir * H) + dir * H + iu] = hnew;
+      }
+    }
+    if (tid < kRB * H) hbuf[(s + 1) & 1][ib][iu] = hnew;  // frozen rows re-publish their last state
+#pragma unroll
+    for (int g = 0; g < G; ++g) gxv[g] = gxn[g];
+    __syncthreads();
+  }
+  if (has_item) {
+    const size_t o = static_cast<size_t>(b0 + ib) * (p.ndir * H) + dir * H + iu;
+    if (p.ymax) p.ymax[o] = imax;
+    if (p.h_final) p.h_final[(static_cast<size_t>(dir) * p.B + b0 + ib) * H + iu] = ih;
+  }
+}
+
 template <int G, int CL, bool WREG = false>
 cudaError_t launch_t(const RnnScanParams& p, cudaStream_t st) {
   const int HS = p.H / CL;
@@ -284,7 +417,13 @@ cudaError_t launch_rnn_scan(const RnnScanParams& p, cudaStream_t st) {
   const int cl = rnn_scan_cluster_size(G, p.H);
   if (cl < 0 || (G != 3 && G != 4)) return cudaErrorInvalidValue;
   ProfScope prof_scope(kProfOther, st);
-  // flagship hidden size: weights in registers (GRU: 384 threads x 128 weights; LSTM: a 2-CTA cluster of 256)
+  // flagship hidden size: weights in registers.  GRU: K-split pairs (768 threads x 64 weights); TN_RNN_NO_KSPLIT=1 selects the
+  // round-1 kernel (384 threads x 128 weights) for A/B.  LSTM: a 2-CTA cluster of 256 threads x 128 weights.
+  if (p.H == kHReg && G == 3 && !getenv("TN_RNN_NO_WREG") && !getenv("TN_RNN_NO_KSPLIT")) {
+    const int tiles = (p.B + kRB - 1) / kRB;
+    gru_scan_h128_kernel<<<dim3(tiles, p.ndir), 768, 0, st>>>(p);
+    return cudaGetLastError();
+  }
   if (p.H == kHReg && !getenv("TN_RNN_NO_WREG")) return G == 3 ? launch_t<3, 1, true>(p, st) : launch_t<4, 2, true>(p, st);
   if (G == 3) {
     switch (cl) {
