@@ -15,6 +15,8 @@
 
 #include <memory>
 
+#include <stdlib.h>
+
 #include "tn_common.h"
 
 namespace {
@@ -112,6 +114,103 @@ __global__ void __launch_bounds__(256) cell_kernel(const float* __restrict__ xa,
   }
   h_out[static_cast<size_t>(r) * H + u] = hnew;
   // layer output handed to the next layer / projection; with use_residual: out = h' + layer input (gnmt.py:395-396)
+  if (out_plus_res) out_plus_res[static_cast<size_t>(r) * H + u] = hnew + x[u];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Same cell step, weights staged in shared memory (default).  The kernel above walks K + H = 356..384 dependent global loads
+// per thread (one weight row per iteration): ncu shows 82 warps stalled on long_scoreboard per issue and 2.3 % issue utilisation,
+// ~400 us per launch -- 82 % of a decode step (profiles/r2_gnmt_decode.md).  Here a CTA owns 32 rows x 8 hidden units: it loads
+// its (K + H) x 8 x G weight slice ONCE (48 KB, coalesced 32-byte runs) and the 32 input/state rows, then every thread reads
+// weights as one LDS.128 per k (all gates of its unit) and its row as one LDS.128 per four k.
+template <int G>
+__global__ void __launch_bounds__(256) cell_kernel_v2(const float* __restrict__ xa, int Da, const int* __restrict__ xa_index,
+                                                      const float* __restrict__ xb, int Db, const int* __restrict__ xb_src,
+                                                      const float* __restrict__ h_in, const float* __restrict__ c_in,
+                                                      const int* __restrict__ src_row, const float* __restrict__ WihT,
+                                                      const float* __restrict__ WhhT, const float* __restrict__ bih,
+                                                      const float* __restrict__ bhh, float* __restrict__ h_out,
+                                                      float* __restrict__ c_out, float* __restrict__ out_plus_res,
+                                                      int R, int H) {
+  extern __shared__ __align__(16) float sm[];
+  const int K = Da + Db, KT = K + H, KTp = KT + 4;  // +4: the four rows of a warp start in different bank groups
+  float* sW = sm;              // [KT][8 units][4] (gate slot 3 unused for the GRU)
+  float* sx = sm + KT * 32;    // [32][KTp]: row = [xa_row ; xb_row ; h_row]
+  const int r0 = blockIdx.x * 32, u0 = blockIdx.y * 8;
+  const int tid = threadIdx.x;
+  const int GH = G * H;
+  for (int i = tid; i < KT * 8 * G; i += 256) {
+    const int uu = i & 7, g = (i >> 3) % G, k = i / (8 * G);
+    const float* W = k < K ? WihT + static_cast<size_t>(k) * GH : WhhT + static_cast<size_t>(k - K) * GH;
+    sW[(k * 8 + uu) * 4 + g] = __ldg(W + g * H + u0 + uu);
+  }
+  for (int i = tid; i < 32 * KT; i += 256) {
+    const int rr = i / KT, k = i - rr * KT;
+    const int r = r0 + rr;
+    float v = 0.f;
+    if (r < R) {
+      if (k < Da) v = xa[static_cast<size_t>(xa_index ? xa_index[r] : r) * Da + k];
+      else if (k < K) v = xb[static_cast<size_t>(xb_src ? xb_src[r] : r) * Db + (k - Da)];
+      else v = h_in[static_cast<size_t>(src_row ? src_row[r] : r) * H + (k - K)];
+    }
+    sx[rr * KTp + k] = v;
+  }
+  __syncthreads();
+  const int rr = tid >> 3, uu = tid & 7;
+  const int r = r0 + rr, u = u0 + uu;
+  if (r >= R || u >= H) return;
+  float ai[G], ah[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ai[g] = bih[g * H + u];
+    ah[g] = bhh[g * H + u];
+  }
+  const float* x = sx + rr * KTp;
+  const float4* w4 = reinterpret_cast<const float4*>(sW) + uu;  // [k * 8]
+  int k = 0;
+  for (; k + 4 <= K; k += 4) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + k);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 w = w4[(k + kk) * 8];
+      const float wg[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int g = 0; g < G; ++g) ai[g] = fmaf(xs[kk], wg[g], ai[g]);
+    }
+  }
+  for (; k < K; ++k) {
+    const float4 w = w4[k * 8];
+    const float wg[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int g = 0; g < G; ++g) ai[g] = fmaf(x[k], wg[g], ai[g]);
+  }
+  const float* hp = x + K;
+  for (int kh = 0; kh < H; ++kh) {  // (K is not always a multiple of 4: scalar row reads keep this loop alignment-free)
+    const float4 w = w4[(K + kh) * 8];
+    const float wg[4] = {w.x, w.y, w.z, w.w};
+    const float hv = hp[kh];
+#pragma unroll
+    for (int g = 0; g < G; ++g) ah[g] = fmaf(hv, wg[g], ah[g]);
+  }
+  const float hprev = hp[u];
+  float hnew;
+  if (G == 3) {  // GRU [r,z,n]
+    const float rg = sigmoidf_(ai[0] + ah[0]);
+    const float zg = sigmoidf_(ai[1] + ah[1]);
+    const float ng = tanhf(ai[2] + rg * ah[2]);
+    hnew = (1.f - zg) * ng + zg * hprev;
+  } else {  // LSTM [i,f,g,o]
+    const float cprev = c_in[static_cast<size_t>(src_row ? src_row[r] : r) * H + u];
+    const float ig = sigmoidf_(ai[0] + ah[0]);
+    const float fg = sigmoidf_(ai[1] + ah[1]);
+    const float gg = tanhf(ai[2] + ah[2]);
+    const float og = sigmoidf_(ai[G - 1] + ah[G - 1]);
+    const float cn = fg * cprev + ig * gg;
+    c_out[static_cast<size_t>(r) * H + u] = cn;
+    hnew = og * tanhf(cn);
+  }
+  h_out[static_cast<size_t>(r) * H + u] = hnew;
   if (out_plus_res) out_plus_res[static_cast<size_t>(r) * H + u] = hnew + x[u];
 }
 
@@ -400,10 +499,38 @@ const float* run_step(const tn_gnmt* g, const StepBufs& sb, int cur, const int* 
                       const float* step_emb = nullptr) {
   const int H = g->H, nxt = 1 - cur;
   dim3 grid((R + 15) / 16, (H + 15) / 16);
+  static const bool cell_v1 = getenv("TN_GNMT_CELL_V1") != nullptr;  // A/B: the round-1 global-memory cell kernel
   auto launch_cell = [&](int l, const float* xa, int Da, const int* xa_index, const float* xb, int Db, const int* xb_src,
                          float* out_res) {
-    const size_t smem = (16 * static_cast<size_t>(Da + Db) + 16 * H) * sizeof(float);
     ProfScope ps(kProfOther, st);
+    if (!cell_v1 && (H % 8) == 0) {
+      const int KT = Da + Db + H;
+      const size_t smem2 = (static_cast<size_t>(KT) * 32 + 32 * static_cast<size_t>(KT + 4)) * sizeof(float);
+      if (smem2 <= 200 * 1024) {
+        dim3 grid2((R + 31) / 32, H / 8);
+        if (g->G == 3) {
+          static size_t cfg3 = 0;
+          if (smem2 > cfg3) {
+            cudaFuncSetAttribute(cell_kernel_v2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2));
+            cfg3 = smem2;
+          }
+          cell_kernel_v2<3><<<grid2, 256, smem2, st>>>(xa, Da, xa_index, xb, Db, xb_src, sb.h[cur][l], sb.c[cur][l], src_row,
+                                                       g->WihT[l], g->WhhT[l], g->bih[l], g->bhh[l], sb.h[nxt][l], sb.c[nxt][l],
+                                                       out_res, R, H);
+        } else {
+          static size_t cfg4 = 0;
+          if (smem2 > cfg4) {
+            cudaFuncSetAttribute(cell_kernel_v2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2));
+            cfg4 = smem2;
+          }
+          cell_kernel_v2<4><<<grid2, 256, smem2, st>>>(xa, Da, xa_index, xb, Db, xb_src, sb.h[cur][l], sb.c[cur][l], src_row,
+                                                       g->WihT[l], g->WhhT[l], g->bih[l], g->bhh[l], sb.h[nxt][l], sb.c[nxt][l],
+                                                       out_res, R, H);
+        }
+        return;
+      }
+    }
+    const size_t smem = (16 * static_cast<size_t>(Da + Db) + 16 * H) * sizeof(float);
     if (g->G == 3)
       cell_kernel<3><<<grid, 256, smem, st>>>(xa, Da, xa_index, xb, Db, xb_src, sb.h[cur][l], sb.c[cur][l], src_row, g->WihT[l],
                                               g->WhhT[l], g->bih[l], g->bhh[l], sb.h[nxt][l], sb.c[nxt][l], out_res, R, H);

@@ -259,17 +259,18 @@ __global__ void __launch_bounds__(WREG ? G * kHReg / CL : 1024, 1) rnn_scan_kern
 // GRU, H = 128 (the event detector's head, definitions.py:94-96): K-split scan.
 // The 384-thread register-resident kernel above keeps 128 recurrent weights per thread; with 168 registers per thread ptxas has no
 // room left to software-pipeline the hidden-state loads, every FFMA2 waits ~30 cycles on its own LDS and a step takes ~7400
-// cycles at 25 % issue utilisation (ncu: stall_short_scoreboard 5.9 warps per issue, profiles/r2_gru_head.md).  Here a PAIR of
-// threads shares one gate column: 768 threads, 64 weights each (k in [64*half, 64*half+64)), the two partial dot products are
-// combined with one shuffle.  Twice the warps hide the shared-memory latency and the loads of a block are issued together.
+// cycles at 25 % issue utilisation (ncu: stall_short_scoreboard 5.9 warps per issue, profiles/r2_gru_head.md).  Here TWO threads
+// share one gate column: 768 threads, 64 weights each; threads 0-383 take k in [0,64), threads 384-767 k in [64,128) (warp-
+// uniform, so every hidden-state LDS.128 stays a single-address broadcast) and the two partial dot products meet in shared memory.
+// Twice the warps hide the shared-memory latency.
 constexpr int kKS = 64;  // weights per thread
 __global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanParams p) {
   constexpr int H = 128, G = 3, NJ = G * H, GH = G * H;
   __shared__ __align__(16) float hbuf[2][kRB][H];
-  __shared__ __align__(16) float hh[kRB][NJ];
+  __shared__ __align__(16) float hh[2][kRB][NJ];  // partial sums of the two k halves
   const int tid = threadIdx.x;
-  const int j = tid >> 1;        // gate column (g, u)
-  const int kh = tid & 1;        // which half of k
+  const int kh = tid >= NJ ? 1 : 0;  // which half of k (warp-uniform: 384 = 12 warps)
+  const int j = tid - kh * NJ;       // gate column (g, u)
   const int tile = blockIdx.x, dir = blockIdx.y;
   const int b0 = tile * kRB;
 
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanPara
 #pragma unroll
     for (int k = 0; k < kKS; ++k) wreg[k] = __ldg(src + static_cast<size_t>(k) * GH);
   }
-  const float bhh = __ldg(p.bhh + static_cast<size_t>(dir) * GH + j);
+  const float bhh = kh == 0 ? __ldg(p.bhh + static_cast<size_t>(dir) * GH + j) : 0.f;
   for (int idx = tid; idx < kRB * H; idx += 768) {
     const int b = idx / H, k = idx - b * H;
     float v = 0.f;
@@ -344,17 +345,14 @@ __global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanPara
       part[bp + 1] = (a1.x + a1.y) + (a1b.x + a1b.y);
     }
 #pragma unroll
-    for (int b = 0; b < kRB; ++b) part[b] += __shfl_xor_sync(0xffffffffu, part[b], 1);  // + the other half of k
-    // each thread of the pair publishes two of the four rows
-    hh[2 * kh][j] = part[2 * kh] + bhh;
-    hh[2 * kh + 1][j] = part[2 * kh + 1] + bhh;
+    for (int b = 0; b < kRB; ++b) hh[kh][b][j] = part[b] + bhh;
     __syncthreads();
 
     float hnew = ih;
     if (has_item && s < ilen) {
-      const float r = sigmoidf_(gxv[0] + hh[ib][iu]);
-      const float z = sigmoidf_(gxv[1] + hh[ib][H + iu]);
-      const float nn = tanhf(gxv[2] + r * hh[ib][2 * H + iu]);
+      const float r = sigmoidf_(gxv[0] + (hh[0][ib][iu] + hh[1][ib][iu]));
+      const float z = sigmoidf_(gxv[1] + (hh[0][ib][H + iu] + hh[1][ib][H + iu]));
+      const float nn = tanhf(gxv[2] + r * (hh[0][ib][2 * H + iu] + hh[1][ib][2 * H + iu]));
       hnew = (1.f - z) * nn + z * ih;
       ih = hnew;
       imax = fmaxf(imax, hnew);
