@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "tn_common.h"
 #include "tn_conv3x3.h"
 #include "tn_ptx.cuh"
@@ -38,13 +40,14 @@ constexpr int kN = 96;                 // 3 dx taps x 32 output channels
 constexpr int kWBlob = kN * 128;       // one (dy, half) weight blob: 96 rows x 64 bf16, swizzled
 constexpr int kWBytes = 6 * kWBlob;    // 72 KB
 constexpr int kTmemCols = 256;         // 2 x 96 used
+constexpr int kMaxBuf = 4;             // halo buffers: as many as fit beside the weights (2 at 56 x 56, 3 at 28 x 28, 4 below)
 
 struct Conv3x3Params {
   int Wp, HpWp, H, W, NR;     // padded width, padded rows per frame, unpadded dims, total padded rows
   int RH;                     // halo tile rows = 128 + 2*Wp
   int nbox, box_rows;         // TMA boxes per 64-channel half and their height (multiple of 8 when nbox == 2)
   int a_half_bytes;           // nbox*box_rows*128 rounded up to 1024
-  int nbuf;                   // 1 or 2 halo buffers
+  int nbuf;                   // 1..kMaxBuf halo buffers
   int l2_ahead;               // TMA L2 prefetch distance in tiles (0 = off)
   int num_tiles;
   const uint8_t* wpack;       // 6 blobs [dy][half]
@@ -67,13 +70,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   uint8_t* sA = smem + kWBytes;                         // nbuf x 2 halves x a_half_bytes
   const int a_buf_bytes = 2 * p.a_half_bytes;
   uint8_t* tail = sA + p.nbuf * a_buf_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);  // [2]
-  uint64_t* a_empty = a_full + 2;                        // [2]
-  uint64_t* acc_full = a_empty + 2;                      // [2]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);  // [kMaxBuf]
+  uint64_t* a_empty = a_full + kMaxBuf;                  // [kMaxBuf]
+  uint64_t* acc_full = a_empty + kMaxBuf;                // [2]
   uint64_t* acc_empty = acc_full + 2;                    // [2]
   uint64_t* w_full = acc_empty + 2;                      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* xch = reinterpret_cast<float*>(tail + 128);     // [2 parity][2 halves][4 quarters][2][16]
+  float* xch = reinterpret_cast<float*>(tail + 256);     // [2 parity][2 halves][4 quarters][2][16]
 
   const int tid = threadIdx.x;
   griddep_launch_dependents();
@@ -81,9 +84,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   const int lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxBuf; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 8);  // one arrive per epilogue warp
     }
@@ -342,7 +347,10 @@ cudaError_t launch_conv3x3_halo(const Conv3x3Dev& cv, const __nv_bfloat16* in_pa
   p.NR = static_cast<int>(NR);
   halo_geometry(W, &p.RH, &p.nbox, &p.box_rows, &p.a_half_bytes);
   const int fixed = kWBytes + 4096;
-  p.nbuf = (fixed + 4 * p.a_half_bytes <= kMaxSmem) ? 2 : 1;
+  p.nbuf = (kMaxSmem - fixed) / (2 * p.a_half_bytes);
+  if (p.nbuf > kMaxBuf) p.nbuf = kMaxBuf;
+  if (const char* e = getenv("TN_3X3_NBUF")) p.nbuf = std::max(1, std::min(p.nbuf, atoi(e)));  // A/B: cap the look-ahead
+  if (p.nbuf < 1) return cudaErrorInvalidValue;
   p.num_tiles = (p.NR + kTileRows - 1) / kTileRows;
   {
     const char* e = getenv("TN_3X3_L2_AHEAD");  // read per call: tools/ab_bench.py sweeps it in-process

@@ -317,6 +317,187 @@ __global__ void __launch_bounds__(128) proj_kernel(const float* __restrict__ out
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Attention, one block per SENTENCE (default when the memory fits in shared memory): the `beam` decoder rows of a sentence share
+// its encoder memory, so the (len x H) tile is staged in shared memory ONCE per block and serves the scores and the context of all
+// rows; the round-1 kernel above ran one block per row and walked the tile twice through dependent global loads (ncu: 89 us per
+// launch, long_scoreboard 11 warps per issue).  Same arithmetic: q = (x Wq^T) / sqrt(H), score_t = q . m_t (masked -> -1e18),
+// softmax over T, ctx = sum_t (w_t / sum) m_t.
+constexpr int kAttnMaxBeam = 8;
+__global__ void __launch_bounds__(256) attn_kernel_v2(const float* __restrict__ query, const float* __restrict__ WqT,
+                                                      const float* __restrict__ mem, const int* __restrict__ src_len, int beam,
+                                                      int T, int H, float* __restrict__ ctx, int use_mask) {
+  extern __shared__ __align__(16) float sm[];
+  float* smem_m = sm;                      // [T][H]
+  float* sx = smem_m + static_cast<size_t>(T) * H;  // [beam][H] raw queries
+  float* sqp = sx + beam * H;              // [2][beam][H] partial projections (two halves of k)
+  float* sq = sqp + 2 * beam * H;          // [beam][H] projected, scaled queries
+  float* ss = sq + beam * H;               // [beam][T] scores -> weights
+  float* sinv = ss + beam * T;             // [beam] 1 / sum
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = use_mask ? min(max(src_len[b], 0), T) : T;
+  const float* mb = mem + static_cast<size_t>(b) * T * H;
+  for (int i = tid; i < len * H / 4; i += 256)
+    reinterpret_cast<float4*>(smem_m)[i] = __ldg(reinterpret_cast<const float4*>(mb) + i);
+  for (int i = tid; i < beam * H; i += 256) sx[i] = query[static_cast<size_t>(b) * beam * H + i];
+  __syncthreads();
+  {  // query projection: thread (half of k, column j) for all rows of the sentence
+    const int kh = tid >> 7, j = tid & 127;
+    for (int j0 = j; j0 < H; j0 += 128) {
+      float a[kAttnMaxBeam];
+#pragma unroll
+      for (int i = 0; i < kAttnMaxBeam; ++i) a[i] = 0.f;
+      const int k0 = kh * (H / 2), k1 = k0 + H / 2;
+      for (int k = k0; k < k1; ++k) {
+        const float w = __ldg(WqT + static_cast<size_t>(k) * H + j0);
+#pragma unroll
+        for (int i = 0; i < kAttnMaxBeam; ++i)
+          if (i < beam) a[i] = fmaf(sx[i * H + k], w, a[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < kAttnMaxBeam; ++i)
+        if (i < beam) sqp[(kh * beam + i) * H + j0] = a[i];
+    }
+  }
+  __syncthreads();
+  const float inv = rsqrtf(static_cast<float>(H));
+  for (int i = tid; i < beam * H; i += 256) sq[i] = (sqp[i] + sqp[beam * H + i]) * inv;
+  __syncthreads();
+  // scores: one warp per (row, source position), lanes over H (conflict-free rows of the staged tile)
+  for (int it = warp; it < beam * T; it += 8) {
+    const int i = it / T, t = it - i * T;
+    float a = 0.f;
+    if (t < len)
+      for (int k = lane; k < H; k += 32) a = fmaf(sq[i * H + k], smem_m[static_cast<size_t>(t) * H + k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) ss[it] = (t < len) ? a : kNeg;
+  }
+  __syncthreads();
+  // softmax: warp i owns row i
+  for (int i = warp; i < beam; i += 8) {
+    float m = -INFINITY;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, ss[i * T + t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float e = expf(ss[i * T + t] - m);
+      ss[i * T + t] = e;
+      s += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sinv[i] = 1.f / s;
+  }
+  __syncthreads();
+  // context
+  for (int idx = tid; idx < beam * H; idx += 256) {
+    const int i = idx / H, j = idx - i * H;
+    const float invs = sinv[i];
+    float a = 0.f;
+    for (int t = 0; t < len; ++t) a = fmaf(ss[i * T + t] * invs, smem_m[static_cast<size_t>(t) * H + j], a);
+    ctx[(static_cast<size_t>(b) * beam + i) * H + j] = a;
+  }
+}
+
+// logits for a tile of 16 rows per block with the projection matrix staged in shared memory (default when H x V fits): the kernel
+// below runs one block per row and walks W^T through H dependent global loads per thread (ncu: 42 us per launch).
+__global__ void __launch_bounds__(256) proj_kernel_v2(const float* __restrict__ out, const float* __restrict__ WpT,
+                                                      const float* __restrict__ bp, float* __restrict__ logits, int R, int H, int V,
+                                                      int Vp, int log_softmax, const int* __restrict__ row_valid, size_t row_stride) {
+  extern __shared__ __align__(16) float sm[];
+  float* sW = sm;                                   // [H][Vp]
+  float* sx = sW + static_cast<size_t>(H) * Vp;     // [16][H]
+  float* sl = sx + 16 * H;                          // [16][Vp]
+  const int r0 = blockIdx.x * 16, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < H * Vp; i += 256) {
+    const int k = i / Vp, v = i - k * Vp;
+    sW[i] = v < V ? __ldg(WpT + static_cast<size_t>(k) * V + v) : 0.f;
+  }
+  for (int i = tid; i < 16 * H; i += 256) {
+    const int rr = i / H, r = r0 + rr;
+    const bool valid = r < R && (row_valid ? row_valid[r] != 0 : true);
+    sx[i] = valid ? out[static_cast<size_t>(r) * H + (i - rr * H)] : 0.f;
+  }
+  __syncthreads();
+  for (int v = tid; v < Vp; v += 256) {
+    float acc[16];
+    const float bias = v < V ? bp[v] : 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) acc[rr] = bias;
+    for (int k = 0; k < H; k += 4) {
+      const float w0 = sW[(k + 0) * Vp + v], w1 = sW[(k + 1) * Vp + v], w2 = sW[(k + 2) * Vp + v], w3 = sW[(k + 3) * Vp + v];
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const float4 xv = *reinterpret_cast<const float4*>(sx + rr * H + k);
+        acc[rr] = fmaf(xv.x, w0, acc[rr]);
+        acc[rr] = fmaf(xv.y, w1, acc[rr]);
+        acc[rr] = fmaf(xv.z, w2, acc[rr]);
+        acc[rr] = fmaf(xv.w, w3, acc[rr]);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) sl[rr * Vp + v] = acc[rr];
+  }
+  __syncthreads();
+  for (int rr = warp; rr < 16; rr += 8) {
+    const int r = r0 + rr;
+    if (r >= R) continue;
+    float* dst = logits + static_cast<size_t>(r) * row_stride;
+    const float* row = sl + rr * Vp;
+    if (!log_softmax) {
+      for (int v = lane; v < V; v += 32) dst[v] = row[v];
+      continue;
+    }
+    float m = -INFINITY;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(row[v] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = m + logf(s);
+    for (int v = lane; v < V; v += 32) dst[v] = row[v] - lse;
+  }
+}
+
+// host-side dispatch: staged kernels when their tiles fit in shared memory, the per-row kernels otherwise (TN_GNMT_ATTN_V1 /
+// TN_GNMT_PROJ_V1 force the latter for A/B)
+void launch_attn(const float* query, const float* WqT, const float* mem, const int* src_len, int beam, int T, int H, float* ctx,
+                 int use_mask, int R, cudaStream_t st) {
+  static const bool v1 = getenv("TN_GNMT_ATTN_V1") != nullptr;
+  const size_t smem2 = (static_cast<size_t>(T) * H + 4 * static_cast<size_t>(beam) * H + static_cast<size_t>(beam) * T + beam + 8) * sizeof(float);
+  if (!v1 && beam <= kAttnMaxBeam && (H % 4) == 0 && (H % 2) == 0 && R % beam == 0 && smem2 <= 200 * 1024) {
+    static size_t cfg = 0;
+    if (smem2 > cfg) {
+      cudaFuncSetAttribute(attn_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2));
+      cfg = smem2;
+    }
+    attn_kernel_v2<<<R / beam, 256, smem2, st>>>(query, WqT, mem, src_len, beam, T, H, ctx, use_mask);
+    return;
+  }
+  attn_kernel<<<R, 128, (2 * H + T) * sizeof(float), st>>>(query, WqT, mem, src_len, beam, T, H, ctx, use_mask);
+}
+
+void launch_proj(const float* out, const float* WpT, const float* bp, float* logits, int R, int H, int V, int log_softmax,
+                 const int* row_valid, size_t row_stride, cudaStream_t st) {
+  static const bool v1 = getenv("TN_GNMT_PROJ_V1") != nullptr;
+  const int Vp = (V + 31) / 32 * 32;
+  const size_t smem2 = (static_cast<size_t>(H) * Vp + 16 * static_cast<size_t>(H) + 16 * static_cast<size_t>(Vp)) * sizeof(float);
+  if (!v1 && (H % 4) == 0 && smem2 <= 200 * 1024) {
+    static size_t cfg = 0;
+    if (smem2 > cfg) {
+      cudaFuncSetAttribute(proj_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2));
+      cfg = smem2;
+    }
+    proj_kernel_v2<<<(R + 15) / 16, 256, smem2, st>>>(out, WpT, bp, logits, R, H, V, Vp, log_softmax, row_valid, row_stride);
+    return;
+  }
+  proj_kernel<<<R, 128, (H + V) * sizeof(float), st>>>(out, WpT, bp, logits, H, V, log_softmax, row_valid, row_stride);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // One beam-search update for sentence b = blockIdx.x (gluonnlp _BeamSearchStepUpdate, A.7).
 struct BeamState {
   float* scores;      // [B][beam]
@@ -544,7 +725,7 @@ const float* run_step(const tn_gnmt* g, const StepBufs& sb, int cur, const int* 
   else launch_cell(0, g->embed, g->E, ids, sb.att[cur], H, src_row, nullptr);
   {
     ProfScope ps(kProfOther, st);
-    attn_kernel<<<R, 128, (2 * H + T) * sizeof(float), st>>>(sb.h[nxt][0], g->WqT, mem, src_len, beam, T, H, sb.att[nxt], use_mask);
+    launch_attn(sb.h[nxt][0], g->WqT, mem, src_len, beam, T, H, sb.att[nxt], use_mask, R, st);
   }
   const float* prev = sb.h[nxt][0];
   for (int l = 1; l < g->L; ++l) {
@@ -637,7 +818,7 @@ int tn_gnmt_decode_step(tn_gnmt_t* g, const float* step_ids, const float* h_in, 
   TN_CUDA(e);
   {
     tn::ProfScope ps(tn::kProfOther, st);
-    proj_kernel<<<R, 128, (g->H + g->V) * sizeof(float), st>>>(outp, g->WpT, g->bp, logits, g->H, g->V, 0, nullptr, g->V);
+    launch_proj(outp, g->WpT, g->bp, logits, R, g->H, g->V, 0, nullptr, g->V, st);
   }
   TN_CUDA(cudaGetLastError());
   for (int l = 0; l < g->L; ++l) {
@@ -716,8 +897,7 @@ int tn_gnmt_decode_seq(tn_gnmt_t* g, const float* tgt_ids /*(B,T_tgt) float*/, c
     }
     {
       tn::ProfScope ps(tn::kProfOther, st);
-      proj_kernel<<<B, 128, (g->H + g->V) * sizeof(float), st>>>(outp, g->WpT, g->bp, logits + static_cast<size_t>(t) * g->V, g->H,
-                                                                 g->V, 0, rv, static_cast<size_t>(T_tgt) * g->V);
+      launch_proj(outp, g->WpT, g->bp, logits + static_cast<size_t>(t) * g->V, B, g->H, g->V, 0, rv, static_cast<size_t>(T_tgt) * g->V, st);
     }
     TN_CUDA(cudaGetLastError());
     cur = 1 - cur;
@@ -776,7 +956,7 @@ int tn_gnmt_beam_search(tn_gnmt_t* g, const float* mem, const int32_t* src_len, 
     TN_CUDA(e);
     {
       tn::ProfScope ps(tn::kProfOther, st);
-      proj_kernel<<<R, 128, (g->H + g->V) * sizeof(float), st>>>(outp, g->WpT, g->bp, logp, g->H, g->V, 1, nullptr, g->V);
+      launch_proj(outp, g->WpT, g->bp, logp, R, g->H, g->V, 1, nullptr, g->V, st);
     }
     {
       tn::ProfScope ps(tn::kProfOther, st);

@@ -37,7 +37,7 @@ for b, nl in enumerate(cfg):
     if b < 3:
         plan.append(("trans%d 1x1 K=%d" % (b + 1, c), hw[b] * (c // 2) * c))
         c //= 2
-conv = [per[i] for i in sorted(per) if any(t in per[i]['k'] for t in ('conv_gemm_kernel', 'conv3x3_halo_kernel', 'stem_pool_kernel'))]
+conv = [per[i] for i in sorted(per) if any(t in per[i]['k'] for t in ('conv_gemm_kernel', 'conv1x1_ts_kernel', 'conv3x3_halo_kernel', 'stem_pool_kernel'))]
 assert len(conv) == len(plan), (len(conv), len(plan))
 groups = {}
 for (name, macs), e in zip(plan, conv):
