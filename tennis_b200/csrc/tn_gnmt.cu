@@ -139,21 +139,48 @@ __global__ void __launch_bounds__(256) cell_kernel_v2(const float* __restrict__ 
   const int r0 = blockIdx.x * 32, u0 = blockIdx.y * 8;
   const int tid = threadIdx.x;
   const int GH = G * H;
-  for (int i = tid; i < KT * 8 * G; i += 256) {
-    const int uu = i & 7, g = (i >> 3) % G, k = i / (8 * G);
-    const float* W = k < K ? WihT + static_cast<size_t>(k) * GH : WhhT + static_cast<size_t>(k - K) * GH;
-    sW[(k * 8 + uu) * 4 + g] = __ldg(W + g * H + u0 + uu);
-  }
-  for (int i = tid; i < 32 * KT; i += 256) {
-    const int rr = i / KT, k = i - rr * KT;
-    const int r = r0 + rr;
-    float v = 0.f;
-    if (r < R) {
-      if (k < Da) v = xa[static_cast<size_t>(xa_index ? xa_index[r] : r) * Da + k];
-      else if (k < K) v = xb[static_cast<size_t>(xb_src ? xb_src[r] : r) * Db + (k - Da)];
-      else v = h_in[static_cast<size_t>(src_row ? src_row[r] : r) * H + (k - K)];
+  // staging loops: eight independent loads in flight per thread (a plain one-load-per-iteration loop exposes the full L2
+  // latency 48 times per thread and was 90 % of this kernel's time)
+  constexpr int U = 8;
+  for (int base = tid; base < KT * 8 * G; base += 256 * U) {
+    float v[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int i = base + q * 256;
+      v[q] = 0.f;
+      if (i < KT * 8 * G) {
+        const int uu = i & 7, g = (i >> 3) % G, k = i / (8 * G);
+        const float* W = k < K ? WihT + static_cast<size_t>(k) * GH : WhhT + static_cast<size_t>(k - K) * GH;
+        v[q] = __ldg(W + g * H + u0 + uu);
+      }
     }
-    sx[rr * KTp + k] = v;
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int i = base + q * 256;
+      if (i < KT * 8 * G) sW[((i / (8 * G)) * 8 + (i & 7)) * 4 + ((i >> 3) % G)] = v[q];
+    }
+  }
+  for (int base = tid; base < 32 * KT; base += 256 * U) {
+    float v[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int i = base + q * 256;
+      v[q] = 0.f;
+      if (i < 32 * KT) {
+        const int rr = i / KT, k = i - rr * KT;
+        const int r = r0 + rr;
+        if (r < R) {
+          if (k < Da) v[q] = xa[static_cast<size_t>(xa_index ? xa_index[r] : r) * Da + k];
+          else if (k < K) v[q] = xb[static_cast<size_t>(xb_src ? xb_src[r] : r) * Db + (k - Da)];
+          else v[q] = h_in[static_cast<size_t>(src_row ? src_row[r] : r) * H + (k - K)];
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int i = base + q * 256;
+      if (i < 32 * KT) sx[(i / KT) * KTp + (i % KT)] = v[q];
+    }
   }
   __syncthreads();
   const int rr = tid >> 3, uu = tid & 7;
@@ -327,8 +354,9 @@ __global__ void __launch_bounds__(256) attn_kernel_v2(const float* __restrict__ 
                                                       const float* __restrict__ mem, const int* __restrict__ src_len, int beam,
                                                       int T, int H, float* __restrict__ ctx, int use_mask) {
   extern __shared__ __align__(16) float sm[];
-  float* smem_m = sm;                      // [T][H]
-  float* sx = smem_m + static_cast<size_t>(T) * H;  // [beam][H] raw queries
+  const int Tp = T | 1;                    // odd row pitch: conflict-free along t (scores) and along h (context)
+  float* smT = sm;                         // [H][Tp]  encoder memory of this sentence, TRANSPOSED
+  float* sx = smT + static_cast<size_t>(H) * Tp;  // [beam][H] raw queries
   float* sqp = sx + beam * H;              // [2][beam][H] partial projections (two halves of k)
   float* sq = sqp + 2 * beam * H;          // [beam][H] projected, scaled queries
   float* ss = sq + beam * H;               // [beam][T] scores -> weights
@@ -336,22 +364,49 @@ __global__ void __launch_bounds__(256) attn_kernel_v2(const float* __restrict__ 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int len = use_mask ? min(max(src_len[b], 0), T) : T;
   const float* mb = mem + static_cast<size_t>(b) * T * H;
-  for (int i = tid; i < len * H / 4; i += 256)
-    reinterpret_cast<float4*>(smem_m)[i] = __ldg(reinterpret_cast<const float4*>(mb) + i);
+  {  // stage + transpose: 16-byte global loads (4 in flight per thread), scalar conflict-free shared stores
+    const int n4 = len * H / 4, H4 = H / 4;
+    for (int base = tid; base < n4; base += 256 * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = base + q * 256;
+        v[q] = i < n4 ? __ldg(reinterpret_cast<const float4*>(mb) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = base + q * 256;
+        if (i < n4) {
+          const int t = i / H4, k = (i - t * H4) * 4;
+          smT[(k + 0) * Tp + t] = v[q].x;
+          smT[(k + 1) * Tp + t] = v[q].y;
+          smT[(k + 2) * Tp + t] = v[q].z;
+          smT[(k + 3) * Tp + t] = v[q].w;
+        }
+      }
+    }
+  }
   for (int i = tid; i < beam * H; i += 256) sx[i] = query[static_cast<size_t>(b) * beam * H + i];
   __syncthreads();
-  {  // query projection: thread (half of k, column j) for all rows of the sentence
+  {  // query projection: thread (half of k, column j) for all rows of the sentence; 8 weight loads in flight
     const int kh = tid >> 7, j = tid & 127;
     for (int j0 = j; j0 < H; j0 += 128) {
       float a[kAttnMaxBeam];
 #pragma unroll
       for (int i = 0; i < kAttnMaxBeam; ++i) a[i] = 0.f;
       const int k0 = kh * (H / 2), k1 = k0 + H / 2;
-      for (int k = k0; k < k1; ++k) {
-        const float w = __ldg(WqT + static_cast<size_t>(k) * H + j0);
+      for (int k = k0; k < k1; k += 8) {
+        float w[8];
 #pragma unroll
-        for (int i = 0; i < kAttnMaxBeam; ++i)
-          if (i < beam) a[i] = fmaf(sx[i * H + k], w, a[i]);
+        for (int q = 0; q < 8; ++q) w[q] = (k + q < k1) ? __ldg(WqT + static_cast<size_t>(k + q) * H + j0) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (k + q < k1) {
+#pragma unroll
+            for (int i = 0; i < kAttnMaxBeam; ++i)
+              if (i < beam) a[i] = fmaf(sx[i * H + k + q], w[q], a[i]);
+          }
+        }
       }
 #pragma unroll
       for (int i = 0; i < kAttnMaxBeam; ++i)
@@ -362,15 +417,22 @@ __global__ void __launch_bounds__(256) attn_kernel_v2(const float* __restrict__ 
   const float inv = rsqrtf(static_cast<float>(H));
   for (int i = tid; i < beam * H; i += 256) sq[i] = (sqp[i] + sqp[beam * H + i]) * inv;
   __syncthreads();
-  // scores: one warp per (row, source position), lanes over H (conflict-free rows of the staged tile)
-  for (int it = warp; it < beam * T; it += 8) {
-    const int i = it / T, t = it - i * T;
-    float a = 0.f;
-    if (t < len)
-      for (int k = lane; k < H; k += 32) a = fmaf(sq[i * H + k], smem_m[static_cast<size_t>(t) * H + k], a);
+  // scores: one thread per source position, every beam row reuses the loaded memory element
+  for (int t = tid; t < T; t += 256) {
+    float a[kAttnMaxBeam];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) ss[it] = (t < len) ? a : kNeg;
+    for (int i = 0; i < kAttnMaxBeam; ++i) a[i] = 0.f;
+    if (t < len) {
+      for (int k = 0; k < H; ++k) {
+        const float m = smT[k * Tp + t];
+#pragma unroll
+        for (int i = 0; i < kAttnMaxBeam; ++i)
+          if (i < beam) a[i] = fmaf(sq[i * H + k], m, a[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kAttnMaxBeam; ++i)
+      if (i < beam) ss[i * T + t] = (t < len) ? a[i] : kNeg;  // where(mask, score, -1e18)
   }
   __syncthreads();
   // softmax: warp i owns row i
@@ -390,12 +452,14 @@ __global__ void __launch_bounds__(256) attn_kernel_v2(const float* __restrict__ 
     if (lane == 0) sinv[i] = 1.f / s;
   }
   __syncthreads();
-  // context
+  // context = sum_t softmax_t * mask_t * mem_t
   for (int idx = tid; idx < beam * H; idx += 256) {
     const int i = idx / H, j = idx - i * H;
     const float invs = sinv[i];
+    const float* mj = smT + j * Tp;
+    const float* wi = ss + i * T;
     float a = 0.f;
-    for (int t = 0; t < len; ++t) a = fmaf(ss[i * T + t] * invs, smem_m[static_cast<size_t>(t) * H + j], a);
+    for (int t = 0; t < len; ++t) a = fmaf(wi[t] * invs, mj[t], a);
     ctx[(static_cast<size_t>(b) * beam + i) * H + j] = a;
   }
 }
@@ -410,9 +474,17 @@ __global__ void __launch_bounds__(256) proj_kernel_v2(const float* __restrict__ 
   float* sx = sW + static_cast<size_t>(H) * Vp;     // [16][H]
   float* sl = sx + 16 * H;                          // [16][Vp]
   const int r0 = blockIdx.x * 16, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < H * Vp; i += 256) {
-    const int k = i / Vp, v = i - k * Vp;
-    sW[i] = v < V ? __ldg(WpT + static_cast<size_t>(k) * V + v) : 0.f;
+  for (int base = tid; base < H * Vp; base += 256 * 8) {  // eight loads in flight per thread
+    float w[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = base + q * 256;
+      const int k = i / Vp, v = i - k * Vp;
+      w[q] = (i < H * Vp && v < V) ? __ldg(WpT + static_cast<size_t>(k) * V + v) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (base + q * 256 < H * Vp) sW[base + q * 256] = w[q];
   }
   for (int i = tid; i < 16 * H; i += 256) {
     const int rr = i / H, r = r0 + rr;
@@ -467,7 +539,7 @@ __global__ void __launch_bounds__(256) proj_kernel_v2(const float* __restrict__ 
 void launch_attn(const float* query, const float* WqT, const float* mem, const int* src_len, int beam, int T, int H, float* ctx,
                  int use_mask, int R, cudaStream_t st) {
   static const bool v1 = getenv("TN_GNMT_ATTN_V1") != nullptr;
-  const size_t smem2 = (static_cast<size_t>(T) * H + 4 * static_cast<size_t>(beam) * H + static_cast<size_t>(beam) * T + beam + 8) * sizeof(float);
+  const size_t smem2 = (static_cast<size_t>(T | 1) * H + 4 * static_cast<size_t>(beam) * H + static_cast<size_t>(beam) * T + beam + 8) * sizeof(float);
   if (!v1 && beam <= kAttnMaxBeam && (H % 4) == 0 && (H % 2) == 0 && R % beam == 0 && smem2 <= 200 * 1024) {
     static size_t cfg = 0;
     if (smem2 > cfg) {

@@ -303,6 +303,11 @@ class Dropout(Block):
         self.rate = rate
 
     def forward(self, x):
+        from . import autograd
+        if self.rate > 0 and autograd.is_recording():
+            # the captioner's training graph applies its dropout masks itself (models/captioning/train_graph.py); a generic
+            # recorded use of this block would silently train WITHOUT dropout, so refuse instead
+            raise NotImplementedError("Dropout(rate=%g) under autograd.record() is only implemented inside GNMTTrainGraph" % self.rate)
         return x
 
 
@@ -329,17 +334,19 @@ class Dense(Block):
             self.weight.reset_ctx(x.device)
         y = ops.dense(x, self.weight.data(), None if self.bias is None else self.bias.data())
         from . import autograd
-        if autograd.is_recording() and lead is None:
+        out = y if lead is None else y.reshape(tuple(lead) + (self._units,))
+        if autograd.is_recording():
             xin = x.contiguous().float()
 
             def bwd(dy, xin=xin, self=self):
-                dx, dw, db = ops.dense_backward(xin, self.weight.data(), dy)
+                # flatten=False folds the leading axes into rows: the same dense backward on the folded view
+                dx, dw, db = ops.dense_backward(xin, self.weight.data(), dy.reshape(xin.shape[0], -1).contiguous())
                 self.weight._accumulate_grad(dw)
                 if self.bias is not None:
                     self.bias._accumulate_grad(db)
                 return dx.reshape(x_orig.shape)
-            autograd.tag(y, bwd, x_orig)
-        return y if lead is None else y.reshape(tuple(lead) + (self._units,))
+            autograd.tag(out, bwd, x_orig)
+        return out
 
 
 class Embedding(Block):

@@ -38,21 +38,27 @@ class FixedBucketSampler(object):
         buckets = [[] for _ in range(num_buckets)]
         for i, k in enumerate(keys):
             buckets[min((k - lo) // width, num_buckets - 1)].append(i)
-        self._batches = []
-        for b in buckets:
-            for j in range(0, len(b), batch_size):
-                self._batches.append(b[j: j + batch_size])
+        self._buckets, self._batch_size = buckets, batch_size
         self._shuffle, self._rng = shuffle, np.random.RandomState(seed)
+        self._n = sum((len(b) + batch_size - 1) // batch_size for b in buckets)
 
     def __iter__(self):
-        order = list(range(len(self._batches)))
+        """shuffle=True: like gluonnlp, the samples of every bucket are reshuffled each epoch before they are cut into batches
+        (batch membership changes from epoch to epoch), and the batch order is shuffled as well."""
+        batches = []
+        for b in self._buckets:
+            idx = list(b)
+            if self._shuffle:
+                self._rng.shuffle(idx)
+            for j in range(0, len(idx), self._batch_size):
+                batches.append(idx[j: j + self._batch_size])
         if self._shuffle:
-            self._rng.shuffle(order)
-        for i in order:
-            yield self._batches[i]
+            self._rng.shuffle(batches)
+        for bt in batches:
+            yield bt
 
     def __len__(self):
-        return len(self._batches)
+        return self._n
 
 
 class DataLoader(object):

@@ -118,3 +118,57 @@ def test_training_reduces_loss_on_features():
         trainer.step(B)
         losses.append(loss.mean().item())
     assert losses[-1] < 0.5 * losses[0], losses
+
+
+def test_dense_flatten_false_backward_and_dropout_guard():
+    """Dense(flatten=False) on a (B,T,C) input under autograd.record() carries its backward (it silently dropped the
+    gradients); Dropout(rate>0) refuses to run recorded outside the captioner's training graph."""
+    import torch
+    from tennis_b200 import autograd
+    from tennis_b200.gluon import Dense, Dropout
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 5, 8, generator=g)
+    w = torch.randn(4, 8, generator=g)
+    b = torch.randn(4, generator=g)
+    d = Dense(4, in_units=8, flatten=False)
+    d.initialize(ctx=torch.device("cuda", 0))
+    d.weight.set_data(w)
+    d.bias.set_data(b)
+    xc = x.cuda()
+    with autograd.record():
+        y = d(xc)
+    head = torch.randn(3, 5, 4, generator=g)
+    autograd.backward([y], [head.cuda()])
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    (torch.nn.functional.linear(xr, wr, br) * head).sum().backward()
+    assert y.shape == (3, 5, 4)
+    assert (d.weight.grad().cpu() - wr.grad).abs().max().item() < 1e-5
+    assert (d.bias.grad().cpu() - br.grad).abs().max().item() < 1e-5
+    with pytest.raises(NotImplementedError):
+        with autograd.record():
+            Dropout(0.3)(xc)
+    assert Dropout(0.3)(xc) is xc  # inference: identity
+
+
+def test_device_metrics_match_host_metrics_bit_exact():
+    """tn_metrics_update (confusion matrix, top-1 / top-k hits accumulated on the device) against metrics/vision.py on the host,
+    including exact ties (lowest class index first, like a stable argsort / numpy argmax)."""
+    import torch
+    from tennis_b200.metrics.device import DeviceMetrics
+    from tennis_b200.metrics.vision import PRF1, Accuracy
+    names = ["c%d" % i for i in range(11)]
+    g = torch.Generator().manual_seed(4)
+    dm = DeviceMetrics(names, top_k=5, device="cuda:0")
+    acc, top5, prf = Accuracy(), Accuracy("top5", top_k=5), PRF1(label_names=names)
+    for n in (64, 1, 37):
+        logits = torch.randn(n, 11, generator=g)
+        logits[::3] = (logits[::3] * 2).round() / 2  # many exact ties
+        labels = torch.randint(0, 11, (n,), generator=g)
+        dm.update(labels.cuda(), logits.cuda())
+        for m in (acc, top5, prf):
+            m.update([labels], [logits])
+    a, t, p = dm.finish()
+    assert (a.hit, a.n) == (acc.hit, acc.n) and (t.hit, t.n) == (top5.hit, top5.n)
+    assert (p.mat == prf.mat).all() and (p.scores == prf.scores).all()
+    assert p.get() == prf.get()

@@ -67,3 +67,22 @@ def test_host_pipeline_chunk_plan_is_a_partition(B, copy_ms, fixed_ms, compute_m
     cuts = plan_chunks(B, copy_ms, fixed_ms, compute_ms, max_chunks=max_chunks)
     assert cuts[0] == 0 and cuts[-1] == B and len(cuts) - 1 <= max_chunks
     assert all(a < b for a, b in zip(cuts, cuts[1:]))
+
+
+def test_fixed_bucket_sampler_reshuffles_inside_buckets_every_epoch():
+    """gluonnlp's FixedBucketSampler(shuffle=True) draws new batches every epoch: the batch MEMBERSHIP must change
+    between epochs, every sample must appear exactly once per epoch, and a batch never mixes buckets."""
+    from tennis_b200.utils.captioning import FixedBucketSampler
+    lengths = [(5 + (i * 7) % 40, 3 + (i * 3) % 20) for i in range(200)]
+    s = FixedBucketSampler(lengths, batch_size=16, num_buckets=4, shuffle=True, seed=1)
+    e1, e2 = [list(b) for b in s], [list(b) for b in s]
+    assert sorted(i for b in e1 for i in b) == list(range(200)) == sorted(i for b in e2 for i in b)
+    assert len(e1) == len(s) == len(e2)
+    assert set(map(frozenset, e1)) != set(map(frozenset, e2))
+    keys = [max(l) for l in lengths]
+    lo, hi = min(keys), max(keys)
+    width = -(-(hi - lo + 1) // 4)
+    for b in e1:
+        assert len({min((keys[i] - lo) // width, 3) for i in b}) == 1
+    s0 = FixedBucketSampler(lengths, batch_size=16, num_buckets=4, shuffle=False)
+    assert [list(b) for b in s0] == [list(b) for b in s0]
