@@ -139,47 +139,60 @@ __global__ void __launch_bounds__(256) cell_kernel_v2(const float* __restrict__ 
   const int r0 = blockIdx.x * 32, u0 = blockIdx.y * 8;
   const int tid = threadIdx.x;
   const int GH = G * H;
-  // staging loops: eight independent loads in flight per thread (a plain one-load-per-iteration loop exposes the full L2
-  // latency 48 times per thread and was 90 % of this kernel's time)
-  constexpr int U = 8;
-  for (int base = tid; base < KT * 8 * G; base += 256 * U) {
-    float v[U];
+  // staging: 16-byte loads, six in flight per thread (a one-load-per-iteration loop exposes the full L2 latency 48 times per
+  // thread and was 90 % of this kernel's time); requires Da, Db, H multiples of 4 (checked by the launcher)
+  constexpr int U = 6;
+  {
+    const int n4 = KT * G * 2;  // (k, gate, half of the 8 units) -> one float4
+    for (int base = tid; base < n4; base += 256 * U) {
+      float4 v[U];
 #pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int i = base + q * 256;
-      v[q] = 0.f;
-      if (i < KT * 8 * G) {
-        const int uu = i & 7, g = (i >> 3) % G, k = i / (8 * G);
-        const float* W = k < K ? WihT + static_cast<size_t>(k) * GH : WhhT + static_cast<size_t>(k - K) * GH;
-        v[q] = __ldg(W + g * H + u0 + uu);
+      for (int q = 0; q < U; ++q) {
+        const int i = base + q * 256;
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n4) {
+          const int hf = i & 1, g = (i >> 1) % G, k = i / (2 * G);
+          const float* W = k < K ? WihT + static_cast<size_t>(k) * GH : WhhT + static_cast<size_t>(k - K) * GH;
+          v[q] = __ldg(reinterpret_cast<const float4*>(W + g * H + u0 + 4 * hf));
+        }
       }
-    }
 #pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int i = base + q * 256;
-      if (i < KT * 8 * G) sW[((i / (8 * G)) * 8 + (i & 7)) * 4 + ((i >> 3) % G)] = v[q];
-    }
-  }
-  for (int base = tid; base < 32 * KT; base += 256 * U) {
-    float v[U];
-#pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int i = base + q * 256;
-      v[q] = 0.f;
-      if (i < 32 * KT) {
-        const int rr = i / KT, k = i - rr * KT;
-        const int r = r0 + rr;
-        if (r < R) {
-          if (k < Da) v[q] = xa[static_cast<size_t>(xa_index ? xa_index[r] : r) * Da + k];
-          else if (k < K) v[q] = xb[static_cast<size_t>(xb_src ? xb_src[r] : r) * Db + (k - Da)];
-          else v[q] = h_in[static_cast<size_t>(src_row ? src_row[r] : r) * H + (k - K)];
+      for (int q = 0; q < U; ++q) {
+        const int i = base + q * 256;
+        if (i < n4) {
+          const int hf = i & 1, g = (i >> 1) % G, k = i / (2 * G);
+          float* d = sW + (k * 8 + 4 * hf) * 4 + g;
+          d[0] = v[q].x;
+          d[4] = v[q].y;
+          d[8] = v[q].z;
+          d[12] = v[q].w;
         }
       }
     }
+    const int r4 = KT / 4, m4 = 32 * r4;  // rows as float4: [xa | xb | h]
+    for (int base = tid; base < m4; base += 256 * U) {
+      float4 v[U];
 #pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int i = base + q * 256;
-      if (i < 32 * KT) sx[(i / KT) * KTp + (i % KT)] = v[q];
+      for (int q = 0; q < U; ++q) {
+        const int i = base + q * 256;
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < m4) {
+          const int rr = i / r4, k = (i - rr * r4) * 4;
+          const int r = r0 + rr;
+          if (r < R) {
+            const float* src;
+            if (k < Da) src = xa + static_cast<size_t>(xa_index ? xa_index[r] : r) * Da + k;
+            else if (k < K) src = xb + static_cast<size_t>(xb_src ? xb_src[r] : r) * Db + (k - Da);
+            else src = h_in + static_cast<size_t>(src_row ? src_row[r] : r) * H + (k - K);
+            v[q] = __ldg(reinterpret_cast<const float4*>(src));
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int i = base + q * 256;
+        if (i < m4) *reinterpret_cast<float4*>(sx + (i / r4) * KTp + (i % r4) * 4) = v[q];
+      }
     }
   }
   __syncthreads();
@@ -366,15 +379,15 @@ __global__ void __launch_bounds__(256) attn_kernel_v2(const float* __restrict__ 
   const float* mb = mem + static_cast<size_t>(b) * T * H;
   {  // stage + transpose: 16-byte global loads (4 in flight per thread), scalar conflict-free shared stores
     const int n4 = len * H / 4, H4 = H / 4;
-    for (int base = tid; base < n4; base += 256 * 4) {
-      float4 v[4];
+    for (int base = tid; base < n4; base += 256 * 7) {
+      float4 v[7];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 7; ++q) {
         const int i = base + q * 256;
         v[q] = i < n4 ? __ldg(reinterpret_cast<const float4*>(mb) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 7; ++q) {
         const int i = base + q * 256;
         if (i < n4) {
           const int t = i / H4, k = (i - t * H4) * 4;
@@ -388,19 +401,19 @@ __global__ void __launch_bounds__(256) attn_kernel_v2(const float* __restrict__ 
   }
   for (int i = tid; i < beam * H; i += 256) sx[i] = query[static_cast<size_t>(b) * beam * H + i];
   __syncthreads();
-  {  // query projection: thread (half of k, column j) for all rows of the sentence; 8 weight loads in flight
+  {  // query projection: thread (half of k, column j) for all rows of the sentence; 16 weight loads in flight
     const int kh = tid >> 7, j = tid & 127;
     for (int j0 = j; j0 < H; j0 += 128) {
       float a[kAttnMaxBeam];
 #pragma unroll
       for (int i = 0; i < kAttnMaxBeam; ++i) a[i] = 0.f;
       const int k0 = kh * (H / 2), k1 = k0 + H / 2;
-      for (int k = k0; k < k1; k += 8) {
-        float w[8];
+      for (int k = k0; k < k1; k += 16) {
+        float w[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) w[q] = (k + q < k1) ? __ldg(WqT + static_cast<size_t>(k + q) * H + j0) : 0.f;
+        for (int q = 0; q < 16; ++q) w[q] = (k + q < k1) ? __ldg(WqT + static_cast<size_t>(k + q) * H + j0) : 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 16; ++q) {
           if (k + q < k1) {
 #pragma unroll
             for (int i = 0; i < kAttnMaxBeam; ++i)
@@ -474,16 +487,16 @@ __global__ void __launch_bounds__(256) proj_kernel_v2(const float* __restrict__ 
   float* sx = sW + static_cast<size_t>(H) * Vp;     // [16][H]
   float* sl = sx + 16 * H;                          // [16][Vp]
   const int r0 = blockIdx.x * 16, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int base = tid; base < H * Vp; base += 256 * 8) {  // eight loads in flight per thread
-    float w[8];
+  for (int base = tid; base < H * Vp; base += 256 * 16) {  // sixteen loads in flight per thread
+    float w[16];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 16; ++q) {
       const int i = base + q * 256;
       const int k = i / Vp, v = i - k * Vp;
       w[q] = (i < H * Vp && v < V) ? __ldg(WpT + static_cast<size_t>(k) * V + v) : 0.f;
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < 16; ++q)
       if (base + q * 256 < H * Vp) sW[base + q * 256] = w[q];
   }
   for (int i = tid; i < 16 * H; i += 256) {
@@ -756,7 +769,7 @@ const float* run_step(const tn_gnmt* g, const StepBufs& sb, int cur, const int* 
   auto launch_cell = [&](int l, const float* xa, int Da, const int* xa_index, const float* xb, int Db, const int* xb_src,
                          float* out_res) {
     ProfScope ps(kProfOther, st);
-    if (!cell_v1 && (H % 8) == 0) {
+    if (!cell_v1 && (H % 8) == 0 && (Da % 4) == 0 && (Db % 4) == 0) {
       const int KT = Da + Db + H;
       const size_t smem2 = (static_cast<size_t>(KT) * 32 + 32 * static_cast<size_t>(KT + 4)) * sizeof(float);
       if (smem2 <= 200 * 1024) {
