@@ -728,7 +728,6 @@ def bench_gru_head(model, device, iters=20):
 
 
 def main():
-    _capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -743,7 +742,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd))  # the ranks inherit the real stdout: rank 0 prints the JSON line there
+    _capture_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
     else:
