@@ -47,6 +47,8 @@ class CNNTrainGraph(object):
         self.tape = []
         self.touched_stats = []
         self.named = {}  # block outputs by name (kept for inspection by the tests)
+        from ... import tcgemm
+        self.gemm_mode = tcgemm.mode()  # 'x3' / 'bf16': tcgen05 (csrc/tn_gemm_tc.cu); 'fp32': the SIMT SGEMM
 
     # ------------------------------------------------------------------------------------------------ ops
     def _bn(self, src, c0, C, prefix, relu=True):
@@ -81,6 +83,7 @@ class CNNTrainGraph(object):
 
     def _conv(self, src, c0, Cin, wname, stride, pad, dst=None, d0=0):
         from ..captioning.train_graph import sgemm
+        from ... import tcgemm
         N, H, W, Ct = src.shape
         Wp = self.P[wname]
         w = Wp.data()
@@ -94,6 +97,16 @@ class CNNTrainGraph(object):
         wk = w.permute(0, 2, 3, 1).reshape(Cout, K).contiguous()  # (Cout, (r,s,c)): the im2col column order
         direct = R == 1 and S == 1 and stride == 1 and pad == 0
         x2 = src.data.reshape(-1, Ct)[:, c0:c0 + Cin]
+        y2 = dst.data.reshape(-1, Cd)[:, d0:d0 + Cout]
+        gm = self.gemm_mode
+        passes = 3 if gm == "x3" else 1
+        lo = passes == 3
+        # 3x3 / stride 1 / pad 1 on the tensor cores: a tap is a row shift in the zero-padded row space, no im2col matrix
+        shifted = gm != "fp32" and R == 3 and S == 3 and stride == 1 and pad == 1 and Cin % 8 == 0 and Cout % 8 == 0
+        if shifted:
+            Wq = W + 2
+            offs = [(r - 1) * Wq + (s - 1) for r in range(3) for s in range(3)]
+            Mp = tcgemm.padded_rows(N, H, W)
 
         def columns():
             if direct:
@@ -101,22 +114,55 @@ class CNNTrainGraph(object):
             col = torch.empty(N * Ho * Wo, K, device=dev)
             check(lib().tn_im2col_nhwc(_sl(src.data, c0), Ct, N, H, W, Cin, R, S, stride, pad, dptr(col), stream_ptr()))
             return col
-        y2 = dst.data.reshape(-1, Cd)[:, d0:d0 + Cout]
-        sgemm(columns(), wk, y2, tb=True)
+
+        if shifted:
+            xp = tcgemm.planes(x2, pad_hw=(H, W), lo=lo)
+            wp = tcgemm.planes(wk, lo=lo)
+            tcgemm.gemm(xp, wp, Mp, Cout, Cin, y2, Cd, taps=[(offs[t], 0, 0, t * Cin) for t in range(9)], unpad_hw=(H, W),
+                        passes=passes)
+            del xp, wp
+        elif gm != "fp32":
+            tcgemm.matmul(columns(), wk, y2, tb=True, passes=passes)
+        else:
+            sgemm(columns(), wk, y2, tb=True)
 
         def bwd():
             if dst.grad is None:
                 return
             dy2 = dst.grad.reshape(-1, Cd)[:, d0:d0 + Cout]
+            want_dw = Wp.grad_req != 'null'
+            if shifted:
+                if want_dw:
+                    # dW[n, (dy,dx), c] = sum_m dY[m, n] X[m + dy*P + dx, c]: contraction over the padded pixels (row pitch P a
+                    # multiple of 8), one GEMM per tap: the dx shift is baked into three copies of dY^T, dy*P is the TMA offset
+                    P8 = tcgemm.pitch8(W)
+                    Mp8 = tcgemm.padded_rows(N, H, W, P8)
+                    xT = tcgemm.planes(x2, transpose=True, pad_hw=(H, W), lo=lo, pitch=P8)                       # (Cin, Mp8)
+                    dyT = [tcgemm.planes(dy2, transpose=True, pad_hw=(H, W), lo=lo, pitch=P8, shift=dx) for dx in (-1, 0, 1)]
+                    dwk = torch.empty(Cout, K, device=dev)
+                    for t in range(9):
+                        dy_, dx_ = t // 3 - 1, t % 3 - 1
+                        tcgemm.gemm(xT, dyT[dx_ + 1], Cin, Cout, Mp8, dwk[:, t * Cin:], 1, K, taps=[(0, 0, 0, -dy_ * P8)],
+                                    passes=passes)
+                    del xT, dyT
+                    Wp._accumulate_grad(dwk.reshape(Cout, R, S, Cin).permute(0, 3, 1, 2).contiguous())
+                if src.needs_grad:
+                    # dX[m, c] += sum_t sum_n dY[m - off_t, n] W[n, t, c]
+                    dyp = tcgemm.planes(dy2, pad_hw=(H, W), lo=lo)                      # (Mp, Cout)
+                    wT = tcgemm.planes(w.permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).contiguous(), lo=lo)  # (Cin, (t, n))
+                    tcgemm.gemm(dyp, wT, Mp, Cin, Cout, src.g().reshape(-1, Ct)[:, c0:c0 + Cin], Ct,
+                                taps=[(-offs[t], 0, 0, t * Cout) for t in range(9)], beta=1.0, unpad_hw=(H, W), passes=passes)
+                return
+            mm = sgemm if gm == "fp32" else (lambda A, B, C, **kw: tcgemm.matmul(A, B, C, passes=passes, **kw))
             col = columns()  # recomputed: keeping every im2col matrix would dominate the memory
-            if Wp.grad_req != 'null':
-                dwk = sgemm(dy2, col, torch.empty(Cout, K, device=dev), ta=True)
+            if want_dw:
+                dwk = mm(dy2, col, torch.empty(Cout, K, device=dev), ta=True)
                 Wp._accumulate_grad(dwk.reshape(Cout, R, S, Cin).permute(0, 3, 1, 2).contiguous())
             if src.needs_grad:
                 if direct:
-                    sgemm(dy2, wk, src.g().reshape(-1, Ct)[:, c0:c0 + Cin], beta=1.0)
+                    mm(dy2, wk, src.g().reshape(-1, Ct)[:, c0:c0 + Cin], beta=1.0)
                 else:
-                    dcol = sgemm(dy2, wk, col)  # the im2col buffer is free again: reuse it for its gradient
+                    dcol = mm(dy2, wk, col)  # the im2col buffer is free again: reuse it for its gradient
                     check(lib().tn_col2im_nhwc(dptr(dcol), N, H, W, Cin, R, S, stride, pad, _sl(src.g(), c0), Ct, stream_ptr()))
         self.tape.append(bwd)
         return dst

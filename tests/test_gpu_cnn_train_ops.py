@@ -83,8 +83,14 @@ def test_bn_relu_slice_forward_backward(relu):
 
 
 @pytest.mark.parametrize("Cin,Cout,R,stride,pad,H,W", [(24, 32, 1, 1, 0, 6, 5), (16, 32, 3, 1, 1, 7, 7), (16, 48, 3, 2, 1, 9, 8),
-                                                       (32, 64, 1, 2, 0, 8, 8), (3, 64, 7, 2, 3, 20, 17), (512, 64, 3, 1, 1, 7, 7)])
-def test_conv_forward_backward(Cin, Cout, R, stride, pad, H, W):
+                                                       (32, 64, 1, 2, 0, 8, 8), (3, 64, 7, 2, 3, 20, 17), (512, 64, 3, 1, 1, 7, 7),
+                                                       (128, 32, 3, 1, 1, 28, 28), (200, 128, 1, 1, 0, 14, 14)])
+@pytest.mark.parametrize("gemm", ["x3", "fp32", "bf16"])
+def test_conv_forward_backward(Cin, Cout, R, stride, pad, H, W, gemm, monkeypatch):
+    """x3 = split-bf16 on tcgen05 (the default), fp32 = SIMT SGEMM: both at the fp32 bar (1e-4 of the largest entry); bf16 = one
+    tensor-core product: the bf16 bar."""
+    monkeypatch.setenv("TN_TRAIN_GEMM", gemm)
+    tol = 1e-4 if gemm != "bf16" else 2e-2
     g = torch.Generator().manual_seed(1)
     N, Ct, c0 = 3, Cin + 8, 4            # the conv reads channels [4, 4+Cin) of a wider buffer ...
     Cd, d0 = Cout + 16, 8                # ... and writes channels [8, 8+Cout) of a wider destination
@@ -101,14 +107,39 @@ def test_conv_forward_backward(Cin, Cout, R, stride, pad, H, W):
     src = _act(x)
     dst = _Act(torch.zeros(N, Ho, Wo, Cd).cuda())
     G._conv(src, c0, Cin, "w", stride, pad, dst=dst, d0=d0)
-    _close(_nchw(dst.data)[:, d0:d0 + Cout], y_ref.detach(), 1e-4)
+    _close(_nchw(dst.data)[:, d0:d0 + Cout], y_ref.detach(), tol)
     assert (dst.data[..., :d0] == 0).all() and (dst.data[..., d0 + Cout:] == 0).all()
     dst.grad = torch.zeros_like(dst.data)
     dst.grad[..., d0:d0 + Cout] = dy.permute(0, 2, 3, 1).cuda()
     for fn in reversed(G.tape):
         fn()
-    _close(P["w"]._grad.cpu(), wr.grad, 1e-4)
-    _close(_nchw(src.grad), xr.grad, 1e-4)
+    _close(P["w"]._grad.cpu(), wr.grad, tol)
+    _close(_nchw(src.grad), xr.grad, tol)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, True), (True, False), (False, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(300, 32, 64), (129, 100, 200), (64, 128, 5000), (1000, 257, 72)])
+def test_tensor_core_gemm_matches_fp64(ta, tb, M, N, K):
+    """tn_split_bf16 + tn_gemm_tc on strided fp32 views, every transpose combination, ragged sizes, split-K (K = 5000), alpha/beta:
+    split-bf16 within 3e-5 of the fp64 product (fp32 SGEMM grade), plain bf16 within 1e-2."""
+    from tennis_b200 import tcgemm
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn((K, M + 3) if ta else (M, K + 5), generator=g)
+    B = torch.randn((N, K + 2) if tb else (K, N + 7), generator=g)
+    C0 = torch.randn(M, N + 4, generator=g)
+    Av = A[:, :M] if ta else A[:, :K]
+    Bv = B[:, :K] if tb else B[:, :N]
+    opA = Av.t() if ta else Av
+    opB = Bv.t() if tb else Bv
+    ref = 0.5 * (opA.double() @ opB.double()) + 2.0 * C0[:, :N].double()
+    scale = ref.abs().max().item()
+    for passes, tol in ((3, 3e-5), (1, 1e-2)):
+        Ad, Bd, Cd = A.cuda(), B.cuda(), C0.clone().cuda()
+        tcgemm.matmul(Ad[:, :M] if ta else Ad[:, :K], Bd[:, :K] if tb else Bd[:, :N], Cd[:, :N], ta=ta, tb=tb, alpha=0.5, beta=2.0,
+                      passes=passes)
+        err = (Cd[:, :N].cpu().double() - ref).abs().max().item()
+        assert err < tol * scale, (passes, err, scale)
+        assert torch.equal(Cd[:, N:].cpu(), C0[:, N:])  # columns outside the view untouched
 
 
 def test_pooling_forward_backward():
