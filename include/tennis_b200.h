@@ -263,14 +263,16 @@ int tn_axpy(float* y, const float* x, float a, size_t n, tn_stream_t stream);
  * tn_gemm_tc: D[m,n] = sum_t sum_k A[m + taps[4t], taps[4t+1] + k] * B[n + taps[4t+2], taps[4t+3] + k], k < K, taps on the HOST
  *   (NULL = one tap, no offsets; out-of-range reads are zeros; contraction offsets must be multiples of 8), passes = 3: hi*hi + hi*lo + lo*hi (fp32-grade), 1: hi*hi;
  *   C[orow(m)*c_row_stride + n*c_col_stride] = alpha*D + beta*C, unpad_h/w > 0: m runs over the padded grid, border rows are
- *   dropped.  Few output tiles + long K: split-K through `workspace` (deterministic); a strided column needs the workspace. */
-long long tn_gemm_tc_workspace_bytes(int M, int N);
+ *   dropped.  tile_taps != 0: the taps are ntaps INDEPENDENT products in one launch (a 3x3 weight gradient), tap t written at
+ *   C + t*c_tap_stride.  Few output tiles + long K: split-K through `workspace` (deterministic, tn_gemm_tc_workspace_bytes(M, N,
+ *   tile_taps ? ntaps : 0) is always enough); a strided column needs the workspace. */
+long long tn_gemm_tc_workspace_bytes(int M, int N, int tile_taps);
 int tn_split_bf16(const float* src, long long ld, long long rows, int cols, int transpose, int pad_h, int pad_w, int pad_pitch,
                   int shift, void* hi, void* lo, long long out_ld, tn_stream_t stream);
 int tn_gemm_tc(int M, int N, int K, int ntaps, const int* taps, int passes, const void* a_hi, const void* a_lo, long long a_rows,
                long long a_kdim, long long a_ld, const void* b_hi, const void* b_lo, long long b_rows, long long b_kdim,
-               long long b_ld, float alpha, float beta, float* C, long long c_row_stride, long long c_col_stride, int unpad_h,
-               int unpad_w, void* workspace, long long workspace_bytes, tn_stream_t stream);
+               long long b_ld, float alpha, float beta, float* C, long long c_row_stride, long long c_col_stride, int tile_taps,
+               long long c_tap_stride, int unpad_h, int unpad_w, void* workspace, long long workspace_bytes, tn_stream_t stream);
 int tn_im2col_nhwc(const float* x, long long ldx, int N, int H, int W, int C, int R, int S, int stride, int pad, float* col,
                    tn_stream_t stream);
 int tn_col2im_nhwc(const float* dcol, int N, int H, int W, int C, int R, int S, int stride, int pad, float* dx, long long lddx,

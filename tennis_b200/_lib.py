@@ -169,10 +169,10 @@ SIGNATURES.update({
 })
 
 SIGNATURES.update({
-    "tn_gemm_tc_workspace_bytes": (_LL, [c_int, c_int]),
+    "tn_gemm_tc_workspace_bytes": (_LL, [c_int, c_int, c_int]),
     "tn_split_bf16": (c_int, [c_void_p, _LL, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, _LL, c_void_p]),
     "tn_gemm_tc": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, _LL, _LL, _LL, c_void_p, c_void_p, _LL,
-                           _LL, _LL, c_float, c_float, c_void_p, _LL, _LL, c_int, c_int, c_void_p, _LL, c_void_p]),
+                           _LL, _LL, c_float, c_float, c_void_p, _LL, _LL, c_int, _LL, c_int, c_int, c_void_p, _LL, c_void_p]),
     "tn_im2col_nhwc": (c_int, [c_void_p, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tn_col2im_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, _LL, c_void_p]),
     "tn_bn_train_forward": (c_int, [c_void_p, _LL, _LL, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int,

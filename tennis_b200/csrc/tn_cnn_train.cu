@@ -50,81 +50,174 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, int N, int H, int 
 }
 
 // ---------------------------------------------------------------------------------------------------- BatchNorm (training)
-// One block per 32 channels, 8 row lanes; fp32 two-pass statistics (mean, then centred second moment) for accuracy.
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, long long ldx, long long M, int C,
-                                                       float* __restrict__ mean, float* __restrict__ var,
-                                                       float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                       float momentum) {
-  __shared__ float red[8][33];
-  __shared__ float smean[32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  float acc = 0.f;
-  if (c < C)
-    for (long long m = ty; m < M; m += 8) acc += x[m * ldx + c];
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0) {
-    float s = 0.f;
-    for (int r = 0; r < 8; ++r) s += red[r][tx];
-    smean[tx] = s / static_cast<float>(M);
-  }
-  __syncthreads();
-  const float mu = smean[tx];
-  acc = 0.f;
-  if (c < C)
-    for (long long m = ty; m < M; m += 8) {
-      const float d = x[m * ldx + c] - mu;
-      acc = fmaf(d, d, acc);
-    }
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    float s = 0.f;
-    for (int r = 0; r < 8; ++r) s += red[r][tx];
-    const float v = s / static_cast<float>(M);  // biased, also for the running estimate (MXNet)
-    mean[c] = mu;
-    var[c] = v;
-    if (running_mean) running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * mu;
-    if (running_var) running_var[c] = momentum * running_var[c] + (1.f - momentum) * v;
-  }
+// Per-channel reductions over M = frames x pixels rows: the rows are split over gridDim.y blocks (one block = 32 channels x 8 row
+// lanes over a contiguous row range) so that the whole machine streams the activation once; the per-block partial sums go to a
+// stream-ordered scratch buffer and a second, tiny kernel adds them in a fixed order (deterministic) in double precision.
+// Variance by the shifted-data formula with the channel's first row as the shift: one pass over x, no cancellation between two
+// large sums (var = (S2 - S1^2/M)/M with S1 = sum(x - k), S2 = sum((x - k)^2)).
+constexpr int kBnMaxSplits = 512;
+
+struct BnSplit {
+  int splits;
+  long long rows_per_block;
+};
+inline BnSplit bn_split(long long M, int C) {
+  const int cgroups = (C + 31) / 32;
+  long long s = (148LL * 8 + cgroups - 1) / cgroups;
+  const long long by_rows = (M + 63) / 64;
+  if (s > by_rows) s = by_rows;
+  if (s > kBnMaxSplits) s = kBnMaxSplits;
+  if (s < 1) s = 1;
+  long long rpb = (M + s - 1) / s;
+  rpb = (rpb + 7) / 8 * 8;
+  BnSplit r;
+  r.rows_per_block = rpb;
+  r.splits = static_cast<int>((M + rpb - 1) / rpb);
+  return r;
 }
 
-// y = relu?( (x - mean) * invstd * gamma + beta )
+// part[(split * 2 + {0,1}) * C + c] = sum (x - x[0][c]), sum (x - x[0][c])^2 over the block's rows
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(const float* __restrict__ x, long long ldx, long long M, int C,
+                                                               long long rows_per_block, float* __restrict__ part) {
+  __shared__ float r1[8][33], r2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long m0 = blockIdx.y * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+  if (c < C) {
+    const float k = x[c];
+    const float* xc = x + c;
+    long long m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {  // four independent loads in flight per thread
+      const float d0 = xc[m * ldx] - k, d1 = xc[(m + 8) * ldx] - k, d2 = xc[(m + 16) * ldx] - k, d3 = xc[(m + 24) * ldx] - k;
+      a1 += d0; a2 = fmaf(d0, d0, a2);
+      b1 += d1; b2 = fmaf(d1, d1, b2);
+      a1 += d2; a2 = fmaf(d2, d2, a2);
+      b1 += d3; b2 = fmaf(d3, d3, b2);
+    }
+    for (; m < m1; m += 8) {
+      const float d = xc[m * ldx] - k;
+      a1 += d; a2 = fmaf(d, d, a2);
+    }
+  }
+  r1[ty][tx] = a1 + b1;
+  r2[ty][tx] = a2 + b2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < 8; ++r) {
+      s1 += r1[r][tx];
+      s2 += r2[r][tx];
+    }
+    part[(static_cast<size_t>(blockIdx.y) * 2 + 0) * C + c] = s1;
+    part[(static_cast<size_t>(blockIdx.y) * 2 + 1) * C + c] = s2;
+  }
+}
+// one block = 32 channels x 8 split lanes: lane r adds splits r, r+8, ... in double, the eight lane sums are added in order
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ x, const float* __restrict__ part, int splits,
+                                                                long long M, int C, float* __restrict__ mean, float* __restrict__ var,
+                                                                float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                float momentum) {
+  __shared__ double r1[8][33], r2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C)
+    for (int s = ty; s < splits; s += 8) {
+      s1 += static_cast<double>(part[(static_cast<size_t>(s) * 2 + 0) * C + c]);
+      s2 += static_cast<double>(part[(static_cast<size_t>(s) * 2 + 1) * C + c]);
+    }
+  r1[ty][tx] = s1;
+  r2[ty][tx] = s2;
+  __syncthreads();
+  if (ty != 0 || c >= C) return;
+  s1 = s2 = 0.0;
+  for (int r = 0; r < 8; ++r) {
+    s1 += r1[r][tx];
+    s2 += r2[r][tx];
+  }
+  const double inv = 1.0 / static_cast<double>(M);
+  const float mu = static_cast<float>(static_cast<double>(x[c]) + s1 * inv);
+  double vv = (s2 - s1 * s1 * inv) * inv;  // biased, also for the running estimate (MXNet)
+  if (vv < 0.0) vv = 0.0;
+  const float v = static_cast<float>(vv);
+  mean[c] = mu;
+  var[c] = v;
+  if (running_mean) running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * mu;
+  if (running_var) running_var[c] = momentum * running_var[c] + (1.f - momentum) * v;
+}
+
+// y = relu?( (x - mean) * invstd * gamma + beta ); VEC = 4: rows and channel counts allow 16-byte accesses
+template <int VEC>
 __global__ void bn_apply_kernel(const float* __restrict__ x, long long ldx, long long M, int C, const float* __restrict__ mean,
                                 const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
                                 float eps, int relu, float* __restrict__ y, long long ldy) {
-  const size_t total = static_cast<size_t>(M) * C;
+  const unsigned Cv = static_cast<unsigned>(C / VEC);
+  const size_t total = static_cast<size_t>(M) * Cv;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t m = i / C;
-    const int c = static_cast<int>(i - m * C);
-    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-    float v = (x[m * ldx + c] - mean[c]) * rsqrtf(var[c] + eps) * g + b;
-    if (relu) v = fmaxf(v, 0.f);
-    y[m * ldy + c] = v;
+    size_t m;
+    int c;
+    if (total < 0xffffffffull) {
+      const unsigned iu = static_cast<unsigned>(i), mu = iu / Cv;
+      m = mu;
+      c = static_cast<int>(iu - mu * Cv) * VEC;
+    } else {
+      m = i / Cv;
+      c = static_cast<int>(i - m * Cv) * VEC;
+    }
+    float xv[VEC], o[VEC];
+    if (VEC == 4) *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(x + m * ldx + c);
+    else xv[0] = x[m * ldx + c];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const float g = gamma ? gamma[c + q] : 1.f, b = beta ? beta[c + q] : 0.f;
+      float v = (xv[q] - mean[c + q]) * rsqrtf(var[c + q] + eps) * g + b;
+      if (relu) v = fmaxf(v, 0.f);
+      o[q] = v;
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(y + m * ldy + c) = *reinterpret_cast<const float4*>(o);
+    else y[m * ldy + c] = o[0];
   }
 }
 
-// dgamma[c] = sum dy' xhat, dbeta[c] = sum dy'  with dy' = dy * (y > 0) when relu
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y,
-                                                            long long ldy, const float* __restrict__ dy, long long lddy, long long M,
-                                                            int C, const float* __restrict__ mean, const float* __restrict__ var,
-                                                            float eps, int relu, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+// dgamma[c] = sum dy' xhat, dbeta[c] = sum dy'  with dy' = dy * (y > 0) when relu; same row split as the statistics
+__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y,
+                                                             long long ldy, const float* __restrict__ dy, long long lddy, long long M,
+                                                             int C, const float* __restrict__ mean, const float* __restrict__ var,
+                                                             float eps, int relu, long long rows_per_block, float* __restrict__ part) {
   __shared__ float rg[8][33], rb[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
-  float ag = 0.f, ab = 0.f;
+  const long long m0 = blockIdx.y * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float ag = 0.f, ab = 0.f, bg = 0.f, bb = 0.f;
   if (c < C) {
     const float mu = mean[c], is = rsqrtf(var[c] + eps);
-    for (long long m = ty; m < M; m += 8) {
+    long long m = m0 + ty;
+    for (; m + 8 < m1; m += 16) {
+      float d0 = dy[m * lddy + c], d1 = dy[(m + 8) * lddy + c];
+      const float x0 = x[m * ldx + c], x1 = x[(m + 8) * ldx + c];
+      if (relu) {
+        if (!(y[m * ldy + c] > 0.f)) d0 = 0.f;
+        if (!(y[(m + 8) * ldy + c] > 0.f)) d1 = 0.f;
+      }
+      ag = fmaf(d0, (x0 - mu) * is, ag);
+      ab += d0;
+      bg = fmaf(d1, (x1 - mu) * is, bg);
+      bb += d1;
+    }
+    for (; m < m1; m += 8) {
       float d = dy[m * lddy + c];
       if (relu && !(y[m * ldy + c] > 0.f)) d = 0.f;
       ag = fmaf(d, (x[m * ldx + c] - mu) * is, ag);
       ab += d;
     }
   }
-  rg[ty][tx] = ag;
-  rb[ty][tx] = ab;
+  rg[ty][tx] = ag + bg;
+  rb[ty][tx] = ab + bb;
   __syncthreads();
   if (ty == 0 && c < C) {
     float sg = 0.f, sb = 0.f;
@@ -132,30 +225,79 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
       sg += rg[r][tx];
       sb += rb[r][tx];
     }
-    dgamma[c] = sg;
-    dbeta[c] = sb;
+    part[(static_cast<size_t>(blockIdx.y) * 2 + 0) * C + c] = sg;
+    part[(static_cast<size_t>(blockIdx.y) * 2 + 1) * C + c] = sb;
   }
+}
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ part, int splits, int C,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double r1[8][33], r2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  double sg = 0.0, sb = 0.0;
+  if (c < C)
+    for (int s = ty; s < splits; s += 8) {
+      sg += static_cast<double>(part[(static_cast<size_t>(s) * 2 + 0) * C + c]);
+      sb += static_cast<double>(part[(static_cast<size_t>(s) * 2 + 1) * C + c]);
+    }
+  r1[ty][tx] = sg;
+  r2[ty][tx] = sb;
+  __syncthreads();
+  if (ty != 0 || c >= C) return;
+  sg = sb = 0.0;
+  for (int r = 0; r < 8; ++r) {
+    sg += r1[r][tx];
+    sb += r2[r][tx];
+  }
+  dgamma[c] = static_cast<float>(sg);
+  dbeta[c] = static_cast<float>(sb);
 }
 
 // dx (+)= gamma * invstd / M * (M dy' - dbeta - xhat dgamma)
+template <int VEC>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
                                     const float* __restrict__ dy, long long lddy, long long M, int C, const float* __restrict__ mean,
                                     const float* __restrict__ var, const float* __restrict__ gamma, float eps, int relu,
                                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx,
                                     long long lddx, int accumulate) {
-  const size_t total = static_cast<size_t>(M) * C;
+  const unsigned Cv = static_cast<unsigned>(C / VEC);
+  const size_t total = static_cast<size_t>(M) * Cv;
   const float invM = 1.f / static_cast<float>(M);
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t m = i / C;
-    const int c = static_cast<int>(i - m * C);
-    const float is = rsqrtf(var[c] + eps);
-    float d = dy[m * lddy + c];
-    if (relu && !(y[m * ldy + c] > 0.f)) d = 0.f;
-    const float xh = (x[m * ldx + c] - mean[c]) * is;
-    const float g = gamma ? gamma[c] : 1.f;
-    const float v = g * is * (d - invM * (dbeta[c] + xh * dgamma[c]));
-    float* o = dx + m * lddx + c;
-    *o = accumulate ? *o + v : v;
+    size_t m;
+    int c;
+    if (total < 0xffffffffull) {
+      const unsigned iu = static_cast<unsigned>(i), mu = iu / Cv;
+      m = mu;
+      c = static_cast<int>(iu - mu * Cv) * VEC;
+    } else {
+      m = i / Cv;
+      c = static_cast<int>(i - m * Cv) * VEC;
+    }
+    float xv[VEC], dv[VEC], yv[VEC], o[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(x + m * ldx + c);
+      *reinterpret_cast<float4*>(dv) = *reinterpret_cast<const float4*>(dy + m * lddy + c);
+      if (relu) *reinterpret_cast<float4*>(yv) = *reinterpret_cast<const float4*>(y + m * ldy + c);
+      if (accumulate) *reinterpret_cast<float4*>(o) = *reinterpret_cast<const float4*>(dx + m * lddx + c);
+    } else {
+      xv[0] = x[m * ldx + c];
+      dv[0] = dy[m * lddy + c];
+      if (relu) yv[0] = y[m * ldy + c];
+      if (accumulate) o[0] = dx[m * lddx + c];
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const float is = rsqrtf(var[c + q] + eps);
+      float d = dv[q];
+      if (relu && !(yv[q] > 0.f)) d = 0.f;
+      const float xh = (xv[q] - mean[c + q]) * is;
+      const float g = gamma ? gamma[c + q] : 1.f;
+      const float v = g * is * (d - invM * (dbeta[c + q] + xh * dgamma[c + q]));
+      o[q] = accumulate ? o[q] + v : v;
+    }
+    if (VEC == 4) *reinterpret_cast<float4*>(dx + m * lddx + c) = *reinterpret_cast<const float4*>(o);
+    else dx[m * lddx + c] = o[0];
   }
 }
 
@@ -263,9 +405,19 @@ int tn_bn_train_forward(const float* x, long long ldx, long long M, int C, const
   if (!x || !mean || !var || !y) return set_error(TN_ERR_INVALID, "null device pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope ps(kProfOther, st);
-  bn_stats_kernel<<<(C + 31) / 32, 256, 0, st>>>(x, ldx, M, C, mean, var, running_mean, running_var, momentum);
-  bn_apply_kernel<<<min(nblk(static_cast<size_t>(M) * C, 256), 148u * 32u), 256, 0, st>>>(x, ldx, M, C, mean, var, gamma, beta, eps, relu,
-                                                                                       y, ldy);
+  const BnSplit sp = bn_split(M, C);
+  float* part = nullptr;
+  TN_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), static_cast<size_t>(sp.splits) * 2 * C * sizeof(float), st));
+  bn_stats_partial_kernel<<<dim3((C + 31) / 32, sp.splits), 256, 0, st>>>(x, ldx, M, C, sp.rows_per_block, part);
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(x, part, sp.splits, M, C, mean, var, running_mean, running_var, momentum);
+  TN_CUDA(cudaFreeAsync(part, st));
+  const bool v4 = C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 == 0;
+  if (v4)
+    bn_apply_kernel<4><<<min(nblk(static_cast<size_t>(M) * (C / 4), 256), 148u * 32u), 256, 0, st>>>(x, ldx, M, C, mean, var, gamma, beta,
+                                                                                                 eps, relu, y, ldy);
+  else
+    bn_apply_kernel<1><<<min(nblk(static_cast<size_t>(M) * C, 256), 148u * 32u), 256, 0, st>>>(x, ldx, M, C, mean, var, gamma, beta, eps,
+                                                                                            relu, y, ldy);
   TN_CUDA(cudaGetLastError());
   return TN_OK;
 }
@@ -277,9 +429,22 @@ int tn_bn_train_backward(const float* x, long long ldx, const float* y, long lon
   if (!x || !dy || !mean || !var || !dgamma || !dbeta || !dx || (relu && !y)) return set_error(TN_ERR_INVALID, "null device pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope ps(kProfOther, st);
-  bn_bwd_reduce_kernel<<<(C + 31) / 32, 256, 0, st>>>(x, ldx, y, ldy, dy, lddy, M, C, mean, var, eps, relu, dgamma, dbeta);
-  bn_bwd_apply_kernel<<<min(nblk(static_cast<size_t>(M) * C, 256), 148u * 32u), 256, 0, st>>>(x, ldx, y, ldy, dy, lddy, M, C, mean, var, gamma,
-                                                                                           eps, relu, dgamma, dbeta, dx, lddx, accumulate);
+  const BnSplit sp = bn_split(M, C);
+  float* part = nullptr;
+  TN_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), static_cast<size_t>(sp.splits) * 2 * C * sizeof(float), st));
+  bn_bwd_partial_kernel<<<dim3((C + 31) / 32, sp.splits), 256, 0, st>>>(x, ldx, y, ldy, dy, lddy, M, C, mean, var, eps, relu,
+                                                                         sp.rows_per_block, part);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(part, sp.splits, C, dgamma, dbeta);
+  TN_CUDA(cudaFreeAsync(part, st));
+  const bool v4 = C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (!relu || ldy % 4 == 0) &&
+                  (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                   (relu ? reinterpret_cast<uintptr_t>(y) : 0)) % 16 == 0;
+  if (v4)
+    bn_bwd_apply_kernel<4><<<min(nblk(static_cast<size_t>(M) * (C / 4), 256), 148u * 32u), 256, 0, st>>>(
+        x, ldx, y, ldy, dy, lddy, M, C, mean, var, gamma, eps, relu, dgamma, dbeta, dx, lddx, accumulate);
+  else
+    bn_bwd_apply_kernel<1><<<min(nblk(static_cast<size_t>(M) * C, 256), 148u * 32u), 256, 0, st>>>(
+        x, ldx, y, ldy, dy, lddy, M, C, mean, var, gamma, eps, relu, dgamma, dbeta, dx, lddx, accumulate);
   TN_CUDA(cudaGetLastError());
   return TN_OK;
 }

@@ -54,6 +54,8 @@ struct TcParams {
   int Npad;
   int unpad_h, unpad_w;  // > 0: m indexes the padded (h+2)x(w+2) row space; border rows are dropped, the rest re-indexed
   int vec4;              // direct output rows are 16-byte aligned
+  int tile_taps, ntn;    // tile_taps: the taps are independent outputs (blockIdx.y = tap * ntn + n tile), not accumulated
+  long long c_tap_stride;
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
@@ -85,11 +87,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const uint32_t b_bytes = static_cast<uint32_t>(BN) * kBK * 2;
   const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN, split = blockIdx.z;
+  const int tsel = p.tile_taps ? static_cast<int>(blockIdx.y) / p.ntn : -1;  // this CTA's tap when taps are output tiles
+  const int m0 = blockIdx.x * kBM, n0 = (p.tile_taps ? static_cast<int>(blockIdx.y) % p.ntn : static_cast<int>(blockIdx.y)) * BN;
+  const int split = blockIdx.z;
   const int it0 = split * p.iters_per_split;
   int it1 = it0 + p.iters_per_split;
   if (it1 > p.iters_total) it1 = p.iters_total;
-  const int niter = (it1 - it0) * p.passes;  // ring slots this CTA consumes (>= 1 by construction)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -113,7 +116,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (lane == 0) {
       int slot = 0;
       for (int it = it0; it < it1; ++it) {
-        const int tap = it / p.kchunks, chunk = it - tap * p.kchunks;
+        const int tap_it = it / p.kchunks, chunk = it - tap_it * p.kchunks;
+        const int tap = tsel >= 0 ? tsel : tap_it;
         const int k0 = chunk * kBK;
         for (int ps = 0; ps < p.passes; ++ps, ++slot) {
           const int s = slot % kStages;
@@ -160,8 +164,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       orow = unpad_row(m, p.unpad_h, p.unpad_w);
       row_ok = orow >= 0;
     }
-    float* dst = direct ? p.C + orow * p.ldc + n0
-                        : p.partial + (static_cast<long long>(split) * p.M + m) * p.Npad + n0;
+    const int tcol = tsel >= 0 ? tsel : 0, ntc = p.tile_taps ? p.ntaps : 1;
+    float* dst = direct ? p.C + orow * p.ldc + tcol * p.c_tap_stride + n0
+                        : p.partial + ((static_cast<long long>(split) * p.M + m) * ntc + tcol) * p.Npad + n0;
     const float alpha = direct ? p.alpha : 1.f, beta = direct ? p.beta : 0.f;
     const bool vec = direct ? (p.vec4 != 0) : true;
     for (int c = 0; c < BN; c += 32) {
@@ -203,34 +208,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
 }
 
-// C[orow(m) * rs + n * cs] = alpha * sum_s partial[s][m][n] + beta * C[...]
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, int Npad, float alpha, float beta,
-                                     float* __restrict__ C, long long rs, long long cs, int unpad_h, int unpad_w) {
-  const long long total = static_cast<long long>(M) * N;
+// C[orow(m) * rs + n * cs + t * ts] = alpha * sum_s partial[s][m][t][n] + beta * C[...]
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, int Npad, int T, float alpha,
+                                     float beta, float* __restrict__ C, long long rs, long long cs, long long ts, int unpad_h,
+                                     int unpad_w) {
+  const long long total = static_cast<long long>(M) * N * T;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / N;
-    const int n = static_cast<int>(i - m * N);
+    const int n = static_cast<int>(i % N);
+    const long long mt = i / N;
+    const int t = static_cast<int>(mt % T);
+    const long long m = mt / T;
     long long orow = m;
     if (unpad_h > 0) {
       orow = unpad_row(m, unpad_h, unpad_w);
       if (orow < 0) continue;
     }
     float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(static_cast<long long>(k) * M + m) * Npad + n];
-    float* d = C + orow * rs + n * cs;
+    for (int k = 0; k < splits; ++k) s += partial[((static_cast<long long>(k) * M + m) * T + t) * Npad + n];
+    float* d = C + orow * rs + n * cs + t * ts;
     *d = beta != 0.f ? fmaf(beta, *d, alpha * s) : alpha * s;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------- operand preparation
-// (n, y, x) -> (n, y+1, x+1) in the zero-padded grid of (h+2) rows of `pitch` (>= w+2) pixels
-__device__ __forceinline__ long long pad_row(long long r, int h, int w, int pitch) {
-  const int x = static_cast<int>(r % w);
-  const long long t = r / w;
-  const int y = static_cast<int>(t % h);
-  const long long n = t / h;
-  return (n * (h + 2) + (y + 1)) * pitch + (x + 1);
+// Both kernels walk the OUTPUT index, so the zero border of a padded plane is written by the same pass (no memset).
+// padded index j -> source row (n, y, x), or -1 on the border / outside the grid (32-bit arithmetic: the callers check the range)
+__device__ __forceinline__ long long src_row_of(long long j, long long padded_total, int h, int w, int pitch) {
+  if (h <= 0) return j;
+  if (j < 0 || j >= padded_total) return -1;
+  const unsigned ju = static_cast<unsigned>(j);
+  const unsigned t = ju / static_cast<unsigned>(pitch);
+  const int xp = static_cast<int>(ju - t * static_cast<unsigned>(pitch));
+  const unsigned n = t / static_cast<unsigned>(h + 2);
+  const int yp = static_cast<int>(t - n * static_cast<unsigned>(h + 2));
+  if (xp < 1 || xp > w || yp < 1 || yp > h) return -1;
+  return (static_cast<long long>(n) * h + (yp - 1)) * w + (xp - 1);
 }
 __device__ __forceinline__ void split1(float v, __nv_bfloat16* h, __nv_bfloat16* l) {
   const __nv_bfloat16 hh = __float2bfloat16_rn(v);
@@ -238,67 +251,97 @@ __device__ __forceinline__ void split1(float v, __nv_bfloat16* h, __nv_bfloat16*
   *l = __float2bfloat16_rn(v - __bfloat162float(hh));
 }
 
-// out[orow(r)][c] = split(src[r * ld + c]); four columns per thread
-__global__ void split_rows_kernel(const float* __restrict__ src, long long ld, long long rows, int cols, int pad_h, int pad_w,
+// out[j][c] = split(src[row(j) * ld + c]) (zeros on the border); four columns per thread
+__global__ void split_rows_kernel(const float* __restrict__ src, long long ld, long long out_rows, int cols, int pad_h, int pad_w,
                                   int pitch, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long out_ld, int vec_in) {
   const int c4n = (cols + 3) >> 2;
-  const long long total = rows * c4n;
+  const long long total = out_rows * c4n;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / c4n;
-    const int c = static_cast<int>(i - r * c4n) * 4;
-    const long long orow = pad_h > 0 ? pad_row(r, pad_h, pad_w, pitch) : r;
-    const float* s = src + r * ld + c;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec_in && c + 4 <= cols) {
-      const float4 t = *reinterpret_cast<const float4*>(s);
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    long long j;
+    int c;
+    if (total < 0x7fffffffLL) {
+      const unsigned iu = static_cast<unsigned>(i), ju = iu / static_cast<unsigned>(c4n);
+      j = ju;
+      c = static_cast<int>(iu - ju * static_cast<unsigned>(c4n)) * 4;
     } else {
-      for (int j = 0; j < 4; ++j)
-        if (c + j < cols) v[j] = s[j];
+      j = i / c4n;
+      c = static_cast<int>(i - j * c4n) * 4;
+    }
+    const long long r = src_row_of(j, out_rows, pad_h, pad_w, pitch);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r >= 0) {
+      const float* s = src + r * ld + c;
+      if (vec_in && c + 4 <= cols) {
+        const float4 t = *reinterpret_cast<const float4*>(s);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        for (int q = 0; q < 4; ++q)
+          if (c + q < cols) v[q] = s[q];
+      }
     }
     __nv_bfloat16 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split1(v[j], &h[j], &l[j]);
-    __nv_bfloat16* ph = hi + orow * out_ld + c;
+    for (int q = 0; q < 4; ++q) split1(v[q], &h[q], &l[q]);
+    __nv_bfloat16* ph = hi + j * out_ld + c;
     if (c + 4 <= cols) {  // out_ld is a multiple of 8 and c of 4: 8-byte aligned
       *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<const uint2*>(h);
-      if (lo) *reinterpret_cast<uint2*>(lo + orow * out_ld + c) = *reinterpret_cast<const uint2*>(l);
+      if (lo) *reinterpret_cast<uint2*>(lo + j * out_ld + c) = *reinterpret_cast<const uint2*>(l);
     } else {
-      for (int j = 0; j < 4; ++j)
-        if (c + j < cols) {
-          ph[j] = h[j];
-          if (lo) lo[orow * out_ld + c + j] = l[j];
+      for (int q = 0; q < 4; ++q)
+        if (c + q < cols) {
+          ph[q] = h[q];
+          if (lo) lo[j * out_ld + c + q] = l[q];
         }
     }
   }
 }
 
-// out[c][orow(r) + shift] = split(src[r * ld + c]): 64 x 64 tiles through shared memory
-__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, long long ld, long long rows, int cols,
+// out[c][j] = split(src[row(j - shift) * ld + c]): 64 (j) x 64 (c) tiles through shared memory, two j per thread on the way out
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ src, long long ld, long long out_k, int cols,
                                                               int pad_h, int pad_w, int pitch, int shift,
                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                               long long out_ld) {
   __shared__ float tile[64][65];
-  const long long r0 = static_cast<long long>(blockIdx.x) * 64;
+  __shared__ long long srow[64];
+  const long long j0 = static_cast<long long>(blockIdx.x) * 64;
   const int c0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
-  for (int rr = ty; rr < 64; rr += 4) {
-    const long long r = r0 + rr;
-    const int c = c0 + tx;
-    tile[rr][tx] = (r < rows && c < cols) ? src[r * ld + c] : 0.f;
+  if (threadIdx.x < 64) {
+    const long long j = j0 + threadIdx.x;
+    srow[threadIdx.x] = j < out_k ? src_row_of(j - shift, out_k, pad_h, pad_w, pitch) : -1;
   }
   __syncthreads();
-  const long long r = r0 + tx;
-  if (r >= rows) return;
-  const long long orow = (pad_h > 0 ? pad_row(r, pad_h, pad_w, pitch) : r) + shift;
-  for (int cc = ty; cc < 64; cc += 4) {
+  {
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 columns x 4 rows per pass
+    const int c = c0 + tx;
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {  // sixteen independent loads in flight
+      const long long r = srow[ty + 4 * q];
+      v[q] = (r >= 0 && c < cols) ? src[r * ld + c] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) tile[ty + 4 * q][tx] = v[q];
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 j pairs x 8 columns per pass
+  const long long j = j0 + 2 * tx;
+  if (j >= out_k) return;
+  const bool pair = j + 1 < out_k;  // out_ld is even and j0 a multiple of 64: the pair is 4-byte aligned
+  for (int cc = ty; cc < 64; cc += 8) {
     const int c = c0 + cc;
     if (c >= cols) break;
-    __nv_bfloat16 h, l;
-    split1(tile[tx][cc], &h, &l);
-    hi[static_cast<long long>(c) * out_ld + orow] = h;
-    if (lo) lo[static_cast<long long>(c) * out_ld + orow] = l;
+    __nv_bfloat16 h[2], l[2];
+    split1(tile[2 * tx][cc], &h[0], &l[0]);
+    split1(tile[2 * tx + 1][cc], &h[1], &l[1]);
+    const long long o = static_cast<long long>(c) * out_ld + j;
+    if (pair) {
+      *reinterpret_cast<uint32_t*>(hi + o) = *reinterpret_cast<const uint32_t*>(h);
+      if (lo) *reinterpret_cast<uint32_t*>(lo + o) = *reinterpret_cast<const uint32_t*>(l);
+    } else {
+      hi[o] = h[0];
+      if (lo) lo[o] = l[0];
+    }
   }
 }
 
@@ -339,8 +382,8 @@ int num_sms_cached() {
 }
 
 // split-K plan: enough CTAs for two per SM when the tile grid alone cannot fill the machine
-int plan_splits(int M, int N, int iters_total, int BN, bool force_partial, size_t ws_bytes, int Npad) {
-  const long long tiles = static_cast<long long>((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+int plan_splits(int M, int N, int T, int iters_total, int BN, bool force_partial, size_t ws_bytes, int Npad) {
+  const long long tiles = static_cast<long long>((M + kBM - 1) / kBM) * ((N + BN - 1) / BN) * T;
   const int target = 2 * num_sms_cached();
   int splits = 1;
   if (tiles < target && iters_total >= 8) {
@@ -349,7 +392,7 @@ int plan_splits(int M, int N, int iters_total, int BN, bool force_partial, size_
     if (splits > 128) splits = 128;
     if (splits < 1) splits = 1;
   }
-  const size_t per = static_cast<size_t>(M) * Npad * sizeof(float);
+  const size_t per = static_cast<size_t>(M) * Npad * T * sizeof(float);
   if (splits > 1 || force_partial) {
     const size_t fit = per ? ws_bytes / per : 0;
     if (fit < 1) return force_partial ? -1 : 1;
@@ -362,15 +405,16 @@ int plan_splits(int M, int N, int iters_total, int BN, bool force_partial, size_
 
 extern "C" {
 
-long long tn_gemm_tc_workspace_bytes(int M, int N) {
+long long tn_gemm_tc_workspace_bytes(int M, int N, int tile_taps) {
   if (M <= 0 || N <= 0) return 0;
+  const long long T = tile_taps > 1 ? tile_taps : 1;
   const long long Npad = (N + 3) / 4 * 4;
   const int BN = pick_bn(N);
-  const long long tiles = static_cast<long long>((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  const long long tiles = static_cast<long long>((M + kBM - 1) / kBM) * ((N + BN - 1) / BN) * T;
   const int target = 2 * num_sms_cached();
   long long splits = tiles < target ? (target + tiles - 1) / tiles : 1;
   if (splits > 128) splits = 128;
-  return splits * M * Npad * static_cast<long long>(sizeof(float));
+  return splits * M * Npad * T * static_cast<long long>(sizeof(float));
 }
 
 int tn_split_bf16(const float* src, long long ld, long long rows, int cols, int transpose, int pad_h, int pad_w, int pad_pitch,
@@ -390,15 +434,18 @@ int tn_split_bf16(const float* src, long long ld, long long rows, int cols, int 
   ProfScope prof_scope(kProfOther, st);
   __nv_bfloat16* h = static_cast<__nv_bfloat16*>(hi);
   __nv_bfloat16* l = static_cast<__nv_bfloat16*>(lo);
+  // extent of the pixel index on the output side (the whole padded grid, borders included)
+  const long long out_n = pad_h > 0 ? rows / (static_cast<long long>(pad_h) * pad_w) * (pad_h + 2) * pad_pitch : rows;
+  if (pad_h > 0 && out_n >= 0x7fffffffLL) return set_error(TN_ERR_INVALID, "padded pixel count %lld exceeds 2^31", out_n);
   if (!transpose) {
     const int vec_in = (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
-    const long long total = rows * ((cols + 3) / 4);
+    const long long total = out_n * ((cols + 3) / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    split_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, ld, rows, cols, pad_h, pad_w, pad_pitch, h, l, out_ld, vec_in);
+    split_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, ld, out_n, cols, pad_h, pad_w, pad_pitch, h, l, out_ld, vec_in);
   } else {
-    dim3 grid(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((cols + 63) / 64));
-    split_transpose_kernel<<<grid, 256, 0, st>>>(src, ld, rows, cols, pad_h, pad_w, pad_pitch, shift, h, l, out_ld);
+    dim3 grid(static_cast<unsigned>((out_n + 63) / 64), static_cast<unsigned>((cols + 63) / 64));
+    split_transpose_kernel<<<grid, 256, 0, st>>>(src, ld, out_n, cols, pad_h, pad_w, pad_pitch, shift, h, l, out_ld);
   }
   TN_CUDA(cudaGetLastError());
   return TN_OK;
@@ -406,8 +453,8 @@ int tn_split_bf16(const float* src, long long ld, long long rows, int cols, int 
 
 int tn_gemm_tc(int M, int N, int K, int ntaps, const int* taps, int passes, const void* a_hi, const void* a_lo, long long a_rows,
                long long a_kdim, long long a_ld, const void* b_hi, const void* b_lo, long long b_rows, long long b_kdim,
-               long long b_ld, float alpha, float beta, float* C, long long c_row_stride, long long c_col_stride, int unpad_h,
-               int unpad_w, void* workspace, long long workspace_bytes, tn_stream_t stream) {
+               long long b_ld, float alpha, float beta, float* C, long long c_row_stride, long long c_col_stride, int tile_taps,
+               long long c_tap_stride, int unpad_h, int unpad_w, void* workspace, long long workspace_bytes, tn_stream_t stream) {
   if (M < 0 || N < 0 || K < 0) return set_error(TN_ERR_INVALID, "negative GEMM size");
   if (M == 0 || N == 0) return TN_OK;
   if (passes != 1 && passes != 3) return set_error(TN_ERR_INVALID, "passes must be 1 (bf16) or 3 (split bf16), got %d", passes);
@@ -432,7 +479,11 @@ int tn_gemm_tc(int M, int N, int K, int ntaps, const int* taps, int passes, cons
   p.passes = passes;
   p.kchunks = (K + kBK - 1) / kBK;
   if (p.kchunks < 1) p.kchunks = 1;
-  p.iters_total = ntaps * p.kchunks;
+  p.tile_taps = tile_taps ? 1 : 0;
+  p.ntn = (N + p.BN - 1) / p.BN;
+  p.c_tap_stride = c_tap_stride;
+  const int T = p.tile_taps ? ntaps : 1;
+  p.iters_total = (p.tile_taps ? 1 : ntaps) * p.kchunks;
   for (int t = 0; t < ntaps; ++t) {
     p.a_row_off[t] = taps ? taps[4 * t + 0] : 0;
     p.a_k_off[t] = taps ? taps[4 * t + 1] : 0;
@@ -450,9 +501,9 @@ int tn_gemm_tc(int M, int N, int K, int ntaps, const int* taps, int passes, cons
   p.unpad_w = unpad_w;
   const bool force_partial = c_col_stride != 1;
   const size_t ws = workspace ? static_cast<size_t>(workspace_bytes < 0 ? 0 : workspace_bytes) : 0;
-  int splits = plan_splits(M, N, p.iters_total, p.BN, force_partial, ws, p.Npad);
+  int splits = plan_splits(M, N, T, p.iters_total, p.BN, force_partial, ws, p.Npad);
   if (splits < 0) return set_error(TN_ERR_INVALID, "a strided output needs a workspace of at least %lld bytes",
-                                   static_cast<long long>(M) * p.Npad * 4);
+                                   static_cast<long long>(M) * p.Npad * T * 4);
   p.iters_per_split = (p.iters_total + splits - 1) / splits;
   splits = (p.iters_total + p.iters_per_split - 1) / p.iters_per_split;  // no empty split
   p.splits = splits;
@@ -475,7 +526,7 @@ int tn_gemm_tc(int M, int N, int K, int ntaps, const int* taps, int passes, cons
     TN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  dim3 grid((M + kBM - 1) / kBM, (N + p.BN - 1) / p.BN, splits);
+  dim3 grid((M + kBM - 1) / kBM, p.ntn * T, splits);
   {
     ProfScope prof_scope(kProfConvGemm, st);
     gemm_tc_kernel<<<grid, kThreads, smem, st>>>(mAh, mAl, mBh, mBl, p);
@@ -483,11 +534,11 @@ int tn_gemm_tc(int M, int N, int K, int ntaps, const int* taps, int passes, cons
   }
   if (use_partial) {
     ProfScope prof_scope(kProfOther, st);
-    const long long total = static_cast<long long>(M) * N;
+    const long long total = static_cast<long long>(M) * N * T;
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p.partial, splits, M, N, p.Npad, alpha, beta, C, c_row_stride,
-                                                                      c_col_stride, unpad_h, unpad_w);
+    splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p.partial, splits, M, N, p.Npad, T, alpha, beta, C, c_row_stride,
+                                                                      c_col_stride, c_tap_stride, unpad_h, unpad_w);
     TN_CUDA(cudaGetLastError());
   }
   return TN_OK;

@@ -138,12 +138,13 @@ class CNNTrainGraph(object):
                     P8 = tcgemm.pitch8(W)
                     Mp8 = tcgemm.padded_rows(N, H, W, P8)
                     xT = tcgemm.planes(x2, transpose=True, pad_hw=(H, W), lo=lo, pitch=P8)                       # (Cin, Mp8)
-                    dyT = [tcgemm.planes(dy2, transpose=True, pad_hw=(H, W), lo=lo, pitch=P8, shift=dx) for dx in (-1, 0, 1)]
+                    dyT = tcgemm.empty_planes(3 * Cout, Mp8, dev, lo=lo)                                         # (dx, Cout) x Mp8
+                    for dx in (-1, 0, 1):
+                        tcgemm.planes(dy2, transpose=True, pad_hw=(H, W), lo=lo, pitch=P8, shift=dx, into=dyT, row0=(dx + 1) * Cout)
                     dwk = torch.empty(Cout, K, device=dev)
-                    for t in range(9):
-                        dy_, dx_ = t // 3 - 1, t % 3 - 1
-                        tcgemm.gemm(xT, dyT[dx_ + 1], Cin, Cout, Mp8, dwk[:, t * Cin:], 1, K, taps=[(0, 0, 0, -dy_ * P8)],
-                                    passes=passes)
+                    # tap t = (dy, dx): B rows (dx+1)*Cout.., contraction offset -dy*P8; D_t[c, n] -> dwk[n, t*Cin + c]
+                    tcgemm.gemm(xT, dyT, Cin, Cout, Mp8, dwk, 1, K, taps=[(0, 0, (t % 3) * Cout, -(t // 3 - 1) * P8) for t in range(9)],
+                                passes=passes, tile_taps=True, c_tap_stride=Cin)
                     del xT, dyT
                     Wp._accumulate_grad(dwk.reshape(Cout, R, S, Cin).permute(0, 3, 1, 2).contiguous())
                 if src.needs_grad:

@@ -43,10 +43,11 @@ def pitch8(w):
     return _r8(w + 2)
 
 
-def planes(src, transpose=False, pad_hw=None, lo=True, pitch=None, shift=0):
+def planes(src, transpose=False, pad_hw=None, lo=True, pitch=None, shift=0, into=None, row0=0):
     """src: 2-D fp32 view (rows, cols) with unit column stride.  transpose=False: the contraction runs along the columns;
     True: along the rows.  pad_hw=(H, W): rows are (n, y, x) pixels, re-indexed into the zero-padded grid of (H+2) rows of `pitch`
-    (default W+2) pixels; shift (-1/0/+1, transposed padded planes): every pixel lands `shift` positions later."""
+    (default W+2) pixels; shift (-1/0/+1, transposed padded planes): every pixel lands `shift` positions later.
+    into / row0: write into rows [row0, row0 + rows) of an existing Planes of the same contraction length."""
     assert src.dim() == 2 and src.dtype == torch.float32 and src.is_cuda and (src.shape[1] == 1 or src.stride(1) == 1), \
         (src.shape, src.stride(), src.dtype)
     R, C = src.shape
@@ -58,13 +59,22 @@ def planes(src, transpose=False, pad_hw=None, lo=True, pitch=None, shift=0):
         h = w = 0
         Rp = R
     rows, kdim = (C, Rp) if transpose else (Rp, C)
-    ld = _r8(kdim)
-    alloc = torch.zeros if pad_hw is not None else torch.empty
-    hi = alloc((rows, ld), dtype=torch.bfloat16, device=src.device)
-    lo_t = alloc((rows, ld), dtype=torch.bfloat16, device=src.device) if lo else None
+    if into is not None:
+        assert into.kdim == kdim and row0 + rows <= into.rows and (into.lo is not None) == bool(lo)
+        hi, lo_t, ld = into.hi[row0:], (into.lo[row0:] if lo else None), into.ld
+    else:
+        ld = _r8(kdim)
+        hi = torch.empty((rows, ld), dtype=torch.bfloat16, device=src.device)
+        lo_t = torch.empty((rows, ld), dtype=torch.bfloat16, device=src.device) if lo else None
     check(lib().tn_split_bf16(dptr(src), src.stride(0), R, C, int(transpose), h, w, int(pitch or 0), int(shift), dptr(hi),
                               dptr(lo_t) if lo else None, ld, stream_ptr()))
-    return Planes(hi, lo_t, rows, kdim, ld)
+    return into if into is not None else Planes(hi, lo_t, rows, kdim, ld)
+
+
+def empty_planes(rows, kdim, device, lo=True):
+    ld = _r8(kdim)
+    return Planes(torch.empty((rows, ld), dtype=torch.bfloat16, device=device),
+                  torch.empty((rows, ld), dtype=torch.bfloat16, device=device) if lo else None, rows, kdim, ld)
 
 
 _WS = {}
@@ -78,9 +88,11 @@ def _workspace(device, nbytes):
     return ws
 
 
-def gemm(A, B, M, N, K, C, c_row_stride, c_col_stride=1, taps=None, alpha=1.0, beta=0.0, unpad_hw=None, passes=3):
+def gemm(A, B, M, N, K, C, c_row_stride, c_col_stride=1, taps=None, alpha=1.0, beta=0.0, unpad_hw=None, passes=3,
+         tile_taps=False, c_tap_stride=0):
     """C[orow(m)*c_row_stride + n*c_col_stride] = alpha * sum_t sum_{k<K} A[m + ar_t, ak_t + k] * B[n + br_t, bk_t + k] + beta * C.
-    C: the fp32 tensor (or view) whose data pointer is element (0, 0) of the output; taps: list of (ar, ak, br, bk)."""
+    C: the fp32 tensor (or view) whose data pointer is element (0, 0) of the output; taps: list of (ar, ak, br, bk).
+    tile_taps: the taps are independent products of one launch, tap t written at C + t * c_tap_stride."""
     if passes == 3:
         assert A.lo is not None and B.lo is not None
     nt = 1 if taps is None else len(taps)
@@ -88,12 +100,12 @@ def gemm(A, B, M, N, K, C, c_row_stride, c_col_stride=1, taps=None, alpha=1.0, b
     if taps is not None:
         flat = [int(v) for t in taps for v in t]
         tap_arr = (ctypes.c_int * len(flat))(*flat)
-    nbytes = int(lib().tn_gemm_tc_workspace_bytes(M, N))
+    nbytes = int(lib().tn_gemm_tc_workspace_bytes(M, N, nt if tile_taps else 0))
     ws = _workspace(C.device, nbytes)
     uh, uw = unpad_hw if unpad_hw is not None else (0, 0)
     check(lib().tn_gemm_tc(M, N, K, nt, tap_arr, passes, dptr(A.hi), dptr(A.lo) if A.lo is not None else None, A.rows, A.kdim, A.ld,
                            dptr(B.hi), dptr(B.lo) if B.lo is not None else None, B.rows, B.kdim, B.ld, alpha, beta, dptr(C),
-                           c_row_stride, c_col_stride, uh, uw, dptr(ws), ws.numel(), stream_ptr()))
+                           c_row_stride, c_col_stride, int(tile_taps), c_tap_stride, uh, uw, dptr(ws), ws.numel(), stream_ptr()))
     return C
 
 

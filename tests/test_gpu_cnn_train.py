@@ -21,9 +21,14 @@ def _load(block, p, dev):
         prm._version += 1
 
 
+@pytest.mark.parametrize("gemm", ["x3", "fp32"])
 @pytest.mark.parametrize("arch", ["resnet18_v2", "densenet121"])
-def test_frame_model_gradients_match_oracle_autograd(arch):
-    """train.py's default flow: FrameModel(backbone, 11) on single frames, SoftmaxCrossEntropyLoss, ag.backward."""
+def test_frame_model_gradients_match_oracle_autograd(arch, gemm, monkeypatch):
+    """train.py's default flow: FrameModel(backbone, 11) on single frames, SoftmaxCrossEntropyLoss, ag.backward.
+    gemm = fp32: the SIMT SGEMM (24-bit operands, the parity anchor); x3: the default, split-bf16 on tcgen05 -- operands carry 18
+    significant bits (hi + lo, 2^-18 relative), measured: features within 8e-5 of the fp64 oracle (2.5e-6 for fp32), which moves the
+    tensors above the last ReLU by up to 3e-3 of their largest entry."""
+    monkeypatch.setenv("TN_TRAIN_GEMM", gemm)
     from oracle import vision as O
     from tennis_b200 import autograd, model_zoo
     from tennis_b200.gluon import SoftmaxCrossEntropyLoss
@@ -86,7 +91,7 @@ def test_frame_model_gradients_match_oracle_autograd(arch):
     worst_cos = min(coss, key=lambda e: e[1])
     print("  lowest cosine %.6f at %s" % (worst_cos[1], worst_cos[0]))
     final_gamma = "bn5.gamma" if arch == "densenet121" else "bn_final.gamma"
-    assert dict(errs)[final_gamma] < 1e-3           # above every ReLU decision that can differ: tight
+    assert dict(errs)[final_gamma] < (1e-3 if gemm == "fp32" else 8e-3)  # above every ReLU decision that can differ: tight
     assert worst_cos[1] > 0.995, worst_cos
     assert worst[1] < 0.25, worst
     # running statistics: 0.9 * old + 0.1 * batch (biased variance)
