@@ -376,6 +376,13 @@ def run_ours(args, rank, world, local_rank):
     except Exception as exc:
         extra["train_step"] = {"error": repr(exc)}
 
+    # ---- the same step with a TRAINABLE backbone (train.py without --freeze_backbone / --feats_model): training-mode BatchNorm,
+    # forward / data-gradient / weight-gradient contractions on tcgen05 (csrc/tn_gemm_tc.cu), gradient all-reduce of every parameter
+    try:
+        extra["train_step_trainable"] = bench_train_step_trainable(model, clips_dev, device, world, barrier)
+    except Exception as exc:
+        extra["train_step_trainable"] = {"error": repr(exc)}
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         conv_ms = prof["conv_ms"]
@@ -660,6 +667,63 @@ def bench_train_step(model, clips_dev, device, world, barrier, args, steps=3):
                         "DenseNet-121 backbone, NCCL gradient all-reduce" % (per * world, T, per),
             "ms_per_step": ms, "clips_per_s": per * world / (ms * 1e-3), "frames_per_s": per * world * T / (ms * 1e-3),
             "scaling": "strong", "loss_finite": lv == lv}
+
+
+def bench_train_step_trainable(model, clips_dev, device, world, barrier, clips_per_gpu=8, steps=2):
+    """CNN+GRU training step with the DenseNet-121 backbone TRAINED end to end (reference train.py:410-424 without
+    --freeze_backbone): batch-statistics BatchNorm, convolution forward / dgrad / wgrad as split-bf16 tcgen05 GEMMs, bi-GRU BPTT,
+    SGD with momentum on every parameter, NCCL all-reduce of all gradients.  Weak scaling: `clips_per_gpu` clips on every GPU."""
+    import torch
+    import torch.distributed as dist
+    from tennis_b200 import _lib, autograd, tcgemm
+    from tennis_b200.gluon import SoftmaxCrossEntropyLoss, Trainer
+    x = clips_dev[:clips_per_gpu]
+    per = x.shape[0]
+    backbone_params = list(model.td.model.collect_params().values())
+    saved = [prm.grad_req for prm in backbone_params]
+    for prm in backbone_params:
+        if not prm.name.endswith(("running_mean", "running_var")):
+            prm.grad_req = 'write'
+    labels = torch.arange(per, device=device) % CLASSES
+    loss_fn = SoftmaxCrossEntropyLoss()
+    tr = Trainer(model.collect_params(), 'sgd', {'learning_rate': 1e-4, 'momentum': 0.9, 'wd': 1e-4})
+
+    def step():
+        with autograd.record():
+            loss = loss_fn(model(x), labels)
+        autograd.backward([loss])
+        tr.step(per * world)
+        return loss
+    try:
+        loss = step()
+        barrier()
+        _lib.profile_read(reset=True)
+        _lib.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        barrier()
+        prof = _lib.profile_read(reset=True)
+        _lib.profile_enable(False)
+        t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item() / steps
+        lv = float(loss.float().mean().item())
+    finally:
+        for prm, g in zip(backbone_params, saved):
+            prm.grad_req = g
+    frames = per * world * T
+    return {"workload": "CNN+GRU training step (fwd+bwd+SGD) with a TRAINABLE DenseNet-121, %d clips x %d frames per GPU, "
+                        "NCCL all-reduce of every gradient" % (per, T),
+            "ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "clips_per_s": per * world / (ms * 1e-3), "scaling": "weak",
+            "gemm": "TN_TRAIN_GEMM=%s (x3: split-bf16, three tcgen05 products per contraction)" % tcgemm.mode(),
+            "tensor_core_gemm_ms_per_step": prof["conv_ms"] / steps, "tensor_core_gemm_launches_per_step": prof["conv_launches"] // steps,
+            "other_kernels_ms_per_step": prof["other_ms"] / steps,
+            "round1_simt_fp32_path": "954 ms per 64 frames = 67 frames/s on the same GPU type (profiles/r2_cnn_train.md)",
+            "loss_finite": lv == lv}
 
 
 def bench_resnet18(clips_dev, device, steps=5):

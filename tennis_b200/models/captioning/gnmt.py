@@ -312,8 +312,10 @@ class NMTModel(Block):
             from .train_graph import GNMTTrainGraph
             self._train_calls = getattr(self, "_train_calls", 0) + 1
             graph = GNMTTrainGraph(self, seed=self._train_calls)
-            logits = graph.forward(self.src_embed(src_seq), tgt_seq, src_valid_length, tgt_valid_length)
-            autograd.tag(logits, graph.backward, None)
+            src = self.src_embed(src_seq)
+            logits = graph.forward(src, tgt_seq, src_valid_length, tgt_valid_length)
+            # a source produced by a trainable TimeDistributed(CNN) continues the walk with d(loss)/d(source features)
+            autograd.tag(logits, graph.backward, src if getattr(src, "_tn_node", None) is not None else None)
             return logits, [[], []]
         encoder_outputs, enc_add = self.encode(src_seq, valid_length=src_valid_length)
         decoder_states = self.decoder.init_state_from_encoder(encoder_outputs, encoder_valid_length=src_valid_length)

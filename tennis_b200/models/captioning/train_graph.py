@@ -179,6 +179,8 @@ class GNMTTrainGraph(object):
         if enc._use_residual or dec._use_residual:
             raise NotImplementedError("use_residual=True is never selected by the scripts (gnmt.py:408 default False)")
         dev = src.device
+        # a source that carries a backward (frames through a trainable TimeDistributed(CNN), train_gnmt.py:150-170) wants d(loss)/d(src)
+        self.need_dsrc = getattr(src, "_tn_node", None) is not None
         src = src.contiguous().float()
         B, Ts, _ = src.shape
         H = enc._hidden_size
@@ -369,7 +371,7 @@ class GNMTTrainGraph(object):
             if layer["mask"] is not None:
                 d = mul_mask(d, layer["mask"], None)
             dh_last, dc_last = dinit[i] if i < len(dinit) and dinit[i] is not None else (None, None)
-            need_dx = i > 0
+            need_dx = i > 0 or self.need_dsrc
             if layer["kind"] == "uni":
                 d, _, _ = layer["un"].backward(d, dh_last, dc_last, need_dx=need_dx)
             else:
@@ -380,4 +382,4 @@ class GNMTTrainGraph(object):
                 if need_dx:
                     d = dxl
                     check(L.tn_axpy(dptr(d), dptr(_seq_reverse(dxr, self.ridx)), 1.0, d.numel(), stream_ptr()))
-        return None
+        return d if self.need_dsrc else None  # (B, T_src, D): gradient of the source features, zero past valid_length

@@ -109,3 +109,33 @@ def test_gnmt_adam_steps_reduce_loss_with_dropout():
         assert last == last and abs(last) < 1e4
     print("loss %.4f -> %.4f after 26 Adam steps" % (first, last))
     assert last < first
+
+
+@pytest.mark.parametrize("cell", ["lstm", "gru"])
+def test_gnmt_source_feature_gradient_matches_oracle_autograd(cell):
+    """train_gnmt.py:150-170 with a trainable CNN as `src_embed`: the training graph hands d(loss)/d(source features) to whatever
+    produced the source (here a recorded leaf that captures it); rows past valid_length get exactly zero."""
+    from oracle import captioning as C
+    from tennis_b200 import autograd
+    from tennis_b200.gluon import MaskedSoftmaxCELoss
+    H, D, E, V = 32, 48, 20, 37
+    model, p, _ = _build(cell, H, D, E, V, 0.3)
+    B, T, Tt = 5, 9, 7
+    x, vl = C.synthetic_sources(B, T, D, seed=3)
+    tgt = torch.randint(0, V, (B, Tt), generator=torch.Generator().manual_seed(5)).float()
+    tvl = torch.tensor([7., 6., 4., 2., 7.])
+    xr = x.clone().requires_grad_(True)
+    out = C.nmt_forward({k: v.clone() for k, v in p.items()}, xr, tgt[:, :-1], vl, tvl - 1, cell=cell, H=H)
+    C.masked_softmax_ce(out, tgt[:, 1:], tvl - 1).sum().backward()
+    got = []
+    xs = x.cuda()
+    autograd.tag(xs, lambda g: got.append(g) or None, None)   # stands for TimeDistributed(CNN)'s output
+    with autograd.record():
+        o, _ = model(xs, tgt[:, :-1].cuda(), vl.cuda(), tvl.cuda() - 1)
+        loss = MaskedSoftmaxCELoss()(o, tgt[:, 1:].cuda(), tvl.cuda() - 1)
+    autograd.backward([loss])
+    assert len(got) == 1 and tuple(got[0].shape) == (B, T, D)
+    d = got[0].cpu()
+    assert (d - xr.grad).abs().max().item() < 2e-4 * xr.grad.abs().max().item()
+    for b in range(B):
+        assert (d[b, int(vl[b]):] == 0).all()

@@ -81,6 +81,15 @@ def test_train_cnn_framewise_trainable_backbone(tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "models", "vision", "experiments", "t044", "0000.params"))
 
 
+def test_train_gnmt_trainable_cnn_source(tmp_path):
+    """train_gnmt.py:150-170 of the reference: frames -> TimeDistributed(trainable CNN) -> GNMT; the encoder's source-feature
+    gradient trains the backbone (one epoch on the synthetic stand-in)."""
+    out = _run([os.path.join(ROOT, "train_gnmt.py"), "--backbone", "resnet18_v2", "--data_shape", "224", "--cell_type", "gru",
+                "--batch_size", "2", "--test_batch_size", "2", "--tgt_max_len", "10", "--every", "8", "--epochs", "1", "--log_interval",
+                "1", "--num_hidden", "32", "--synthetic", "--model_id", "t103"], str(tmp_path))
+    assert "Training the CNN through the captioner" in out and "[Epoch 0] valid Loss=" in out
+
+
 def test_train_frozen_backbone_cnn_gru(tmp_path):
     out = _run([os.path.join(ROOT, "train.py"), "--backbone", "resnet18_v2", "--freeze_backbone", "--temp_pool", "gru", "--window", "4",
                 "--data_shape", "224", "--batch_size", "4", "--every", "24,48,48", "--epochs", "1", "--synthetic", "--model_id",

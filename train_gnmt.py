@@ -123,8 +123,9 @@ def main(_argv):
     exp_dir = os.path.join('models', 'captioning', 'experiments', FLAGS.model_id)
     cli.setup_logging(exp_dir)
     if FLAGS.feats_model is None and not FLAGS.freeze_backbone:
-        raise SystemExit("the captioner's training graph takes its source features as constants (the gradient is not routed into "
-                         "the CNN, DESIGN.md section 8): pass --feats_model <id> (the published setting) or --freeze_backbone")
+        logging.info('Training the CNN through the captioner: the source-feature gradient of the encoder is routed into the '
+                     'backbone (train_gnmt.py:150-170 of the reference); activations of every source frame are kept, use a '
+                     'small --batch_size / --every')
     syn = {} if FLAGS.synthetic else None
     train_tf = test_tf = None
     if FLAGS.feats_model is None:  # frames through the (frozen) CNN: host-side geometry as in train_gnmt.py:172-188
