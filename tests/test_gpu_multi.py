@@ -61,6 +61,9 @@ if world > 1:
 """
 
 
+_CACHE = {}
+
+
 def _run(world, out_path, tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % {"root": ROOT})
@@ -76,10 +79,16 @@ def _run(world, out_path, tmp_path):
     return torch.load(out_path)
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_world2_inference_bit_identical_and_sgd_step_equal(tmp_path):
-    one = _run(1, str(tmp_path / "w1.pt"), tmp_path)
-    two = _run(2, str(tmp_path / "w2.pt"), tmp_path)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_world_n_inference_bit_identical_and_sgd_step_equal(world, tmp_path):
+    """W in {1, 2, 4, 8} give bit-identical logits (also with ragged frame / clip shards and ranks without work: 6 and
+    7 clips, 21 frames, 8 training clips over up to 8 ranks)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs >= %d GPUs" % world)
+    if "one" not in _CACHE:  # the single-process result is the same for every world size
+        _CACHE["one"] = _run(1, str(tmp_path / "w1.pt"), tmp_path)
+    one = _CACHE["one"]
+    two = _run(world, str(tmp_path / "wn.pt"), tmp_path)
     assert one["out"].shape == (6, 11) and torch.equal(one["out"], two["out"])
     assert one["out_odd"].shape == (7, 11) and torch.equal(one["out_odd"], two["out_odd"])
     # gradient sums associate differently across ranks (fp32): equal to rounding, not bit-identical
