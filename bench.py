@@ -788,7 +788,7 @@ def bench_gru_head(model, device, iters=20):
     return {"workload": "BiGRU(128)+max+Dense(11) on (256,32,1024) bf16 features", "us_per_call": us,
             "algorithmic_bytes": bytes_alg, "achieved_gbs": gbs, "hbm_peak_gbs": peaks["hbm_gbs"],
             "frac_of_hbm_roofline": gbs / peaks["hbm_gbs"],
-            "note": "32 serial recurrence steps: latency-bound (per-step breakdown: profiles/r2_gru_head.md)"}
+            "note": "32 serial recurrence steps: latency-bound (per-step breakdown: profiles/r2_summary.md section 5)"}
 
 
 def main():
