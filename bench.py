@@ -33,12 +33,16 @@ TRAIN_GLOBAL_CLIPS = 256  # BASELINE.json configs[2]: 256 clips sharded over the
 
 
 def kernel_source_hash():
-    """sha256 over the CUDA sources: profiles/conv_traffic.json is only valid for the kernels it was measured on."""
+    """sha256 over the CUDA sources of the inference CNN (everything a DenseNet-121 forward launches): profiles/conv_traffic.json
+    is only valid for the kernels it was measured on."""
     import hashlib
     d = os.path.join(ROOT, "tennis_b200", "csrc")
     h = hashlib.sha256()
+    path_sources = ("tn_backbone.cu", "tn_common.cu", "tn_common.h", "tn_conv1x1_ts.cu", "tn_conv1x1_ts.h", "tn_conv3x3.cu",
+                    "tn_conv3x3.h", "tn_conv_gemm.cu", "tn_conv_gemm.h", "tn_dense_fused.cu", "tn_dense_fused.h", "tn_elementwise.cu",
+                    "tn_elementwise.h", "tn_precise.cu", "tn_precise.h", "tn_ptx.cuh", "tn_stem.cu", "tn_stem.h")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
+        if f in path_sources:
             with open(os.path.join(d, f), "rb") as fh:
                 h.update(f.encode() + b"\0" + fh.read())
     return h.hexdigest()[:16]
