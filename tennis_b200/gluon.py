@@ -420,6 +420,15 @@ class Trainer(object):
             for p in live:
                 if p._grad is None:
                     p._grad = torch.zeros_like(p.data())
+            # a rank that has not materialised a deferred-shape parameter yet would enter a smaller all-reduce and hang every
+            # rank: compare the bucket sizes first (one 2-element all-reduce) and fail loudly instead
+            n = sum(p._grad.numel() for p in live)
+            chk = torch.tensor([n, -n], dtype=torch.int64, device=live[0]._grad.device if live else "cuda")
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+            if int(chk[0]) != -int(chk[1]):
+                raise RuntimeError("Trainer.step: the ranks hold different parameter sets (%d gradient elements here, %d..%d over "
+                                   "the ranks): run one forward on every rank before the first step (deferred-shape parameters)"
+                                   % (n, -int(chk[1]), int(chk[0])))
         else:
             live = [p for p in self._params if p.grad_req != 'null' and p._grad is not None]
         for p in live:

@@ -4,6 +4,7 @@ import subprocess
 import sys
 
 import pytest
+import torch
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -88,6 +89,26 @@ def test_train_gnmt_trainable_cnn_source(tmp_path):
                 "--batch_size", "2", "--test_batch_size", "2", "--tgt_max_len", "10", "--every", "8", "--epochs", "1", "--log_interval",
                 "1", "--num_hidden", "32", "--synthetic", "--model_id", "t103"], str(tmp_path))
     assert "Training the CNN through the captioner" in out and "[Epoch 0] valid Loss=" in out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_scripts_with_num_gpus_2(tmp_path):
+    """--num_gpus 2 (reference train.py:103): the script re-launches itself with one process per GPU, shards every batch, sums the
+    gradients over NCCL and lets rank 0 write the artefacts exactly once."""
+    args = [os.path.join(ROOT, "train.py"), "--feats_model", "0006", "--temp_pool", "gru", "--window", "8", "--batch_size", "16",
+            "--every", "4,8,8", "--epochs", "2", "--log_interval", "2", "--lr", "0.05", "--synthetic", "--model_id", "t045",
+            "--num_gpus", "2"]
+    out = _run(args, str(tmp_path))
+    exp = os.path.join(str(tmp_path), "models", "vision", "experiments", "t045")
+    assert os.path.exists(os.path.join(exp, "0001.params")) and "test AVG_NB_f1" in out
+    assert len(open(os.path.join(exp, "scores.txt")).read().split()) == 4   # written once, by rank 0
+    out = _run([os.path.join(ROOT, "evaluate.py"), "--backbone", "resnet18_v2", "--temp_pool", "gru", "--window", "4", "--data_shape",
+                "224", "--batch_size", "6", "--every", "24,48,48", "--synthetic", "--model_id", "t046", "--num_gpus", "2"], str(tmp_path))
+    assert "AVG_NB_f1" in out
+    out = _run([os.path.join(ROOT, "train_gnmt.py"), "--feats_model", "0006", "--cell_type", "gru", "--batch_size", "4",
+                "--test_batch_size", "4", "--tgt_max_len", "10", "--epochs", "1", "--log_interval", "1", "--num_hidden", "32",
+                "--synthetic", "--model_id", "t104", "--num_gpus", "2"], str(tmp_path))
+    assert "[Epoch 0] valid Loss=" in out
 
 
 def test_train_frozen_backbone_cnn_gru(tmp_path):

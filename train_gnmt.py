@@ -40,6 +40,12 @@ def train(data_train, data_val, data_test, model, loss_function, val_tgt_sentenc
     train_data_loader, val_data_loader, test_data_loader = get_dataloaders(data_train, data_val, data_test, FLAGS.batch_size,
                                                                            FLAGS.test_batch_size, FLAGS.num_buckets)
     best_valid_bleu = 0.0
+    if cli.world()[1] > 1:
+        # deferred-shape parameters (the encoder's input size comes from the data) are created by the first forward; a rank
+        # whose shard of the first batch is empty would otherwise enter Trainer.step with fewer parameters than its peers
+        src0, tgt0, svl0, tvl0 = next(iter(train_data_loader))
+        model(src0[:1].to(ctx).float(), tgt0[:1, :-1].to(ctx).float(), svl0[:1].to(ctx), tvl0[:1].to(ctx) - 1)
+        cli.broadcast_parameters(model)
     for epoch_id in range(start_epoch, FLAGS.epochs):
         log_avg_loss, log_wc, nlog = 0.0, 0.0, 0
         log_start_time = time.time()
