@@ -11,6 +11,7 @@
 
 #include "tn_common.h"
 #include "tn_conv3x3.h"
+#include "tn_conv3x3_c64.h"
 #include "tn_dense_fused.h"
 #include "tn_elementwise.h"
 #include "tn_precise.h"
@@ -40,7 +41,9 @@ struct Transition {
 struct ResBlock {
   BnDev bn1, bn2;
   ConvDev conv1, conv2, ds;
+  Conv3x3C64Dev c1h, c2h;  // 64 -> 64 / stride 1 blocks: the same weights packed for the halo kernel (tn_conv3x3_c64.cu)
   bool has_ds;
+  bool halo = false;
   int cin, c, stride;
 };
 
@@ -542,6 +545,11 @@ int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int 
   __nv_bfloat16* xb = ws.get<__nv_bfloat16>(act);
   __nv_bfloat16* tb = ws.get<__nv_bfloat16>(act);
   __nv_bfloat16* rb = ws.get<__nv_bfloat16>(act);
+  // 64 -> 64 / stride 1 blocks (stage 1) run the halo kernel on pre-activated, zero-padded tensors (TN_RESNET_NO_HALO=1: gather GEMM)
+  const bool halo_ok = conv3x3_c64_supported(d.Hp, d.Wp) && !getenv("TN_RESNET_NO_HALO");
+  const size_t padded = static_cast<size_t>(n) * (d.Hp + 2) * (d.Wp + 2) * 64;
+  __nv_bfloat16* apad = halo_ok ? ws.get<__nv_bfloat16>(padded) : nullptr;
+  __nv_bfloat16* tpad = halo_ok ? ws.get<__nv_bfloat16>(padded) : nullptr;
   if (dry) return TN_OK;
   {
     // 7x7/2 stem == 4x4/1 conv on the zero-padded space-to-depth image (tn_stem.cu), BN folded, ReLU
@@ -555,8 +563,24 @@ int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int 
   int H = d.Hp, W = d.Wp;
   __nv_bfloat16* x = xa;
   __nv_bfloat16* y = xb;
-  for (const ResBlock& B : bb->rblocks) {
+  bool apad_ready = false;  // apad already holds relu(bn1(x)) of the current block (written by the previous block's conv2)
+  for (size_t bi = 0; bi < bb->rblocks.size(); ++bi) {
+    const ResBlock& B = bb->rblocks[bi];
     const int Ho = (H + 2 - 3) / B.stride + 1, Wo = (W + 2 - 3) / B.stride + 1;
+    if (B.halo && halo_ok) {
+      if (!apad_ready) TN_CUDA(launch_bn_relu_pad(x, 64, n, H, W, 64, B.bn1.scale, B.bn1.shift, apad, st));
+      // conv1: relu(bn2(conv(a))) -> padded, activated; conv2: + x -> raw block output (+ the next block's activated input)
+      TN_CUDA(launch_conv3x3_c64(B.c1h, apad, n, H, W, B.bn2.shift, 1, nullptr, 0, nullptr, 0, tpad, nullptr, nullptr, bb->num_sms, st));
+      const bool next_halo = bi + 1 < bb->rblocks.size() && bb->rblocks[bi + 1].halo;
+      const ResBlock* nx = next_halo ? &bb->rblocks[bi + 1] : nullptr;
+      TN_CUDA(launch_conv3x3_c64(B.c2h, tpad, n, H, W, nullptr, 0, x, 64, y, 64, next_halo ? apad : nullptr,
+                                 nx ? nx->bn1.scale : nullptr, nx ? nx->bn1.shift : nullptr, bb->num_sms, st));
+      apad_ready = next_halo;
+      __nv_bfloat16* t = x;
+      x = y;
+      y = t;
+      continue;
+    }
     const __nv_bfloat16* res = x;
     int res_cs = B.cin;
     if (B.has_ds) {  // downsample acts on relu(bn1(x)) (BasicBlockV2)
@@ -719,8 +743,16 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
         B.stride = (b == 0 && s > 0) ? 2 : 1;
         B.has_ds = (b == 0 && cin != B.c);
         ok = ok && take_bn(cur, bb->arena, cin, &B.bn1);
-        ok = ok && take_conv_bn(cur, bb->arena, B.c, cin, 3, 3, tn::kModeConv, &B.conv1, &B.bn2);
+        const float* w1 = cur.p;
+        std::vector<float> hs2;
+        ok = ok && take_conv_bn(cur, bb->arena, B.c, cin, 3, 3, tn::kModeConv, &B.conv1, &B.bn2, &hs2);
+        const float* w2 = cur.p;
         ok = ok && take_conv(cur, bb->arena, B.c, B.c, 3, 3, tn::kModeConv, &B.conv2);
+        B.halo = ok && cin == 64 && B.c == 64 && B.stride == 1;
+        if (B.halo) {
+          ok = ok && tn::make_conv3x3_c64(bb->arena, w1, hs2.data(), &B.c1h);
+          ok = ok && tn::make_conv3x3_c64(bb->arena, w2, nullptr, &B.c2h);
+        }
         if (B.has_ds) ok = ok && take_conv(cur, bb->arena, B.c, cin, 1, 1, tn::kModeConv, &B.ds);
         bb->rblocks.push_back(B);
         cin = B.c;
