@@ -41,9 +41,9 @@ struct Transition {
 struct ResBlock {
   BnDev bn1, bn2;
   ConvDev conv1, conv2, ds;
-  Conv3x3C64Dev c1h, c2h;  // 64 -> 64 / stride 1 blocks: the same weights packed for the halo kernel (tn_conv3x3_c64.cu)
+  Conv3x3C64Dev c1h, c2h;  // stride-1 3x3 convs with 64 / 128 channels: the same weights packed for the halo kernel
   bool has_ds;
-  bool halo = false;
+  bool h1 = false, h2 = false;  // conv1 / conv2 can run on the halo kernel (tn_conv3x3_c64.cu)
   int cin, c, stride;
 };
 
@@ -545,11 +545,12 @@ int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int 
   __nv_bfloat16* xb = ws.get<__nv_bfloat16>(act);
   __nv_bfloat16* tb = ws.get<__nv_bfloat16>(act);
   __nv_bfloat16* rb = ws.get<__nv_bfloat16>(act);
-  // 64 -> 64 / stride 1 blocks (stage 1) run the halo kernel on pre-activated, zero-padded tensors (TN_RESNET_NO_HALO=1: gather GEMM)
-  const bool halo_ok = conv3x3_c64_supported(d.Hp, d.Wp) && !getenv("TN_RESNET_NO_HALO");
-  const size_t padded = static_cast<size_t>(n) * (d.Hp + 2) * (d.Wp + 2) * 64;
-  __nv_bfloat16* apad = halo_ok ? ws.get<__nv_bfloat16>(padded) : nullptr;
-  __nv_bfloat16* tpad = halo_ok ? ws.get<__nv_bfloat16>(padded) : nullptr;
+  // stride-1 3x3 convs with 64 / 128 channels (stages 1-2) run the halo kernel on pre-activated, zero-padded tensors
+  // (TN_RESNET_NO_HALO=1: everything through the gather GEMM)
+  const bool halo_on = !getenv("TN_RESNET_NO_HALO");
+  const size_t padded = static_cast<size_t>(n) * (d.Hp + 2) * (d.Wp + 2) * 64;  // stage 1 is the largest padded activation
+  __nv_bfloat16* apad = halo_on ? ws.get<__nv_bfloat16>(padded) : nullptr;
+  __nv_bfloat16* tpad = halo_on ? ws.get<__nv_bfloat16>(padded) : nullptr;
   if (dry) return TN_OK;
   {
     // 7x7/2 stem == 4x4/1 conv on the zero-padded space-to-depth image (tn_stem.cu), BN folded, ReLU
@@ -567,20 +568,40 @@ int resnet_forward(tn_backbone* bb, const __nv_bfloat16* in4, int n, int h, int 
   for (size_t bi = 0; bi < bb->rblocks.size(); ++bi) {
     const ResBlock& B = bb->rblocks[bi];
     const int Ho = (H + 2 - 3) / B.stride + 1, Wo = (W + 2 - 3) / B.stride + 1;
-    if (B.halo && halo_ok) {
-      if (!apad_ready) TN_CUDA(launch_bn_relu_pad(x, 64, n, H, W, 64, B.bn1.scale, B.bn1.shift, apad, st));
-      // conv1: relu(bn2(conv(a))) -> padded, activated; conv2: + x -> raw block output (+ the next block's activated input)
-      TN_CUDA(launch_conv3x3_c64(B.c1h, apad, n, H, W, B.bn2.shift, 1, nullptr, 0, nullptr, 0, tpad, nullptr, nullptr, bb->num_sms, st));
-      const bool next_halo = bi + 1 < bb->rblocks.size() && bb->rblocks[bi + 1].halo;
-      const ResBlock* nx = next_halo ? &bb->rblocks[bi + 1] : nullptr;
-      TN_CUDA(launch_conv3x3_c64(B.c2h, tpad, n, H, W, nullptr, 0, x, 64, y, 64, next_halo ? apad : nullptr,
-                                 nx ? nx->bn1.scale : nullptr, nx ? nx->bn1.shift : nullptr, bb->num_sms, st));
-      apad_ready = next_halo;
+    const bool use_h2 = halo_on && B.h2 && conv3x3_c64_supported(Ho, Wo, B.c);
+    const bool use_h1 = use_h2 && B.h1 && conv3x3_c64_supported(H, W, B.c);
+    if (use_h2) {
+      const __nv_bfloat16* res = x;
+      int res_cs = B.cin;
+      if (B.has_ds) {  // downsample acts on relu(bn1(x)) (BasicBlockV2)
+        ConvGemmParams pd = conv_params(B.ds, x, B.cin, n, H, W, Ho, Wo, B.stride, 0, &B.bn1, rb, B.c, 0, nullptr, false);
+        TN_CUDA(launch_conv_gemm(pd, st));
+        res = rb;
+        res_cs = B.c;
+      }
+      if (use_h1) {  // conv1: relu(bn2(conv(a))) -> padded, activated
+        if (!apad_ready) TN_CUDA(launch_bn_relu_pad(x, B.cin, n, H, W, B.cin, B.bn1.scale, B.bn1.shift, apad, st));
+        TN_CUDA(launch_conv3x3_c64(B.c1h, apad, n, H, W, B.bn2.shift, 1, nullptr, 0, nullptr, 0, tpad, nullptr, nullptr, bb->num_sms, st));
+      } else {       // strided conv1 through the gather GEMM, written into the padded layout (borders zeroed first)
+        TN_CUDA(launch_zero_border(tpad, n, Ho + 2, Wo + 2, B.c, st));
+        ConvGemmParams p1 = conv_params(B.conv1, x, B.cin, n, H, W, Ho, Wo, B.stride, 1, &B.bn1, tpad, B.c, 0, &B.bn2, true);
+        p1.out_pad = 1;
+        TN_CUDA(launch_conv_gemm(p1, st));
+      }
+      // conv2: + residual -> raw block output (+ the next block's activated, padded input when that block starts with a halo conv)
+      const ResBlock* nx = bi + 1 < bb->rblocks.size() ? &bb->rblocks[bi + 1] : nullptr;
+      const bool next_h1 = nx && nx->h1 && nx->cin == B.c && conv3x3_c64_supported(Ho, Wo, nx->c);
+      TN_CUDA(launch_conv3x3_c64(B.c2h, tpad, n, Ho, Wo, nullptr, 0, res, res_cs, y, B.c, next_h1 ? apad : nullptr,
+                                 next_h1 ? nx->bn1.scale : nullptr, next_h1 ? nx->bn1.shift : nullptr, bb->num_sms, st));
+      apad_ready = next_h1;
       __nv_bfloat16* t = x;
       x = y;
       y = t;
+      H = Ho;
+      W = Wo;
       continue;
     }
+    apad_ready = false;
     const __nv_bfloat16* res = x;
     int res_cs = B.cin;
     if (B.has_ds) {  // downsample acts on relu(bn1(x)) (BasicBlockV2)
@@ -748,11 +769,10 @@ int tn_backbone_create(tn_backbone_t** out, int arch, int device, const float* p
         ok = ok && take_conv_bn(cur, bb->arena, B.c, cin, 3, 3, tn::kModeConv, &B.conv1, &B.bn2, &hs2);
         const float* w2 = cur.p;
         ok = ok && take_conv(cur, bb->arena, B.c, B.c, 3, 3, tn::kModeConv, &B.conv2);
-        B.halo = ok && cin == 64 && B.c == 64 && B.stride == 1;
-        if (B.halo) {
-          ok = ok && tn::make_conv3x3_c64(bb->arena, w1, hs2.data(), &B.c1h);
-          ok = ok && tn::make_conv3x3_c64(bb->arena, w2, nullptr, &B.c2h);
-        }
+        B.h2 = ok && (B.c == 64 || B.c == 128);
+        B.h1 = B.h2 && cin == B.c && B.stride == 1;
+        if (B.h1) ok = ok && tn::make_conv3x3_c64(bb->arena, w1, B.c, hs2.data(), &B.c1h);
+        if (B.h2) ok = ok && tn::make_conv3x3_c64(bb->arena, w2, B.c, nullptr, &B.c2h);
         if (B.has_ds) ok = ok && take_conv(cur, bb->arena, B.c, cin, 1, 1, tn::kModeConv, &B.ds);
         bb->rblocks.push_back(B);
         cin = B.c;

@@ -40,7 +40,8 @@ constexpr int kMaxSmem = 227 * 1024;
 
 struct C64Params {
   int Wp, HpWp, H, W, NR;
-  int RH, a_bytes, nbuf, num_tiles;
+  int RH, a_half_bytes, a_bytes, nbuf, num_tiles;
+  int cout;                       // 64, or 128: two N halves of 64 handled by the even / odd CTAs
   const uint8_t* wpack;
   const float* shift;             // per output channel, added before relu / residual (nullable)
   int relu;
@@ -48,7 +49,7 @@ struct C64Params {
   int res_cs;
   __nv_bfloat16* out;             // unpadded output (F, H, W, out_cs) or null
   int out_cs;
-  __nv_bfloat16* out_pad;         // padded output (F, H+2, W+2, 64) or null
+  __nv_bfloat16* out_pad;         // padded output (F, H+2, W+2, cout) or null
   const float* act_scale;         // when both outputs are written: out_pad = relu(act_scale * bf16(value) + act_shift)
   const float* act_shift;
 };
@@ -60,11 +61,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
       : "memory");
 }
 
+// NH = 64-channel halves of C_in (1: 64 -> 64, 2: 128 -> 128 with the output channels split over CTA parity)
+template <int NH>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap, const C64Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem;                          // 72 KB
-  uint8_t* sA = smem + kWBytes;                // nbuf x a_bytes
+  uint8_t* sW = smem;                          // NH x 72 KB
+  uint8_t* sA = smem + NH * kWBytes;           // nbuf x a_bytes
+  const int nsplit = p.cout / kC;              // CTAs per tile (one per 64 output channels)
+  const int n_half = nsplit == 2 ? (blockIdx.x & 1) : 0;
+  const int tile0 = nsplit == 2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tstep = nsplit == 2 ? (gridDim.x >> 1) : gridDim.x;
   uint8_t* tail = sA + p.nbuf * p.a_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);  // [kMaxBuf]
   uint64_t* a_empty = a_full + kMaxBuf;                  // [kMaxBuf]
@@ -97,21 +104,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
-    mbar_arrive_expect_tx(w_full, kWBytes);
-    for (int b = 0; b < 3; ++b) bulk_g2s(sW + b * kWBlob, p.wpack + b * kWBlob, kWBlob, w_full);
+    mbar_arrive_expect_tx(w_full, NH * kWBytes);
+    const uint8_t* wsrc = p.wpack + static_cast<size_t>(n_half) * NH * kWBytes;  // [n half][dy][c_in half]
+    for (int b = 0; b < 3 * NH; ++b) bulk_g2s(sW + b * kWBlob, wsrc + b * kWBlob, kWBlob, w_full);
   }
   griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      for (int t = tile0; t < p.num_tiles; t += tstep, ++it) {
         const int buf = it % p.nbuf;
         const int use = it / p.nbuf;
         mbar_wait(&a_empty[buf], (use & 1) ^ 1);
-        mbar_arrive_expect_tx(&a_full[buf], static_cast<uint32_t>(p.RH * 128));
-        // one box of RH rows x 64 channels; rows outside the tensor are zero-filled by the TMA engine
-        tma_load_2d(smem_u32(sA + buf * p.a_bytes), &tmap, 0, t * kTileRows - 1 - p.Wp, &a_full[buf]);
+        mbar_arrive_expect_tx(&a_full[buf], static_cast<uint32_t>(NH * p.RH * 128));
+        // one box of RH rows x 64 channels per half; rows outside the tensor are zero-filled by the TMA engine
+        for (int half = 0; half < NH; ++half)
+          tma_load_2d(smem_u32(sA + buf * p.a_bytes + half * p.a_half_bytes), &tmap, half * 64, t * kTileRows - 1 - p.Wp, &a_full[buf]);
       }
     }
   } else if (warp == 1) {
@@ -119,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
       const uint32_t idesc = umma_idesc_bf16_m128(kN);
       mbar_wait(w_full, 0);
       int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      for (int t = tile0; t < p.num_tiles; t += tstep, ++it) {
         const int buf = it % p.nbuf;
         const int ab = it & 1;
         mbar_wait(&a_full[buf], (it / p.nbuf) & 1);
@@ -131,12 +140,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
         uint32_t acc = 0;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-          const uint64_t da = umma_desc_sw128(a_base + dy * p.Wp * 128);
-          const uint64_t db = umma_desc_sw128(w_base + dy * kWBlob);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
-            acc = 1;
+          for (int half = 0; half < NH; ++half) {
+            const uint64_t da = umma_desc_sw128(a_base + half * p.a_half_bytes + dy * p.Wp * 128);
+            const uint64_t db = umma_desc_sw128(w_base + (dy * NH + half) * kWBlob);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+              acc = 1;
+            }
           }
         }
         umma_commit(&a_empty[buf]);
@@ -149,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
     const int hf = (warp - 2) >> 2;
     const int r = qw * 32 + lane;
     int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < p.num_tiles; t += tstep, ++it) {
       const int ab = it & 1;
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
         const int yp = rem / p.Wp;
         const int xp = rem - yp * p.Wp;
         const bool interior = yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
-        const int cbase = hf * 32;
+        const int cbase = n_half * kC + hf * 32;
         uint32_t packed[16];
         if (interior) {
           if (p.shift) {
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
           for (int j = 0; j < 16; ++j) packed[j] = 0u;  // border rows of the padded output stay zero
         }
         if (p.out_pad) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out_pad + static_cast<size_t>(q) * kC + cbase);
+          uint4* dst = reinterpret_cast<uint4*>(p.out_pad + static_cast<size_t>(q) * p.cout + cbase);
 #pragma unroll
           for (int c = 0; c < 4; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
         }
@@ -307,25 +319,39 @@ EncodeTiledFn get_encode() {
 
 }  // namespace
 
-bool conv3x3_c64_supported(int H, int W) {
+namespace {
+constexpr int kFixedSmem = 256 + 2 * 2 * 4 * 2 * 32 * 4 + 1024;  // barriers, exchange, alignment slack
+}
+bool conv3x3_c64_supported(int H, int W, int C) {
+  if (C != 64 && C != 128) return false;
   const int RH = 128 + 2 * (W + 2);
-  return H >= 1 && W >= 1 && RH <= 256;  // one TMA box (<= 256 rows) per halo tile
+  const int NH = C / 64;
+  const size_t a_bytes = NH * align_up(static_cast<size_t>(RH) * 128, 1024);
+  // one TMA box (<= 256 rows) per halo half; resident weights + at least one halo buffer must fit
+  return H >= 1 && W >= 1 && RH <= 256 && NH * kWBytes + kFixedSmem + a_bytes <= static_cast<size_t>(kMaxSmem);
 }
 
-bool make_conv3x3_c64(DeviceArena& arena, const float* w /* (64,64,3,3) OIHW */, const float* fold_scale, Conv3x3C64Dev* out) {
-  std::vector<uint8_t> blob(kWBytes, 0);
-  for (int dy = 0; dy < 3; ++dy)
-    for (int n = 0; n < kN; ++n) {
-      const int dx = n / kC, c = n % kC;
-      for (int kk = 0; kk < 64; ++kk) {
-        float v = w[((static_cast<size_t>(c) * 64 + kk) * 3 + dy) * 3 + dx];
-        if (fold_scale) v *= fold_scale[c];
-        __nv_bfloat16 b = __float2bfloat16(v);
-        const size_t off = static_cast<size_t>(dy) * kWBlob + n * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
-        memcpy(&blob[off], &b, 2);
-      }
-    }
+bool make_conv3x3_c64(DeviceArena& arena, const float* w /* (C,C,3,3) OIHW */, int C, const float* fold_scale, Conv3x3C64Dev* out) {
+  if (C != 64 && C != 128) return false;
+  const int NH = C / 64, NS = C / 64;  // input halves, output halves
+  std::vector<uint8_t> blob(static_cast<size_t>(NS) * NH * kWBytes, 0);
+  for (int ns = 0; ns < NS; ++ns)
+    for (int dy = 0; dy < 3; ++dy)
+      for (int half = 0; half < NH; ++half)
+        for (int n = 0; n < kN; ++n) {
+          const int dx = n / kC, c = ns * kC + n % kC;
+          for (int kk = 0; kk < 64; ++kk) {
+            const int ci = half * 64 + kk;
+            float v = w[((static_cast<size_t>(c) * C + ci) * 3 + dy) * 3 + dx];
+            if (fold_scale) v *= fold_scale[c];
+            __nv_bfloat16 b = __float2bfloat16(v);
+            const size_t off = (static_cast<size_t>(ns) * 3 * NH + dy * NH + half) * kWBlob + n * 128 + (((kk >> 3) ^ (n & 7)) << 4) +
+                               (kk & 7) * 2;
+            memcpy(&blob[off], &b, 2);
+          }
+        }
   out->wpack = static_cast<const uint8_t*>(arena.upload(blob.data(), blob.size()));
+  out->C = C;
   return out->wpack != nullptr;
 }
 
@@ -347,9 +373,11 @@ cudaError_t launch_conv3x3_c64(const Conv3x3C64Dev& cv, const __nv_bfloat16* in_
                                cudaStream_t st) {
   EncodeTiledFn encode = get_encode();
   if (!encode) return cudaErrorNotSupported;
-  if (!conv3x3_c64_supported(H, W) || (!out && !out_pad)) return cudaErrorInvalidValue;
+  const int C = cv.C, NH = C / 64;
+  if (!conv3x3_c64_supported(H, W, C) || (!out && !out_pad)) return cudaErrorInvalidValue;
   C64Params p;
   memset(&p, 0, sizeof(p));
+  p.cout = C;
   p.Wp = W + 2;
   p.HpWp = (H + 2) * (W + 2);
   p.H = H;
@@ -358,9 +386,10 @@ cudaError_t launch_conv3x3_c64(const Conv3x3C64Dev& cv, const __nv_bfloat16* in_
   if (NR >= (1LL << 31) - 256) return cudaErrorInvalidValue;
   p.NR = static_cast<int>(NR);
   p.RH = 128 + 2 * p.Wp;
-  p.a_bytes = static_cast<int>(align_up(static_cast<size_t>(p.RH) * 128, 1024));
+  p.a_half_bytes = static_cast<int>(align_up(static_cast<size_t>(p.RH) * 128, 1024));
+  p.a_bytes = NH * p.a_half_bytes;
   p.num_tiles = static_cast<int>((NR + kTileRows - 1) / kTileRows);
-  const int fixed = kWBytes + 256 + 2 * 2 * 4 * 2 * 32 * 4 + 1024;  // weights, barriers, exchange, alignment slack
+  const int fixed = NH * kWBytes + kFixedSmem;
   int nbuf = (kMaxSmem - fixed) / p.a_bytes;
   if (nbuf > kMaxBuf) nbuf = kMaxBuf;
   if (nbuf < 1) return cudaErrorInvalidValue;
@@ -379,23 +408,29 @@ cudaError_t launch_conv3x3_c64(const Conv3x3C64Dev& cv, const __nv_bfloat16* in_
   const int smem = fixed + p.nbuf * p.a_bytes;
 
   CUtensorMap tmap;
-  cuuint64_t gdim[2] = {64, static_cast<cuuint64_t>(p.NR)};
-  cuuint64_t gstride[1] = {64 * sizeof(__nv_bfloat16)};
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(p.NR)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(C) * sizeof(__nv_bfloat16)};
   cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.RH)};
   cuuint32_t estr[2] = {1, 1};
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(in_padded), gdim, gstride, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
-  static int configured_smem = 0;
-  if (smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int configured_smem[2] = {0, 0};
+  if (smem > configured_smem[NH - 1]) {
+    cudaError_t e = NH == 1 ? cudaFuncSetAttribute(conv3x3_c64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                            : cudaFuncSetAttribute(conv3x3_c64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured_smem = smem;
+    configured_smem[NH - 1] = smem;
   }
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ProfScope prof_scope(kProfConvGemm, st);
-  return launch_pdl(conv3x3_c64_kernel, dim3(grid), dim3(kThreads), smem, st, tmap, p);
+  if (NH == 1) {
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    return launch_pdl(conv3x3_c64_kernel<1>, dim3(grid), dim3(kThreads), smem, st, tmap, p);
+  }
+  int pairs = num_sms / 2;  // even CTAs: output channels [0, 64), odd CTAs: [64, 128)
+  if (pairs > p.num_tiles) pairs = p.num_tiles;
+  return launch_pdl(conv3x3_c64_kernel<2>, dim3(2 * pairs), dim3(kThreads), smem, st, tmap, p);
 }
 
 }  // namespace tn

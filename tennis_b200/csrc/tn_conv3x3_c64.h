@@ -1,4 +1,4 @@
-// Halo-tile TMA + tcgen05 kernel for the 3x3 / stride 1 convolutions with 64 input and 64 output channels (ResNet-18 v2 stage 1)
+// Halo-tile TMA + tcgen05 kernel for the 3x3 / stride 1 convolutions with 64 -> 64 and 128 -> 128 channels (ResNet-18 v2 stages 1-2)
 // on a pre-activated, zero-padded input layout (see tn_conv3x3_c64.cu).
 #pragma once
 #include <cuda_bf16.h>
@@ -10,12 +10,13 @@
 namespace tn {
 
 struct Conv3x3C64Dev {
-  const uint8_t* wpack = nullptr;  // 3 blobs [dy], each 192 rows (dx*64 + c_out) x 64 bf16, 128B-swizzled
+  const uint8_t* wpack = nullptr;  // blobs [c_out half][dy][c_in half], each 192 rows (dx*64 + c_out) x 64 bf16, 128B-swizzled
+  int C = 0;                       // channels in = out: 64 or 128
 };
 
-bool conv3x3_c64_supported(int H, int W);
-// fold_scale (host, 64 floats or null): per-output-channel scale folded into the weights (the following BatchNorm)
-bool make_conv3x3_c64(DeviceArena& arena, const float* w_oihw_64x64x3x3, const float* fold_scale, Conv3x3C64Dev* out);
+bool conv3x3_c64_supported(int H, int W, int C);
+// w (C, C, 3, 3) OIHW, C = 64 or 128; fold_scale (host, C floats or null): per-output-channel scale folded into the weights
+bool make_conv3x3_c64(DeviceArena& arena, const float* w_oihw, int C, const float* fold_scale, Conv3x3C64Dev* out);
 // out_pad (F, H+2, W+2, C) = relu(scale * x + shift) on the interior, zeros on the border
 cudaError_t launch_bn_relu_pad(const __nv_bfloat16* x, int x_cs, int F, int H, int W, int C, const float* scale, const float* shift,
                                __nv_bfloat16* out_pad, cudaStream_t st);

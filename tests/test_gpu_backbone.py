@@ -14,7 +14,7 @@ FEAT_TOL = {"densenet121": 1e-2, "resnet18_v2": 1e-2}
 # (29x29 in block 2: floor-mode pooling, the in-GEMM transition gather and the non-halo 3x3 path).
 @pytest.mark.parametrize("arch,size,n", [("densenet121", 224, 3), ("resnet18_v2", 224, 3), ("densenet121", 256, 1),
                                          ("densenet121", 512, 1), ("resnet18_v2", 512, 1), ("densenet121", 231, 2),
-                                         ("resnet18_v2", 231, 2)])
+                                         ("resnet18_v2", 231, 2), ("resnet18_v2", 256, 1)])
 def test_backbone_features_match_oracle(arch, size, n):
     from oracle import vision as O
     from tennis_b200 import ops
