@@ -28,7 +28,7 @@ namespace tn {
 
 namespace {
 
-constexpr int kThreads = 320;          // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kThreads = 576;          // TMA warp, MMA warp, 2 groups of 8 epilogue warps (one group per accumulator buffer)
 constexpr int kTileRows = 126;         // valid outputs per tile
 constexpr int kC = 64;
 constexpr int kN = 3 * kC;             // 192: three dx taps stacked along N
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
   uint64_t* acc_empty = acc_full + 2;                    // [2]
   uint64_t* w_full = acc_empty + 2;                      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* xch = reinterpret_cast<float*>(tail + 256);     // [2 parity][2 channel halves][4 quarters][2][32]
+  float* xch = reinterpret_cast<float*>(tail + 256);     // [2 groups][4 channel groups][4 quarters][2][16]
 
   const int tid = threadIdx.x;
   griddep_launch_dependents();
@@ -156,75 +156,94 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
       }
     }
   } else {
-    // epilogue: warps 2..9, lane quarter warp & 3, output channels [32 hf, 32 hf + 32)
+    // epilogue: warps 2..17 = two groups of eight; group g drains accumulator buffer g (tiles it = g, g+2, ...), so the dependent
+    // chain of one tile's epilogue (TMEM load -> exchange -> residual load -> stores, ~2 us of latency) spans two tile periods.
+    // Within a group: lane quarter warp & 3, output channels [32 hf, 32 hf + 32) in two passes of 16 (register budget at 576 threads).
+    const int grp = (warp - 2) >> 3;
     const int qw = warp & 3;
-    const int hf = (warp - 2) >> 2;
+    const int hf = ((warp - 2) >> 2) & 1;
     const int r = qw * 32 + lane;
     int it = 0;
     for (int t = tile0; t < p.num_tiles; t += tstep, ++it) {
       const int ab = it & 1;
+      if (ab != grp) continue;
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t v0[32], v1[32], v2[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * kN + hf * 32;
-      tmem_ld32(taddr, v0);            // dx = -1 block
-      tmem_ld32(taddr + kC, v1);       // dx =  0
-      tmem_ld32(taddr + 2 * kC, v2);   // dx = +1
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
-
-      // dx-tap exchange across the lane quarters: lane 31 publishes its dx=-1 block (needed by the first row of the next quarter),
-      // lane 0 its dx=+1 block (needed by the last row of the previous quarter)
-      float* x = xch + (it & 1) * 512 + hf * 256;
-      if (lane == 0 || lane == 31) {
-        uint4* dst = reinterpret_cast<uint4*>(x + (qw * 2 + (lane == 0 ? 1 : 0)) * 32);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          uint4 w;
-          w.x = (lane == 0) ? v2[4 * j4 + 0] : v0[4 * j4 + 0];
-          w.y = (lane == 0) ? v2[4 * j4 + 1] : v0[4 * j4 + 1];
-          w.z = (lane == 0) ? v2[4 * j4 + 2] : v0[4 * j4 + 2];
-          w.w = (lane == 0) ? v2[4 * j4 + 3] : v0[4 * j4 + 3];
-          dst[j4] = w;
-        }
-      }
-      if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
-      const bool need_up = lane == 0 && qw > 0, need_dn = lane == 31 && qw < 3;
-      float o[32];
-      {
-        const int slot = need_up ? (qw - 1) * 2 : (need_dn ? (qw + 1) * 2 + 1 : 0);
-        const float* src = x + slot * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);      // D[r-1][j]
-          float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);    // D[r+1][128+j]
-          if (need_up) up = src[j];
-          if (need_dn) dn = src[j];
-          o[j] = up + __uint_as_float(v1[j]) + dn;
-        }
-      }
       const int q = t * kTileRows - 1 + r;
-      if (r >= 1 && r <= kTileRows && q < p.NR) {
+      const bool row_ok = r >= 1 && r <= kTileRows && q < p.NR;
+      bool interior = false;
+      size_t urow = 0;
+      if (row_ok) {
         const int f = q / p.HpWp;
         const int rem = q - f * p.HpWp;
         const int yp = rem / p.Wp;
         const int xp = rem - yp * p.Wp;
-        const bool interior = yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
-        const int cbase = n_half * kC + hf * 32;
-        uint32_t packed[16];
+        interior = yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
+        urow = static_cast<size_t>(f * p.H + yp - 1) * p.W + (xp - 1);
+      }
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const int cgi = hf * 2 + sub;                 // 16-channel group within this CTA's 64
+        const int cbase = n_half * kC + cgi * 16;     // channel of the output tensor
+        uint32_t v0[16], v1[16], v2[16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * kN + cgi * 16;
+        __syncwarp();                    // the store branch of the previous pass diverges; tcgen05.ld is warp-collective
+        tmem_ld16(taddr, v0);            // dx = -1 block
+        tmem_ld16(taddr + kC, v1);       // dx =  0
+        tmem_ld16(taddr + 2 * kC, v2);   // dx = +1
+        tmem_ld_wait();
+        if (sub == 1) {                  // accumulator drained by this warp: the MMA warp may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+        }
+        // dx-tap exchange across the lane quarters: lane 31 publishes its dx=-1 block (needed by the first row of the next
+        // quarter), lane 0 its dx=+1 block (needed by the last row of the previous quarter)
+        float* x = xch + grp * 512 + cgi * 128;
+        if (lane == 0 || lane == 31) {
+          uint4* dst = reinterpret_cast<uint4*>(x + (qw * 2 + (lane == 0 ? 1 : 0)) * 16);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 w;
+            w.x = (lane == 0) ? v2[4 * j4 + 0] : v0[4 * j4 + 0];
+            w.y = (lane == 0) ? v2[4 * j4 + 1] : v0[4 * j4 + 1];
+            w.z = (lane == 0) ? v2[4 * j4 + 2] : v0[4 * j4 + 2];
+            w.w = (lane == 0) ? v2[4 * j4 + 3] : v0[4 * j4 + 3];
+            dst[j4] = w;
+          }
+        }
+        if (grp == 0) {
+          if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+        } else {
+          if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 4, 128;" ::: "memory");
+        }
+        const bool need_up = lane == 0 && qw > 0, need_dn = lane == 31 && qw < 3;
+        float o[16];
+        {
+          const int slot = need_up ? (qw - 1) * 2 : (need_dn ? (qw + 1) * 2 + 1 : 0);
+          const float* src = x + slot * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);      // D[r-1][j]
+            float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);    // D[r+1][128+j]
+            if (need_up) up = src[j];
+            if (need_dn) dn = src[j];
+            o[j] = up + __uint_as_float(v1[j]) + dn;
+          }
+        }
+        if (!row_ok) continue;
+        uint32_t packed[8];
         if (interior) {
           if (p.shift) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] += __ldg(p.shift + cbase + j);
+            for (int j = 0; j < 16; ++j) o[j] += __ldg(p.shift + cbase + j);
           }
-          const size_t urow = static_cast<size_t>(f * p.H + yp - 1) * p.W + (xp - 1);
           if (p.res) {
             const uint4* r4 = reinterpret_cast<const uint4*>(p.res + urow * p.res_cs + cbase);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
               const uint4 rv = __ldg(r4 + c);
               const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
@@ -237,18 +256,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+            for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
+          for (int j = 0; j < 8; ++j) packed[j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
           if (p.out) {
             uint4* dst = reinterpret_cast<uint4*>(p.out + urow * p.out_cs + cbase);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+            for (int c = 0; c < 2; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
           }
           if (p.out_pad && p.act_scale) {  // activated copy for the next convolution, from the ROUNDED block output
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const float2 f2 = unpack_bf16x2(packed[j]);
               const float a = fmaxf(fmaf(f2.x, __ldg(p.act_scale + cbase + 2 * j), __ldg(p.act_shift + cbase + 2 * j)), 0.f);
               const float b = fmaxf(fmaf(f2.y, __ldg(p.act_scale + cbase + 2 * j + 1), __ldg(p.act_shift + cbase + 2 * j + 1)), 0.f);
@@ -257,12 +276,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) packed[j] = 0u;  // border rows of the padded output stay zero
+          for (int j = 0; j < 8; ++j) packed[j] = 0u;  // border rows of the padded output stay zero
         }
         if (p.out_pad) {
           uint4* dst = reinterpret_cast<uint4*>(p.out_pad + static_cast<size_t>(q) * p.cout + cbase);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+          for (int c = 0; c < 2; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
         }
       }
     }
