@@ -1,13 +1,19 @@
-// 3x3 / stride 1 / pad 1 convolution with C_in = C_out = 64: the four convolutions of ResNet-18 v2's first stage
-// (gluoncv BasicBlockV2 at 56 x 56, reference train.py:32 `--backbone resnet18_v2`, the scripts' default backbone), 49 % of that
-// network's forward time while they ran through the generic gather-mode GEMM (profiles/r2_summary.md section 8).
+// 3x3 / stride 1 / pad 1 convolution with C_in = C_out = 64 or 128: the stride-1 convolutions of ResNet-18 v2's first two stages
+// (gluoncv BasicBlockV2 at 56 x 56 / 28 x 28, reference train.py:32 `--backbone resnet18_v2`, the scripts' default backbone): 49 %
+// of that network's forward time while they ran through the generic gather-mode GEMM (profiles/r2_summary.md section 8).
 //
-// Same construction as the DenseNet growth conv (tn_conv3x3.cu): the input is a PRE-ACTIVATED, ZERO-PADDED bf16 tensor
-// (F, H+2, W+2, 64) = a 2-D matrix of 128-byte rows, so a filter tap is a row shift; one CTA TMA-loads one halo tile
-// (128 + 2(W+2) rows) per 126 outputs, issues 3 (dy) x 4 (K = 16) UMMAs of M128 x N192 (the three dx taps stacked along N, the A
-// operand of tap-row dy is the same shared-memory tile through a descriptor advanced by dy*(W+2) rows), and applies the dx shift
-// on accumulator rows in the epilogue.  Weights (3 x 192 x 64 bf16 = 72 KB, BatchNorm scale of the FOLLOWING BatchNorm folded in
-// for conv1) stay resident; up to four halo buffers; accumulators double-buffered in TMEM (2 x 192 columns).
+// The input is a PRE-ACTIVATED, ZERO-PADDED bf16 tensor (F, H+2, W+2, C) = a 2-D matrix of rows, so a filter tap (dy, dx) is a
+// row shift by dy*(W+2) + dx.  One CTA TMA-loads one halo tile (128 + 2(W+2) + 2 rows, one box per 64-channel half) per 128
+// outputs and issues 9 taps x NH halves x 4 (K = 16) UMMAs of M128 x N64 into ONE accumulator: the A operand of every tap is the
+// same shared-memory tile through a descriptor advanced by dy*(W+2) + dx rows (SWIZZLE_128B is a function of the absolute
+// shared-memory address, tools/umma_shift_probe.cu, so any row shift is legal).  The first build stacked the three dx taps along N
+// (M128 x N192, a third of the MMAs) and applied the dx shift to accumulator rows in the epilogue like the DenseNet growth conv; with
+// 64 output channels that epilogue (64 shuffles + selects per thread and tile) was instruction-issue bound at 2.3 us per tile, three
+// different warp organisations of it ran at the same speed (profiles/r2_summary.md section 8).  N = 64 taps cost 50 % more tensor
+// time and leave an epilogue of one TMEM load, the per-channel math and the stores.
+// Weights (9 taps x NH x 64 x 64 bf16 = 72 KB per 64 input channels, the FOLLOWING BatchNorm's scale folded in for conv1) stay
+// resident; for C = 128 the output channels are split over CTA parity.  Up to four halo buffers, accumulators double-buffered in
+// TMEM, two epilogue warp groups (one per accumulator buffer).
 //
 // Epilogue variants (pre-activation ResNet: bn1 -> relu -> conv1 -> bn2 -> relu -> conv2 -> + x):
 //   conv1:  t = relu(acc + shift2)                      -> padded, activated input of conv2 (border rows written as zeros)
@@ -29,12 +35,12 @@ namespace tn {
 namespace {
 
 constexpr int kThreads = 576;          // TMA warp, MMA warp, 2 groups of 8 epilogue warps (one group per accumulator buffer)
-constexpr int kTileRows = 126;         // valid outputs per tile
+constexpr int kTileRows = 128;         // outputs per tile (every accumulator row is an output)
 constexpr int kC = 64;
-constexpr int kN = 3 * kC;             // 192: three dx taps stacked along N
-constexpr int kWBlob = kN * 128;       // one dy blob: 192 rows x 64 bf16, swizzled
-constexpr int kWBytes = 3 * kWBlob;    // 72 KB
-constexpr int kTmemCols = 512;         // 2 x 192 used
+constexpr int kN = kC;                 // UMMA N: the 64 output channels of this CTA
+constexpr int kWBlob = kN * 128;       // one (tap, c_in half) blob: 64 rows x 64 bf16, swizzled (8 KB)
+constexpr int kWBytes = 9 * kWBlob;    // 72 KB per 64 input channels
+constexpr int kTmemCols = 128;         // 2 x 64
 constexpr int kMaxBuf = 4;
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -79,7 +85,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
   uint64_t* acc_empty = acc_full + 2;                    // [2]
   uint64_t* w_full = acc_empty + 2;                      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
-  float* xch = reinterpret_cast<float*>(tail + 256);     // [2 groups][4 channel groups][4 quarters][2][16]
 
   const int tid = threadIdx.x;
   griddep_launch_dependents();
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
   if (tid == 0) {  // weights are constants: fetch them before waiting on the producer grid
     mbar_arrive_expect_tx(w_full, NH * kWBytes);
     const uint8_t* wsrc = p.wpack + static_cast<size_t>(n_half) * NH * kWBytes;  // [n half][dy][c_in half]
-    for (int b = 0; b < 3 * NH; ++b) bulk_g2s(sW + b * kWBlob, wsrc + b * kWBlob, kWBlob, w_full);
+    for (int b = 0; b < 9 * NH; ++b) bulk_g2s(sW + b * kWBlob, wsrc + b * kWBlob, kWBlob, w_full);
   }
   griddep_wait();
 
@@ -118,9 +123,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
         const int use = it / p.nbuf;
         mbar_wait(&a_empty[buf], (use & 1) ^ 1);
         mbar_arrive_expect_tx(&a_full[buf], static_cast<uint32_t>(NH * p.RH * 128));
-        // one box of RH rows x 64 channels per half; rows outside the tensor are zero-filled by the TMA engine
+        // one box of RH rows x 64 channels per half (tile row 0 = padded row q0 - (W+2) - 1); rows outside the tensor are
+        // zero-filled by the TMA engine.  Splitting the box or using fewer buffers changes nothing (measured).
         for (int half = 0; half < NH; ++half)
-          tma_load_2d(smem_u32(sA + buf * p.a_bytes + half * p.a_half_bytes), &tmap, half * 64, t * kTileRows - 1 - p.Wp, &a_full[buf]);
+          tma_load_2d(smem_u32(sA + buf * p.a_bytes + half * p.a_half_bytes), &tmap, half * 64, t * kTileRows - 1 - p.Wp,
+                      &a_full[buf]);
       }
     }
   } else if (warp == 1) {
@@ -141,13 +148,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-          for (int half = 0; half < NH; ++half) {
-            const uint64_t da = umma_desc_sw128(a_base + half * p.a_half_bytes + dy * p.Wp * 128);
-            const uint64_t db = umma_desc_sw128(w_base + (dy * NH + half) * kWBlob);
+          for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
-              acc = 1;
+            for (int half = 0; half < NH; ++half) {
+              // tap (dy, dx) of output row m reads tile row m + dy*(W+2) + dx
+              const uint64_t da = umma_desc_sw128(a_base + half * p.a_half_bytes + (dy * p.Wp + dx) * 128);
+              const uint64_t db = umma_desc_sw128(w_base + ((dy * 3 + dx) * NH + half) * kWBlob);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+                acc = 1;
+              }
             }
           }
         }
@@ -156,133 +167,84 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_c64_kernel(const __grid_c
       }
     }
   } else {
-    // epilogue: warps 2..17 = two groups of eight; group g drains accumulator buffer g (tiles it = g, g+2, ...), so the dependent
-    // chain of one tile's epilogue (TMEM load -> exchange -> residual load -> stores, ~2 us of latency) spans two tile periods.
-    // Within a group: lane quarter warp & 3, output channels [32 hf, 32 hf + 32) in two passes of 16 (register budget at 576 threads).
+    // epilogue: warps 2..17 = two groups of eight; group g drains accumulator buffer g (tiles it = g, g+2, ...).  Within a group:
+    // lane quarter qw = warp & 3, output channels [32 hf, 32 hf + 32) of this CTA's 64.  One TMEM load, the per-channel math and
+    // lane-per-row 16-byte global accesses.  (A shared-memory transposed variant with four lanes per row segment, and three warp
+    // organisations of the earlier dx-stacked epilogue, all ran at the same speed: the tile period is set by the shared-memory
+    // data pipe that the tensor core's operand reads, the TMA writes and the LSU share -- profiles/r2_summary.md section 8.)
     const int grp = (warp - 2) >> 3;
     const int qw = warp & 3;
     const int hf = ((warp - 2) >> 2) & 1;
     const int r = qw * 32 + lane;
+    const int cb32 = n_half * kC + hf * 32;
     int it = 0;
     for (int t = tile0; t < p.num_tiles; t += tstep, ++it) {
       const int ab = it & 1;
       if (ab != grp) continue;
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
-      const int q = t * kTileRows - 1 + r;
-      const bool row_ok = r >= 1 && r <= kTileRows && q < p.NR;
-      bool interior = false;
-      size_t urow = 0;
-      if (row_ok) {
-        const int f = q / p.HpWp;
-        const int rem = q - f * p.HpWp;
-        const int yp = rem / p.Wp;
-        const int xp = rem - yp * p.Wp;
-        interior = yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
-        urow = static_cast<size_t>(f * p.H + yp - 1) * p.W + (xp - 1);
-      }
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const int cgi = hf * 2 + sub;                 // 16-channel group within this CTA's 64
-        const int cbase = n_half * kC + cgi * 16;     // channel of the output tensor
-        uint32_t v0[16], v1[16], v2[16];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * kN + cgi * 16;
-        __syncwarp();                    // the store branch of the previous pass diverges; tcgen05.ld is warp-collective
-        tmem_ld16(taddr, v0);            // dx = -1 block
-        tmem_ld16(taddr + kC, v1);       // dx =  0
-        tmem_ld16(taddr + 2 * kC, v2);   // dx = +1
-        tmem_ld_wait();
-        if (sub == 1) {                  // accumulator drained by this warp: the MMA warp may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[ab]);
-        }
-        // dx-tap exchange across the lane quarters: lane 31 publishes its dx=-1 block (needed by the first row of the next
-        // quarter), lane 0 its dx=+1 block (needed by the last row of the previous quarter)
-        float* x = xch + grp * 512 + cgi * 128;
-        if (lane == 0 || lane == 31) {
-          uint4* dst = reinterpret_cast<uint4*>(x + (qw * 2 + (lane == 0 ? 1 : 0)) * 16);
+      uint32_t v[32];
+      __syncwarp();  // tcgen05.ld is warp-collective; the store branch below diverges
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + ab * kN + hf * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);  // accumulator drained: the MMA warp may overwrite it
+      const int q = t * kTileRows + r;
+      if (q >= p.NR) continue;
+      const int f = q / p.HpWp;
+      const int rem = q - f * p.HpWp;
+      const int yp = rem / p.Wp;
+      const int xp = rem - yp * p.Wp;
+      const bool interior = yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
+      uint32_t packed[16];
+      if (interior) {
+        const size_t urow = static_cast<size_t>(f * p.H + yp - 1) * p.W + (xp - 1);
+        float o[32];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 w;
-            w.x = (lane == 0) ? v2[4 * j4 + 0] : v0[4 * j4 + 0];
-            w.y = (lane == 0) ? v2[4 * j4 + 1] : v0[4 * j4 + 1];
-            w.z = (lane == 0) ? v2[4 * j4 + 2] : v0[4 * j4 + 2];
-            w.w = (lane == 0) ? v2[4 * j4 + 3] : v0[4 * j4 + 3];
-            dst[j4] = w;
+        for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + (p.shift ? __ldg(p.shift + cb32 + j) : 0.f);
+        if (p.res) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.res + urow * p.res_cs + cb32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 rv = __ldg(r4 + c);
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f2 = unpack_bf16x2(w[e]);
+              o[8 * c + 2 * e] += f2.x;
+              o[8 * c + 2 * e + 1] += f2.y;
+            }
           }
         }
-        if (grp == 0) {
-          if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
-        } else {
-          if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-          else asm volatile("bar.sync 4, 128;" ::: "memory");
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
         }
-        const bool need_up = lane == 0 && qw > 0, need_dn = lane == 31 && qw < 3;
-        float o[16];
-        {
-          const int slot = need_up ? (qw - 1) * 2 : (need_dn ? (qw + 1) * 2 + 1 : 0);
-          const float* src = x + slot * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
+        if (p.out) {  // raw block output, unpadded rows
+          uint4* dst = reinterpret_cast<uint4*>(p.out + urow * p.out_cs + cb32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        }
+        if (p.out_pad && p.act_scale) {  // the next block's activation, from the ROUNDED block output
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float up = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);      // D[r-1][j]
-            float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);    // D[r+1][128+j]
-            if (need_up) up = src[j];
-            if (need_dn) dn = src[j];
-            o[j] = up + __uint_as_float(v1[j]) + dn;
+            const float2 f2 = unpack_bf16x2(packed[j]);
+            const float a = fmaxf(fmaf(f2.x, __ldg(p.act_scale + cb32 + 2 * j), __ldg(p.act_shift + cb32 + 2 * j)), 0.f);
+            const float b = fmaxf(fmaf(f2.y, __ldg(p.act_scale + cb32 + 2 * j + 1), __ldg(p.act_shift + cb32 + 2 * j + 1)), 0.f);
+            packed[j] = pack_bf16x2(a, b);
           }
         }
-        if (!row_ok) continue;
-        uint32_t packed[8];
-        if (interior) {
-          if (p.shift) {
+      } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] += __ldg(p.shift + cbase + j);
-          }
-          if (p.res) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.res + urow * p.res_cs + cbase);
+        for (int j = 0; j < 16; ++j) packed[j] = 0u;  // border rows of the padded output stay zero
+      }
+      if (p.out_pad) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out_pad + static_cast<size_t>(q) * p.cout + cb32);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const uint4 rv = __ldg(r4 + c);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f2 = unpack_bf16x2(w[e]);
-                o[8 * c + 2 * e] += f2.x;
-                o[8 * c + 2 * e + 1] += f2.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) packed[j] = pack_bf16x2(o[2 * j], o[2 * j + 1]);
-          if (p.out) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + urow * p.out_cs + cbase);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-          }
-          if (p.out_pad && p.act_scale) {  // activated copy for the next convolution, from the ROUNDED block output
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f2 = unpack_bf16x2(packed[j]);
-              const float a = fmaxf(fmaf(f2.x, __ldg(p.act_scale + cbase + 2 * j), __ldg(p.act_shift + cbase + 2 * j)), 0.f);
-              const float b = fmaxf(fmaf(f2.y, __ldg(p.act_scale + cbase + 2 * j + 1), __ldg(p.act_shift + cbase + 2 * j + 1)), 0.f);
-              packed[j] = pack_bf16x2(a, b);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) packed[j] = 0u;  // border rows of the padded output stay zero
-        }
-        if (p.out_pad) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out_pad + static_cast<size_t>(q) * p.cout + cbase);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-        }
+        for (int c = 0; c < 4; ++c) dst[c] = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
       }
     }
   }
@@ -339,11 +301,11 @@ EncodeTiledFn get_encode() {
 }  // namespace
 
 namespace {
-constexpr int kFixedSmem = 256 + 2 * 2 * 4 * 2 * 32 * 4 + 1024;  // barriers, exchange, alignment slack
+constexpr int kFixedSmem = 256 + 1024;  // barriers, alignment slack
 }
 bool conv3x3_c64_supported(int H, int W, int C) {
   if (C != 64 && C != 128) return false;
-  const int RH = 128 + 2 * (W + 2);
+  const int RH = 128 + 2 * (W + 2) + 2;
   const int NH = C / 64;
   const size_t a_bytes = NH * align_up(static_cast<size_t>(RH) * 128, 1024);
   // one TMA box (<= 256 rows) per halo half; resident weights + at least one halo buffer must fit
@@ -356,19 +318,20 @@ bool make_conv3x3_c64(DeviceArena& arena, const float* w /* (C,C,3,3) OIHW */, i
   std::vector<uint8_t> blob(static_cast<size_t>(NS) * NH * kWBytes, 0);
   for (int ns = 0; ns < NS; ++ns)
     for (int dy = 0; dy < 3; ++dy)
-      for (int half = 0; half < NH; ++half)
-        for (int n = 0; n < kN; ++n) {
-          const int dx = n / kC, c = ns * kC + n % kC;
-          for (int kk = 0; kk < 64; ++kk) {
-            const int ci = half * 64 + kk;
-            float v = w[((static_cast<size_t>(c) * C + ci) * 3 + dy) * 3 + dx];
-            if (fold_scale) v *= fold_scale[c];
-            __nv_bfloat16 b = __float2bfloat16(v);
-            const size_t off = (static_cast<size_t>(ns) * 3 * NH + dy * NH + half) * kWBlob + n * 128 + (((kk >> 3) ^ (n & 7)) << 4) +
-                               (kk & 7) * 2;
-            memcpy(&blob[off], &b, 2);
+      for (int dx = 0; dx < 3; ++dx)
+        for (int half = 0; half < NH; ++half)
+          for (int n = 0; n < kN; ++n) {
+            const int c = ns * kC + n;
+            for (int kk = 0; kk < 64; ++kk) {
+              const int ci = half * 64 + kk;
+              float v = w[((static_cast<size_t>(c) * C + ci) * 3 + dy) * 3 + dx];
+              if (fold_scale) v *= fold_scale[c];
+              __nv_bfloat16 b = __float2bfloat16(v);
+              const size_t off = ((static_cast<size_t>(ns) * 9 + dy * 3 + dx) * NH + half) * kWBlob + n * 128 +
+                                 (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
+              memcpy(&blob[off], &b, 2);
+            }
           }
-        }
   out->wpack = static_cast<const uint8_t*>(arena.upload(blob.data(), blob.size()));
   out->C = C;
   return out->wpack != nullptr;
@@ -404,7 +367,7 @@ cudaError_t launch_conv3x3_c64(const Conv3x3C64Dev& cv, const __nv_bfloat16* in_
   const long long NR = static_cast<long long>(F) * p.HpWp;
   if (NR >= (1LL << 31) - 256) return cudaErrorInvalidValue;
   p.NR = static_cast<int>(NR);
-  p.RH = 128 + 2 * p.Wp;
+  p.RH = 128 + 2 * p.Wp + 2;
   p.a_half_bytes = static_cast<int>(align_up(static_cast<size_t>(p.RH) * 128, 1024));
   p.a_bytes = NH * p.a_half_bytes;
   p.num_tiles = static_cast<int>((NR + kTileRows - 1) / kTileRows);
