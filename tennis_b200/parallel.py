@@ -123,6 +123,7 @@ class ShardedCNNRNN(object):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._even_checked = set()
 
     def features_local(self, clips):
         B, T = clips.shape[:2]
@@ -167,6 +168,15 @@ class ShardedCNNRNN(object):
         if self.world == 1:
             D = feats.shape[1]
             return self.head(feats.reshape(B, T, D), None if twin is None else twin.reshape(B, T, D))
+        # forward() is the EVEN-shard form (every rank holds B clips); unequal shards would enter differently sized collectives and
+        # hang every rank, so the first call with a given B checks it (one 2-element all-reduce) -- ragged batches: forward_frames()
+        if B not in self._even_checked:
+            chk = torch.tensor([B, -B], dtype=torch.int64, device=clips.device)
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=self.group)
+            if int(chk[0]) != -int(chk[1]):
+                raise ValueError("ShardedCNNRNN.forward needs the same number of clips on every rank (%d here, %d..%d over the ranks); "
+                                 "use forward_frames() for ragged shards" % (B, -int(chk[1]), int(chk[0])))
+            self._even_checked.add(B)
         # the only large forward collective: per-frame features, exchanged in the dtype the head consumes
         src = twin if twin is not None else feats
         return self.head_sharded(all_gather_rows(src, self.world, self.group), B * self.world, T)
