@@ -252,7 +252,7 @@ int tn_axpy(float* y, const float* x, float a, size_t n, tn_stream_t stream);
  * `with ag.record(): out = net(x); ...; ag.backward(losses)` (train.py:415-421) through gluoncv DenseNet-121 / ResNet-18 v2:
  * training-mode BatchNorm (batch statistics, biased variance, running = momentum*running + (1-momentum)*batch)
  * fused with ReLU, convolutions as im2col + tn_sgemm, max / average pooling, each with its backward.  fp32 NHWC: a row is a
- * pixel, `ld*` is the channel count of the buffer (DenseNet's concat stays a channel offset).  First correct path (SIMT);
+ * pixel, `ld*` is the channel count of the buffer (DenseNet's concat stays a channel offset).  Memory-bound part (SIMT); the contractions are tn_gemm_tc below;
  * sequenced by tennis_b200/models/vision/train_graph.py. */
 /* Tensor-core contractions of the same training path (csrc/tn_gemm_tc.cu): the convolutions' forward, data-gradient and
  * weight-gradient GEMMs (train.py:415-421, MXNet Convolution forward/backward in fp32) on tcgen05.

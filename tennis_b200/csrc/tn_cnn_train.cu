@@ -3,9 +3,10 @@
 // BatchNorm with batch statistics (biased variance, running = 0.9 running + 0.1 batch) fused with ReLU, its backward, im2col /
 // col2im around the shared fp32 SGEMM for the convolutions, max / average pooling with their backwards.
 //
-// This is the FIRST CORRECT path of the CNN backward, not the fast one: fp32 NHWC activations (row = pixel, row stride = channel
-// count of the buffer, so DenseNet's concat stays a channel offset), SIMT kernels, convolutions as explicit im2col GEMMs.  The
-// inference path (tn_backbone.cu: bf16, tcgen05) is untouched.  Parity bar: gradients vs torch.autograd of the fp32 oracle.
+// fp32 NHWC activations (row = pixel, row stride = channel count of the buffer, so DenseNet's concat stays a channel offset).  The
+// contractions run on the tensor cores (tn_gemm_tc.cu); this file holds the memory-bound rest: BatchNorm statistics / apply / backward
+// (row-split reductions with a deterministic second stage), im2col / col2im for the strided and 7x7 convolutions, pooling.  The
+// inference path (tn_backbone.cu: bf16, tcgen05) is untouched.  Parity bar: gradients vs torch.autograd of the fp64 oracle.
 #include <math.h>
 
 #include "tn_common.h"

@@ -2,10 +2,13 @@
 with saved activations, and the backward pass, for the two backbones of the scripts (reference train.py:204 -> gluoncv
 DenseNet-121 / ResNet-18 v2 `features`).
 
-FIRST CORRECT PATH, not the fast one: fp32 NHWC activations, convolutions as im2col + the shared SGEMM, SIMT BatchNorm / pooling
-kernels (csrc/tn_cnn_train.cu, tn_seq_train.cu).  Python only sequences C-ABI calls; torch tensors are containers (allocation,
-views, layout permutes).  The inference path (bf16 tcgen05 kernels) is untouched.  Gradients are checked against
-torch.autograd of the fp32 oracle in tests/test_gpu_cnn_train.py.
+fp32 NHWC activations (a dense block is one buffer; layers read channel prefixes and write channel slices through row strides),
+SIMT BatchNorm / pooling kernels (csrc/tn_cnn_train.cu) and the convolutions' forward / data-gradient / weight-gradient
+contractions on the tensor cores (csrc/tn_gemm_tc.cu through tennis_b200/tcgemm.py): split-bf16 operand planes, three tcgen05
+products per contraction ($TN_TRAIN_GEMM = x3, the default; bf16 = one product; fp32 = the SIMT SGEMM of round 1, the parity
+anchor).  3x3 / stride-1 convolutions never form an im2col matrix: a tap is a row shift in zero-padded row space.  Python only
+sequences C-ABI calls; torch tensors are containers (allocation, views, layout permutes).  The inference path (bf16 tcgen05
+kernels) is untouched.  Gradients are checked against torch.autograd of the fp64 oracle in tests/test_gpu_cnn_train.py.
 """
 import torch
 
