@@ -251,15 +251,16 @@ int tn_axpy(float* y, const float* x, float a, size_t n, tn_stream_t stream);
 /* ------------------------------------------------------------------ CNN training (V7 with a trainable backbone)
  * `with ag.record(): out = net(x); ...; ag.backward(losses)` (train.py:415-421) through gluoncv DenseNet-121 / ResNet-18 v2:
  * training-mode BatchNorm (batch statistics, biased variance, running = momentum*running + (1-momentum)*batch)
- * fused with ReLU, convolutions as im2col + tn_sgemm, max / average pooling, each with its backward.  fp32 NHWC: a row is a
- * pixel, `ld*` is the channel count of the buffer (DenseNet's concat stays a channel offset).  Memory-bound part (SIMT); the contractions are tn_gemm_tc below;
- * sequenced by tennis_b200/models/vision/train_graph.py. */
+ * fused with ReLU, im2col / col2im for the strided and 7x7 convolutions, max / average pooling, each with its backward.  fp32
+ * NHWC: a row is a pixel, `ld*` is the channel count of the buffer (DenseNet's concat stays a channel offset).  These are the
+ * memory-bound kernels (SIMT); the contractions are tn_gemm_tc below (tn_sgemm in the fp32 anchor mode); sequenced by
+ * tennis_b200/models/vision/train_graph.py. */
 /* Tensor-core contractions of the same training path (csrc/tn_gemm_tc.cu): the convolutions' forward, data-gradient and
  * weight-gradient GEMMs (train.py:415-421, MXNet Convolution forward/backward in fp32) on tcgen05.
  * tn_split_bf16: fp32 matrix (rows x cols, row stride ld) -> bf16 planes hi (+ lo, NULL = plain bf16) with x = hi + lo;
  *   transpose = 0: plane[orow(r)][c], 1: plane[c][orow(r)]; pad_h/pad_w > 0: r = (n,y,x) over pad_h x pad_w frames is re-indexed
- *   to (n,y+1,x+1) of the zero-padded grid of (pad_h+2) rows of pad_pitch (0 = pad_w+2) pixels (the caller zero-fills the planes
- *   once); shift in {-1,0,1}: transposed padded planes only, every pixel lands `shift` positions later; out_ld % 8 == 0.
+ *   to (n,y+1,x+1) of the zero-padded grid of (pad_h+2) rows of pad_pitch (0 = pad_w+2) pixels (the border zeros are written by
+ *   the same pass); shift in {-1,0,1}: transposed padded planes only, every pixel lands `shift` positions later; out_ld % 8 == 0.
  * tn_gemm_tc: D[m,n] = sum_t sum_k A[m + taps[4t], taps[4t+1] + k] * B[n + taps[4t+2], taps[4t+3] + k], k < K, taps on the HOST
  *   (NULL = one tap, no offsets; out-of-range reads are zeros; contraction offsets must be multiples of 8), passes = 3: hi*hi + hi*lo + lo*hi (fp32-grade), 1: hi*hi;
  *   C[orow(m)*c_row_stride + n*c_col_stride] = alpha*D + beta*C, unpad_h/w > 0: m runs over the padded grid, border rows are
