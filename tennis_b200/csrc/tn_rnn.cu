@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanPara
   constexpr int H = 128, G = 3, NJ = G * H, GH = G * H;
   __shared__ __align__(16) float hbuf[2][kRB][H];
   __shared__ __align__(16) float hh[2][kRB][NJ];  // partial sums of the two k halves
+  __shared__ float gxs[2][G][kRB * H];            // projected gates of the current / next step, one item per thread
   const int tid = threadIdx.x;
   const int kh = tid >= NJ ? 1 : 0;  // which half of k (warp-uniform: 384 = 12 warps)
   const int j = tid - kh * NJ;       // gate column (g, u)
@@ -301,23 +302,25 @@ __global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanPara
   for (int b = 0; b < kRB; ++b)
     if (b0 + b < p.B) maxlen = max(maxlen, p.valid_len ? min(max(p.valid_len[b0 + b], 0), p.T) : p.T);
   const int gx_row = p.ndir * GH;
-  auto load_gx = [&](int s, float (&dst)[G]) {
-    dst[0] = dst[1] = dst[2] = 0.f;
+  // The projected gates of step s+1 are fetched with cp.async straight into shared memory while step s computes: no registers
+  // are held across the step (ptxas spilled the prefetched values of the register version to local memory, which made every step
+  // wait for the global load it was meant to hide -- STL at 7 % of the samples in profiles/r2_summary.md section 5).
+  auto prefetch_gx = [&](int s) {
     if (has_item && s < ilen) {
       const int pos = (dir == 0 || p.reverse_dir1 == 0) ? s : ilen - 1 - s;
       const float* gp = p.gx + (static_cast<size_t>(b0 + ib) * p.T + pos) * gx_row + dir * GH + iu;
 #pragma unroll
-      for (int g = 0; g < G; ++g) dst[g] = __ldg(gp + g * H);
+      for (int g = 0; g < G; ++g)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&gxs[s & 1][g][tid]))), "l"(gp + g * H) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  float gxv[G];
-  load_gx(0, gxv);
+  prefetch_gx(0);
   __syncthreads();
 
   for (int s = 0; s < maxlen; ++s) {
     const float* hcur = &hbuf[s & 1][0][0] + kh * kKS;
-    float gxn[G];
-    load_gx(s + 1, gxn);  // next step's gates: their L2/HBM latency hides behind this step
+    prefetch_gx(s + 1);  // next step's gates: their L2/HBM latency hides behind this step
     float part[kRB];
 #pragma unroll
     for (int bp = 0; bp < kRB; bp += 2) {
@@ -348,11 +351,13 @@ __global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanPara
     for (int b = 0; b < kRB; ++b) hh[kh][b][j] = part[b] + bhh;
     __syncthreads();
 
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this step's gates have landed (only the group of step s+1 may be pending)
     float hnew = ih;
     if (has_item && s < ilen) {
-      const float r = sigmoidf_(gxv[0] + (hh[0][ib][iu] + hh[1][ib][iu]));
-      const float z = sigmoidf_(gxv[1] + (hh[0][ib][H + iu] + hh[1][ib][H + iu]));
-      const float nn = tanhf(gxv[2] + r * (hh[0][ib][2 * H + iu] + hh[1][ib][2 * H + iu]));
+      const float gx0 = gxs[s & 1][0][tid], gx1 = gxs[s & 1][1][tid], gx2 = gxs[s & 1][2][tid];
+      const float r = sigmoidf_(gx0 + (hh[0][ib][iu] + hh[1][ib][iu]));
+      const float z = sigmoidf_(gx1 + (hh[0][ib][H + iu] + hh[1][ib][H + iu]));
+      const float nn = tanhf(gx2 + r * (hh[0][ib][2 * H + iu] + hh[1][ib][2 * H + iu]));
       hnew = (1.f - z) * nn + z * ih;
       ih = hnew;
       imax = fmaxf(imax, hnew);
@@ -362,10 +367,9 @@ __global__ void __launch_bounds__(768, 1) gru_scan_h128_kernel(const RnnScanPara
       }
     }
     if (tid < kRB * H) hbuf[(s + 1) & 1][ib][iu] = hnew;  // frozen rows re-publish their last state
-#pragma unroll
-    for (int g = 0; g < G; ++g) gxv[g] = gxn[g];
     __syncthreads();
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (has_item) {
     const size_t o = static_cast<size_t>(b0 + ib) * (p.ndir * H) + dir * H + iu;
     if (p.ymax) p.ymax[o] = imax;
