@@ -334,3 +334,50 @@ def test_gluoncv_structural_names_cover_the_inventory_and_load(arch, first_bn, t
         got = model.collect_params()
         for k in ("conv0.weight", ours[5], ours[-1]):
             assert torch.equal(got[prefix + k].data(), p[k]), (prefix, k)
+
+
+_GLOO_MISMATCH_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from tennis_b200.gluon import Parameter, Trainer
+from tennis_b200.parallel import ShardedCNNRNN
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# (1) rank 1 has not materialised its second parameter (deferred shape): Trainer.step must fail on EVERY rank instead of hanging
+a, b = Parameter("a", shape=(3,)), Parameter("b", shape=(2,))
+a._data = torch.zeros(3)
+if rank == 0:
+    b._data = torch.zeros(2)
+tr = Trainer({"a": a, "b": b}, "sgd", {"learning_rate": 0.1})
+try:
+    tr.step(1)
+    raise SystemExit("rank %%d: no error" %% rank)
+except RuntimeError as e:
+    assert "different parameter sets" in str(e), e
+# (2) ShardedCNNRNN.forward is the even-shard form: unequal clip counts are refused on every rank
+class _M(object):
+    class td(object):
+        @staticmethod
+        def model(x):
+            return x.reshape(x.shape[0], -1)[:, :4].float()
+sh = ShardedCNNRNN(_M())
+try:
+    sh(torch.zeros(2 + rank, 3, 1, 2, 2))
+    raise SystemExit("rank %%d: no error" %% rank)
+except ValueError as e:
+    assert "same number of clips" in str(e), e
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_mismatched_ranks_fail_loudly_instead_of_hanging_gloo(tmp_path):
+    """Two ways a multi-GPU run used to hang in a mismatched collective (profiles: 22 GPU-minutes lost to the first one): a rank
+    whose deferred-shape parameters do not exist yet entering Trainer.step, and unequal clip shards through the even-shard forward."""
+    script = tmp_path / "m.py"
+    script.write_text(_GLOO_MISMATCH_WORKER % ROOT)
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_PORT="29617", MASTER_ADDR="127.0.0.1")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
