@@ -107,8 +107,6 @@ class CNNTrainGraph(object):
         # 3x3 / stride 1 / pad 1 on the tensor cores: a tap is a row shift in the zero-padded row space, no im2col matrix
         shifted = gm != "fp32" and R == 3 and S == 3 and stride == 1 and pad == 1 and Cin % 8 == 0 and Cout % 8 == 0
         if shifted:
-            Wq = W + 2
-            offs = [(r - 1) * Wq + (s - 1) for r in range(3) for s in range(3)]
             Mp = tcgemm.padded_rows(N, H, W)
 
         def columns():
@@ -121,8 +119,7 @@ class CNNTrainGraph(object):
         if shifted:
             xp = tcgemm.planes(x2, pad_hw=(H, W), lo=lo)
             wp = tcgemm.planes(wk, lo=lo)
-            tcgemm.gemm(xp, wp, Mp, Cout, Cin, y2, Cd, taps=[(offs[t], 0, 0, t * Cin) for t in range(9)], unpad_hw=(H, W),
-                        passes=passes)
+            tcgemm.gemm(xp, wp, Mp, Cout, Cin, y2, Cd, taps=tcgemm.taps_conv3x3_forward(W, Cin), unpad_hw=(H, W), passes=passes)
             del xp, wp
         elif gm != "fp32":
             tcgemm.matmul(columns(), wk, y2, tb=True, passes=passes)
@@ -146,8 +143,8 @@ class CNNTrainGraph(object):
                         tcgemm.planes(dy2, transpose=True, pad_hw=(H, W), lo=lo, pitch=P8, shift=dx, into=dyT, row0=(dx + 1) * Cout)
                     dwk = torch.empty(Cout, K, device=dev)
                     # tap t = (dy, dx): B rows (dx+1)*Cout.., contraction offset -dy*P8; D_t[c, n] -> dwk[n, t*Cin + c]
-                    tcgemm.gemm(xT, dyT, Cin, Cout, Mp8, dwk, 1, K, taps=[(0, 0, (t % 3) * Cout, -(t // 3 - 1) * P8) for t in range(9)],
-                                passes=passes, tile_taps=True, c_tap_stride=Cin)
+                    tcgemm.gemm(xT, dyT, Cin, Cout, Mp8, dwk, 1, K, taps=tcgemm.taps_conv3x3_wgrad(W, Cout), passes=passes,
+                                tile_taps=True, c_tap_stride=Cin)
                     del xT, dyT
                     Wp._accumulate_grad(dwk.reshape(Cout, R, S, Cin).permute(0, 3, 1, 2).contiguous())
                 if src.needs_grad:
@@ -155,7 +152,7 @@ class CNNTrainGraph(object):
                     dyp = tcgemm.planes(dy2, pad_hw=(H, W), lo=lo)                      # (Mp, Cout)
                     wT = tcgemm.planes(w.permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).contiguous(), lo=lo)  # (Cin, (t, n))
                     tcgemm.gemm(dyp, wT, Mp, Cin, Cout, src.g().reshape(-1, Ct)[:, c0:c0 + Cin], Ct,
-                                taps=[(-offs[t], 0, 0, t * Cout) for t in range(9)], beta=1.0, unpad_hw=(H, W), passes=passes)
+                                taps=tcgemm.taps_conv3x3_dgrad(W, Cout), beta=1.0, unpad_hw=(H, W), passes=passes)
                 return
             mm = sgemm if gm == "fp32" else (lambda A, B, C, **kw: tcgemm.matmul(A, B, C, passes=passes, **kw))
             col = columns()  # recomputed: keeping every im2col matrix would dominate the memory

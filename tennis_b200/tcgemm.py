@@ -43,6 +43,31 @@ def pitch8(w):
     return _r8(w + 2)
 
 
+# ---- tap lists of a 3x3 / stride 1 / pad 1 convolution in zero-padded row space (consumed by `gemm`; the index algebra is
+# checked on the CPU against torch.conv2d and its autograd in tests/test_host_cpu.py::test_tap_lists_reproduce_conv3x3)
+def conv3x3_offsets(w):
+    """Row shift of tap t = 3*r + s in the padded grid of pitch w + 2."""
+    return [(r - 1) * (w + 2) + (s - 1) for r in range(3) for s in range(3)]
+
+
+def taps_conv3x3_forward(w, cin):
+    """Y[m, n] = sum_t sum_c X[m + off_t, c] * Wk[n, t*cin + c]   (A = padded X planes, B = weights (Cout, 9*cin))."""
+    return [(o, 0, 0, t * cin) for t, o in enumerate(conv3x3_offsets(w))]
+
+
+def taps_conv3x3_dgrad(w, cout):
+    """dX[m, c] = sum_t sum_n dY[m - off_t, n] * Wt[c, t*cout + n]   (A = padded dY planes, B = (Cin, 9*cout))."""
+    return [(-o, 0, 0, t * cout) for t, o in enumerate(conv3x3_offsets(w))]
+
+
+def taps_conv3x3_wgrad(w, cout):
+    """Nine independent products (tile_taps): D_t[c, n] = sum_j X^T[c, j] * dYs_dx^T[n, j - dy*P8] with t = (dy+1)*3 + (dx+1),
+    A = X^T over the padded pixels at pitch P8 = pitch8(w), B = the three dx-shifted copies of dY^T stacked by rows ((dx+1)*cout + n):
+    the dx shift lives in the copy (`planes(..., shift=dx)`), the dy shift is the 16-byte aligned contraction offset -dy*P8."""
+    p8 = pitch8(w)
+    return [(0, 0, (t % 3) * cout, -(t // 3 - 1) * p8) for t in range(9)]
+
+
 def planes(src, transpose=False, pad_hw=None, lo=True, pitch=None, shift=0, into=None, row0=0):
     """src: 2-D fp32 view (rows, cols) with unit column stride.  transpose=False: the contraction runs along the columns;
     True: along the rows.  pad_hw=(H, W): rows are (n, y, x) pixels, re-indexed into the zero-padded grid of (H+2) rows of `pitch`

@@ -381,3 +381,77 @@ def test_mismatched_ranks_fail_loudly_instead_of_hanging_gloo(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def _emu_planes(src, transpose=False, pad_hw=None, pitch=None, shift=0):
+    """fp64 emulation of tn_split_bf16's INDEXING (include/tennis_b200.h): rows (n,y,x) -> (n,y+1,x+1) of the zero-padded grid of
+    (h+2) rows of `pitch` pixels, optional transpose, every pixel `shift` positions later."""
+    R, C = src.shape
+    if pad_hw is None:
+        out = src.clone()
+    else:
+        h, w = pad_hw
+        pitch = pitch or (w + 2)
+        n = R // (h * w)
+        out = torch.zeros(n * (h + 2) * pitch, C, dtype=src.dtype)
+        r = torch.arange(R)
+        x, y, f = r % w, (r // w) % h, r // (w * h)
+        out[(f * (h + 2) + y + 1) * pitch + x + 1 + shift] = src
+    return out.t().contiguous() if transpose else out
+
+
+def _emu_gemm(A, B, M, N, K, taps, tile_taps=False):
+    """fp64 emulation of tn_gemm_tc: D[m, n] = sum_t sum_{k<K} A[m + ar, ak + k] * B[n + br, bk + k], reads outside a matrix are
+    zeros; tile_taps: one (M, N) product per tap."""
+    def win(X, r0, nr, k0):
+        out = torch.zeros(nr, K, dtype=X.dtype)
+        rows = torch.arange(r0, r0 + nr)
+        cols = torch.arange(k0, k0 + K)
+        rv = (rows >= 0) & (rows < X.shape[0])
+        cv = (cols >= 0) & (cols < X.shape[1])
+        if rv.any() and cv.any():
+            out[rv.nonzero()[:, 0][:, None], cv.nonzero()[:, 0][None, :]] = X[rows[rv]][:, cols[cv]]
+        return out
+    outs = [win(A, ar, M, ak) @ win(B, br, N, bk).t() for ar, ak, br, bk in taps]
+    return outs if tile_taps else sum(outs)
+
+
+def _unpad(D, n, h, w):
+    return D.reshape(n, h + 2, w + 2, -1)[:, 1:h + 1, 1:w + 1].reshape(n * h * w, -1)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 5, 6, 8, 16), (1, 7, 7, 16, 8), (3, 4, 9, 8, 8)])
+def test_tap_lists_reproduce_conv3x3(n, h, w, cin, cout):
+    """The tap lists the training graph hands to tn_gemm_tc (tcgemm.taps_conv3x3_*), run through an fp64 emulation of the
+    documented tn_split_bf16 / tn_gemm_tc index semantics, reproduce torch's 3x3 / stride 1 / pad 1 convolution, its data gradient
+    and its weight gradient -- including the 8-pixel row pitch and the three dx-shifted copies of the weight-gradient operand."""
+    import torch.nn.functional as F
+    from tennis_b200 import tcgemm
+    g = torch.Generator().manual_seed(n * 100 + h)
+    x = torch.randn(n, cin, h, w, generator=g, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(n, cout, h, w, generator=g, dtype=torch.float64)
+    y = F.conv2d(x, wt, padding=1)
+    (y * dy).sum().backward()
+    x2 = x.detach().permute(0, 2, 3, 1).reshape(-1, cin)          # NHWC rows
+    dy2 = dy.permute(0, 2, 3, 1).reshape(-1, cout)
+    wk = wt.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)    # (Cout, (r,s,c))
+    Mp = tcgemm.padded_rows(n, h, w)
+    # forward
+    Y = _emu_gemm(_emu_planes(x2, pad_hw=(h, w)), wk, Mp, cout, cin, tcgemm.taps_conv3x3_forward(w, cin))
+    assert torch.allclose(_unpad(Y, n, h, w), y.detach().permute(0, 2, 3, 1).reshape(-1, cout), atol=1e-10)
+    # data gradient
+    wT = wt.detach().permute(1, 2, 3, 0).reshape(cin, 9 * cout)    # (Cin, (t, n))
+    DX = _emu_gemm(_emu_planes(dy2, pad_hw=(h, w)), wT, Mp, cin, cout, tcgemm.taps_conv3x3_dgrad(w, cout))
+    assert torch.allclose(_unpad(DX, n, h, w), x.grad.permute(0, 2, 3, 1).reshape(-1, cin), atol=1e-10)
+    # weight gradient: contraction over the padded pixels at pitch P8, dx baked into three copies of dY^T
+    P8 = tcgemm.pitch8(w)
+    assert P8 % 8 == 0 and P8 >= w + 2
+    Mp8 = tcgemm.padded_rows(n, h, w, P8)
+    xT = _emu_planes(x2, transpose=True, pad_hw=(h, w), pitch=P8)
+    dyT = torch.cat([_emu_planes(dy2, transpose=True, pad_hw=(h, w), pitch=P8, shift=dx) for dx in (-1, 0, 1)], 0)
+    taps = tcgemm.taps_conv3x3_wgrad(w, cout)
+    assert all(t[1] % 8 == 0 and t[3] % 8 == 0 for t in taps)      # TMA: 16-byte aligned contraction coordinates
+    Dt = _emu_gemm(xT, dyT, cin, cout, Mp8, taps, tile_taps=True)   # nine (Cin, Cout) products
+    dwk = torch.stack([d.t() for d in Dt], 1).reshape(cout, 9 * cin)  # dwk[n, t*Cin + c] = D_t[c, n]
+    assert torch.allclose(dwk.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2), wt.grad, atol=1e-9)
