@@ -409,6 +409,10 @@ def run_ours(args, rank, world, local_rank):
                        "precision": "value/e2e: bf16 operands + fp32 accumulation (stated tolerance: logits within 2e-2 x max|logit| "
                                     "of the fp32 reference arithmetic); the fp32-grade mode (<= 1e-3) is the `precise` object",
                        "l2": "inputs %.2f GB per GPU per step > 126 MB L2, no flush needed" % (h2d / 1e9),
+                       "input_formats": "`value`: normalised fp32 NCHW clips resident in HBM (the reference's tensor format, 1.23 GB per "
+                                        "step through the input-conversion kernel); `e2e`: uint8 NHWC frames from pinned host memory "
+                                        "(0.31 GB per step, normalised on the device) -- the cheaper conversion is why `e2e` can "
+                                        "come within 1-2 % of `value` or pass it; `e2e_f32_host` is the fp32 host format",
                        "outputs_finite": finite, "numa_node_of_rank0": numa_node},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic_step,
