@@ -455,3 +455,48 @@ def test_tap_lists_reproduce_conv3x3(n, h, w, cin, cout):
     Dt = _emu_gemm(xT, dyT, cin, cout, Mp8, taps, tile_taps=True)   # nine (Cin, Cout) products
     dwk = torch.stack([d.t() for d in Dt], 1).reshape(cout, 9 * cin)  # dwk[n, t*Cin + c] = D_t[c, n]
     assert torch.allclose(dwk.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2), wt.grad, atol=1e-9)
+
+
+def test_num_gpus_relaunch_command(monkeypatch):
+    """`python train.py --num_gpus 4 ...` (reference train.py:103: a context per GPU) re-executes the SAME command line under
+    torch.distributed.run with one process per GPU on the loopback address; a process already under torchrun does not relaunch."""
+    from tennis_b200 import cli
+    seen = {}
+
+    def fake_call(cmd):
+        seen["cmd"] = cmd
+        return 7
+    monkeypatch.setattr("subprocess.call", fake_call)
+    monkeypatch.setattr(sys, "argv", ["train.py", "--num_gpus", "4", "--synthetic"])
+    assert cli._relaunch_under_torchrun(4) == 7       # the child's exit code is passed on
+    cmd = seen["cmd"]
+    assert cmd[0] == sys.executable and cmd[1:3] == ["-m", "torch.distributed.run"]
+    assert "--nnodes=1" in cmd and cmd[cmd.index("--nproc-per-node") + 1] == "4"
+    assert cmd[cmd.index("--master-addr") + 1] == "127.0.0.1" and int(cmd[cmd.index("--master-port") + 1]) > 0
+    assert cmd[-4:] == ["train.py", "--num_gpus", "4", "--synthetic"]
+
+
+def test_device_metric_state_round_trip():
+    """The accumulator layout that metrics are summed in across ranks (cli.sync_metrics): state_tensor / load_state_tensor of the
+    host metrics is lossless and additive -- two ranks that each saw a part of the samples sum to the single-process metric."""
+    import numpy as np
+    from tennis_b200.metrics.vision import PRF1, Accuracy
+    names = ["OTH", "SFI", "SFF", "HFR", "HNR"]
+    rng = np.random.RandomState(0)
+    labels = rng.randint(0, 5, size=40)
+    preds = rng.rand(40, 5)
+    full_a, full_p = Accuracy(), PRF1(label_names=names)
+    full_a.update([labels], [preds])
+    full_p.update([labels], [preds])
+    sa = sp = None
+    for lo, hi in ((0, 13), (13, 40)):
+        a, p = Accuracy(), PRF1(label_names=names)
+        a.update([labels[lo:hi]], [preds[lo:hi]])
+        p.update([labels[lo:hi]], [preds[lo:hi]])
+        sa = a.state_tensor() if sa is None else sa + a.state_tensor()
+        sp = p.state_tensor() if sp is None else sp + p.state_tensor()
+    a2, p2 = Accuracy(), PRF1(label_names=names)
+    a2.load_state_tensor(sa)
+    p2.load_state_tensor(sp)
+    assert a2.get() == full_a.get()
+    assert p2.get() == full_p.get() and np.array_equal(p2.mat, full_p.mat)
