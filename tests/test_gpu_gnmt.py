@@ -259,3 +259,25 @@ def test_beam_search_forced_ties_lowest_index_wins():
     assert (s_ref[:, 0, 1] == 10).all(), s_ref[:, 0, :4]
     assert ((s_ref == 11).sum() > 0) and ((s_ref == 10).sum() >= (s_ref == 11).sum())
     assert (sc.cpu() - sc_ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("cell", ["lstm", "gru"])
+def test_teacher_forced_logits_match_committed_golden(cell):
+    """The CUDA path against the COMMITTED vectors (tests/golden/captioning_oracle.npz, made by tools/make_golden_captioning.py
+    from the oracle): teacher-forced logits within 1e-3, masked-CE loss within 1e-3."""
+    import os
+    import numpy as np
+    from oracle import captioning as C
+    from tennis_b200.gluon import MaskedSoftmaxCELoss
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "captioning_oracle.npz"))
+    model, p, _ = _build(cell, 32, 48, 20, 37, 0.3)
+    x, vl = C.synthetic_sources(4, 9, 48, seed=3)
+    tgt = torch.randint(0, 37, (4, 7), generator=torch.Generator().manual_seed(5)).float()
+    tvl = torch.tensor([7., 6., 4., 2.])
+    out, _ = model(x.cuda(), tgt[:, :-1].cuda(), vl.cuda(), tvl.cuda() - 1)
+    ref = torch.from_numpy(gold[cell + "_logits"])
+    T = ref.shape[1]
+    mask = (torch.arange(T)[None, :] < (tvl - 1)[:, None])  # positions past the target length are undefined in both
+    assert ((out.cpu() - ref).abs() * mask[:, :, None]).max().item() < 1e-3
+    loss = MaskedSoftmaxCELoss()(out, tgt[:, 1:].cuda(), tvl.cuda() - 1)
+    assert (loss.cpu() - torch.from_numpy(gold[cell + "_loss"])).abs().max().item() < 1e-3

@@ -248,3 +248,21 @@ def test_beam_search_oracle_invariants_and_scorer_values():
         n = int(v1[b, 0])
         m = min(n, g.shape[1])
         assert torch.equal(s1[b, 0, :m].float(), g[b, :m]), (s1[b, 0], g[b])
+
+
+def test_captioning_oracle_reproduces_golden_fixtures():
+    """tests/golden/captioning_oracle.npz (tools/make_golden_captioning.py): teacher-forced logits, masked-CE loss and the beam
+    search (token ids, valid lengths bit-exact; scores 1e-5) of seeded LSTM / GRU captioners."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_captioning", os.path.join(os.path.dirname(__file__), "..", "tools",
+                                                                                          "make_golden_captioning.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "captioning_oracle.npz"))
+    for cell in ("lstm", "gru"):
+        got = mod.compute(cell)
+        assert np.abs(got["logits"] - gold[cell + "_logits"]).max() < 1e-5
+        assert np.abs(got["loss"] - gold[cell + "_loss"]).max() < 1e-5
+        assert np.array_equal(got["samples"], gold[cell + "_samples"])
+        assert np.array_equal(got["valid_length"], gold[cell + "_valid_length"])
+        assert np.abs(got["scores"] - gold[cell + "_scores"]).max() < 1e-5
