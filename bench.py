@@ -724,12 +724,19 @@ def bench_train_step_trainable(model, clips_dev, device, world, barrier, clips_p
         for prm, g in zip(backbone_params, saved):
             prm.grad_req = g
     frames = per * world * T
+    peaks, _ = measured_peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    algo_tflops = 3.0 * FLOP_PER_FRAME * per * T / (ms * 1e-3) / 1e12  # forward + dgrad + wgrad, per GPU
     return {"workload": "CNN+GRU training step (fwd+bwd+SGD) with a TRAINABLE DenseNet-121, %d clips x %d frames per GPU, "
                         "NCCL all-reduce of every gradient" % (per, T),
             "ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "clips_per_s": per * world / (ms * 1e-3), "scaling": "weak",
             "gemm": "TN_TRAIN_GEMM=%s (x3: split-bf16, three tcgen05 products per contraction)" % tcgemm.mode(),
             "tensor_core_gemm_ms_per_step": prof["conv_ms"] / steps, "tensor_core_gemm_launches_per_step": prof["conv_launches"] // steps,
             "other_kernels_ms_per_step": prof["other_ms"] / steps,
+            "roofline": {"bound": "tensor", "algorithmic": "3 x 5.666 GFLOP/frame (forward, data gradient, weight gradient)",
+                         "achieved": algo_tflops, "peak": peak, "unit": "TFLOP/s", "frac": algo_tflops / peak,
+                         "note": "whole step incl. BatchNorm, operand splits, BPTT and SGD; fp32 activations bound the batch at 8 "
+                                 "clips x 32 frames per GPU (34 GB), 64 x 32 clips do not fit"},
             "round1_simt_fp32_path": "954 ms per 64 frames = 67 frames/s on the same GPU type (profiles/r2_cnn_train.md)",
             "loss_finite": lv == lv}
 
