@@ -86,3 +86,36 @@ def test_fixed_bucket_sampler_reshuffles_inside_buckets_every_epoch():
         assert len({min((keys[i] - lo) // width, 3) for i in b}) == 1
     s0 = FixedBucketSampler(lengths, batch_size=16, num_buckets=4, shuffle=False)
     assert [list(b) for b in s0] == [list(b) for b in s0]
+
+
+@settings(max_examples=40, deadline=None)
+@given(n=st.integers(1, 3), h=st.integers(1, 9), w=st.integers(1, 14), cin=st.sampled_from([8, 16]), cout=st.sampled_from([8, 24]),
+       seed=st.integers(0, 10 ** 6))
+def test_conv3x3_tap_lists_for_any_geometry(n, h, w, cin, cout, seed):
+    """tcgemm.taps_conv3x3_* (forward, data gradient, weight gradient with the 8-pixel pitch and dx-shifted copies) reproduce
+    torch's conv2d and its autograd for arbitrary frame counts and map sizes, including 1-pixel maps and widths whose padded pitch
+    is already a multiple of 8 (fp64 emulation of the documented tn_split_bf16 / tn_gemm_tc index semantics)."""
+    import torch.nn.functional as F
+    from test_host_cpu import _emu_gemm, _emu_planes, _unpad
+    from tennis_b200 import tcgemm
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(n, cout, h, w, generator=g, dtype=torch.float64)
+    y = F.conv2d(x, wt, padding=1)
+    (y * dy).sum().backward()
+    x2 = x.detach().permute(0, 2, 3, 1).reshape(-1, cin)
+    dy2 = dy.permute(0, 2, 3, 1).reshape(-1, cout)
+    Mp = tcgemm.padded_rows(n, h, w)
+    Y = _emu_gemm(_emu_planes(x2, pad_hw=(h, w)), wt.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin), Mp, cout, cin,
+                  tcgemm.taps_conv3x3_forward(w, cin))
+    assert torch.allclose(_unpad(Y, n, h, w), y.detach().permute(0, 2, 3, 1).reshape(-1, cout), atol=1e-9)
+    DX = _emu_gemm(_emu_planes(dy2, pad_hw=(h, w)), wt.detach().permute(1, 2, 3, 0).reshape(cin, 9 * cout), Mp, cin, cout,
+                   tcgemm.taps_conv3x3_dgrad(w, cout))
+    assert torch.allclose(_unpad(DX, n, h, w), x.grad.permute(0, 2, 3, 1).reshape(-1, cin), atol=1e-9)
+    P8 = tcgemm.pitch8(w)
+    xT = _emu_planes(x2, transpose=True, pad_hw=(h, w), pitch=P8)
+    dyT = torch.cat([_emu_planes(dy2, transpose=True, pad_hw=(h, w), pitch=P8, shift=dx) for dx in (-1, 0, 1)], 0)
+    Dt = _emu_gemm(xT, dyT, cin, cout, tcgemm.padded_rows(n, h, w, P8), tcgemm.taps_conv3x3_wgrad(w, cout), tile_taps=True)
+    dwk = torch.stack([d.t() for d in Dt], 1).reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    assert torch.allclose(dwk, wt.grad, atol=1e-8)
