@@ -500,3 +500,23 @@ def test_device_metric_state_round_trip():
     p2.load_state_tensor(sp)
     assert a2.get() == full_a.get()
     assert p2.get() == full_p.get() and np.array_equal(p2.mat, full_p.mat)
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line on stdout with the contract keys, the CPU
+    oracle port as `cpu_baseline.kind = port`, zero host<->device bytes, and the same metric / unit as the GPU arm."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"].startswith("frames/sec") and d["unit"] == "frames/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
